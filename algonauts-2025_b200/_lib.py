@@ -1,0 +1,148 @@
+"""Loader / builder for ``libtribe_b200.so`` (the C ABI declared in ``include/tribe_b200.h``).
+
+The library is built IN-TREE with nvcc for sm_100a (``csrc/libtribe_b200.so``) so that it travels with the repo
+snapshot to the GPU box.  There is no CPU fallback: if the library cannot be loaded every op raises.
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import ctypes
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+LIB_PATH = os.path.join(CSRC, "libtribe_b200.so")
+SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              f"-I{INCLUDE}", f"-I{CSRC}"]
+
+_lib = None
+
+
+class TribeError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise TribeError("nvcc not found: cannot build libtribe_b200.so")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(INCLUDE, "tribe_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a and link ``libtribe_b200.so`` (no GPU needed: nvcc cross-compiles)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise TribeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose and (r.stdout or r.stderr):
+            print(r.stdout, r.stderr)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIB_PATH + ".tmp"
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise TribeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class TribeOperand(ctypes.Structure):
+    _fields_ = [("ptr", c_vp), ("inner", c_i64), ("rows", c_i64), ("batch", c_i64), ("row_stride", c_i64),
+                ("batch_stride", c_i64), ("mn_major", c_i32), ("inner_off", c_i32), ("zin_stride", c_i32),
+                ("zdiv", c_i32), ("gather", c_vp)]
+
+
+class TribeGemm(ctypes.Structure):
+    _fields_ = [("a", TribeOperand), ("b", TribeOperand), ("m", c_i32), ("n", c_i32), ("k", c_i32), ("batch", c_i32),
+                ("z_inner", c_i32), ("kgroup", c_vp), ("kgroup_len", c_i32), ("d", c_vp), ("d_f32", c_i32),
+                ("d_transposed", c_i32), ("ldd", c_i64), ("d_zo_stride", c_i64), ("d_zi_stride", c_i64),
+                ("epilogue", c_i32), ("alpha", c_f32), ("bias", c_vp), ("bias_gathered", c_i32),
+                ("bias_z_stride", c_i64), ("res", c_vp), ("ld_res", c_i64), ("res_row_mod", c_i32), ("rscale", c_vp),
+                ("aux_in", c_vp), ("aux_out", c_vp), ("ld_aux", c_i64), ("rope", c_vp), ("rope_t", c_i32),
+                ("rope_dim", c_i32), ("head_dim", c_i32), ("rope_cols", c_i32), ("rope_sign", c_f32),
+                ("block_n", c_i32)]
+
+
+# name -> (argtypes); every function returns int except the three introspection calls.
+_SIGS = {
+    "tribe_gemm_bf16": [ctypes.POINTER(TribeGemm), c_vp],
+    "tribe_gemm_bf16_probe": [ctypes.POINTER(TribeGemm), c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
+    "tribe_ingest_features": [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp],
+    "tribe_scalenorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp],
+    "tribe_sublayer_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp],
+    "tribe_softmax_fwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "tribe_softmax_bwd": [c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_i64, c_vp],
+    "tribe_colsum": [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp],
+    "tribe_cast_f32_bf16": [c_vp, c_vp, c_i64, c_vp],
+    "tribe_axpby_f32": [c_vp, c_vp, c_f32, c_i32, c_i64, c_vp],
+    "tribe_adaptive_avg_pool_fwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "tribe_adaptive_avg_pool_bwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "tribe_token_pool_fwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
+    "tribe_token_pool_bwd": [c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
+    "tribe_transpose_cast_bot": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "tribe_subject_bias_grad": [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
+    "tribe_check_subjects": [c_vp, c_i64, c_i64, c_vp, c_vp],
+    "tribe_mse_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp],
+    "tribe_pearson_stats": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp],
+    "tribe_pearson_finalize": [c_vp, c_i64, c_vp, c_vp, c_vp],
+}
+EXPORTS = sorted(list(_SIGS) + ["tribe_last_error", "tribe_abi_version", "tribe_launch_count"])
+
+
+def load():
+    """Return the ctypes handle; builds the library first if sources are newer.  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        build()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise TribeError(f"cannot load {LIB_PATH}: {e} — the CUDA extension is required (no CPU fallback)") from e
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, ctypes.c_int
+    lib.tribe_last_error.restype = ctypes.c_char_p
+    lib.tribe_abi_version.restype = ctypes.c_int
+    lib.tribe_launch_count.restype = ctypes.c_int64
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tribe_last_error().decode(errors="replace")
+        raise TribeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().tribe_launch_count())

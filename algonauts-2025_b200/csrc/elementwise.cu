@@ -1,0 +1,666 @@
+// HBM-bound kernels of the TRIBE hot path (sm_100a): feature ingest, ScaleNorm forward / sub-layer backward tail,
+// attention softmax forward / backward, column sums, casts, adaptive average pooling, small layout converters.
+// Each is a coalesced, 128-bit vectorised streaming kernel; roofline = bytes moved / measured HBM copy bandwidth.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tribe_b200.h"
+#include "tribe_internal.h"
+
+namespace tribe {
+
+constexpr int kMaxBlocks = 148 * 16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum; `red` must hold >= 32 floats.  All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : 0.0f;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// ------------------------------------------------------------------------------------------------ feature ingest
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<double>(double v) { return static_cast<float>(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+// x (B, L, D, T) -> out bf16 (B*T, ld_out): tile of 64 d x 64 t transposed through shared memory.
+// reference: algonauts2025/model.py:147-155 (cast, rearrange "b l d t -> b (l d) t", transpose(1, 2)).
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_kernel(const T* __restrict__ x, int64_t L, int64_t D, int64_t Tn, int layer_mean,
+                                                     __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t col_off) {
+  __shared__ float tile[64][65];
+  const int b = blockIdx.z;
+  const int64_t n_out_rows = layer_mean ? D : L * D;  // output feature index range
+  const int64_t f0 = static_cast<int64_t>(blockIdx.y) * 64;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < 64; r += 8) {
+    const int64_t f = f0 + r;
+    float v0 = 0.f, v1 = 0.f;
+    if (f < n_out_rows) {
+      if (!layer_mean) {
+        const T* src = x + (static_cast<int64_t>(b) * L * D + f) * Tn;
+        if (t0 + lane < Tn) v0 = to_f32<T>(src[t0 + lane]);
+        if (t0 + 32 + lane < Tn) v1 = to_f32<T>(src[t0 + 32 + lane]);
+      } else {
+        for (int64_t l = 0; l < L; ++l) {
+          const T* src = x + ((static_cast<int64_t>(b) * L + l) * D + f) * Tn;
+          if (t0 + lane < Tn) v0 += to_f32<T>(src[t0 + lane]);
+          if (t0 + 32 + lane < Tn) v1 += to_f32<T>(src[t0 + 32 + lane]);
+        }
+        const float inv = 1.0f / static_cast<float>(L);
+        v0 *= inv, v1 *= inv;
+      }
+    }
+    tile[r][lane] = v0;
+    tile[r][lane + 32] = v1;
+  }
+  __syncthreads();
+  for (int tt = warp; tt < 64; tt += 8) {
+    const int64_t t = t0 + tt;
+    if (t >= Tn) break;
+    const int64_t f = f0 + 2 * lane;
+    __nv_bfloat16* dst = out + (static_cast<int64_t>(b) * Tn + t) * ld_out + col_off + f;
+    const float a = tile[2 * lane][tt], c = tile[2 * lane + 1][tt];
+    if (f + 1 < n_out_rows && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(a, c);
+    } else {
+      if (f < n_out_rows) dst[0] = __float2bfloat16(a);
+      if (f + 1 < n_out_rows) dst[1] = __float2bfloat16(c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ScaleNorm
+// y = x / max(||x||, 1e-12) * sqrt(dim) * g   (oracle/xt_encoder.py ScaleNorm; F.normalize eps)
+__global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ rnorm, int64_t rows,
+                                                            int dim) {
+  __shared__ float red[32];
+  const int nvec = dim >> 2;
+  const float scale_g = sqrtf(static_cast<float>(dim)) * __ldg(g);
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    float4 cache[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < nvec) {
+        cache[i] = __ldg(xr + v);
+        ss += cache[i].x * cache[i].x + cache[i].y * cache[i].y + cache[i].z * cache[i].z + cache[i].w * cache[i].w;
+      }
+    }
+    for (int v = threadIdx.x + 1024; v < nvec; v += 256) {
+      const float4 c = __ldg(xr + v);
+      ss += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
+    }
+    ss = block_sum(ss, red);
+    const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (threadIdx.x == 0 && rnorm) rnorm[row] = rn;
+    const float s = rn * scale_g;
+    uint2* yr = reinterpret_cast<uint2*>(y + row * dim);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < nvec) yr[v] = make_uint2(pack_bf16x2(cache[i].x * s, cache[i].y * s), pack_bf16x2(cache[i].z * s, cache[i].w * s));
+    }
+    for (int v = threadIdx.x + 1024; v < nvec; v += 256) {
+      const float4 c = __ldg(xr + v);
+      yr[v] = make_uint2(pack_bf16x2(c.x * s, c.y * s), pack_bf16x2(c.z * s, c.w * s));
+    }
+  }
+}
+
+// Backward tail of one pre-norm residual sub-layer  x_out = branch(ScaleNorm(x_in)) + x_in * rs :
+//   dot      = sum_c d_xn[c] * x_in[c] * rnorm
+//   dx_in[c] = sqrt(dim) g rnorm (d_xn[c] - x_in[c] rnorm dot) + dy_out[c] * rs[c]
+//   d_rs[c] += dy_out[c] * x_in[c]        d_g += sqrt(dim) * dot
+// Each block walks a strided set of rows and keeps its d_rs column partials in registers (dim <= 4096).
+__global__ void __launch_bounds__(256) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
+                                                           const float* __restrict__ x_in, const float* __restrict__ rnorm,
+                                                           const float* __restrict__ g, const float* __restrict__ rs,
+                                                           float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
+                                                           float* __restrict__ d_rs, float* __restrict__ d_g, int64_t rows, int dim) {
+  __shared__ float red[32];
+  const int nvec = dim >> 2;
+  const float sqrt_dim = sqrtf(static_cast<float>(dim));
+  const float gval = g ? __ldg(g) : 0.f;
+  float4 rs_acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dg_acc = 0.f;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float4* xr = reinterpret_cast<const float4*>(x_in + row * dim);
+    const float4* dyr = dy_out ? reinterpret_cast<const float4*>(dy_out + row * dim) : nullptr;
+    const uint2* dnr = d_xn ? reinterpret_cast<const uint2*>(d_xn + row * dim) : nullptr;
+    float4 xc[4], dn[4];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < nvec) {
+        xc[i] = __ldg(xr + v);
+        if (dnr) {
+          const uint2 u = __ldg(dnr + v);
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          dn[i] = make_float4(a.x, a.y, b.x, b.y);
+          dot += dn[i].x * xc[i].x + dn[i].y * xc[i].y + dn[i].z * xc[i].z + dn[i].w * xc[i].w;
+        }
+      }
+    }
+    float coef = 0.f, rn = 0.f;
+    if (dnr) {
+      rn = __ldg(rnorm + row);
+      dot = block_sum(dot, red) * rn;
+      coef = sqrt_dim * gval * rn;
+      dg_acc += dot;  // identical in every thread; thread 0 publishes
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < nvec) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dnr) {
+          const float k = rn * dot;
+          o.x = coef * (dn[i].x - xc[i].x * k), o.y = coef * (dn[i].y - xc[i].y * k);
+          o.z = coef * (dn[i].z - xc[i].z * k), o.w = coef * (dn[i].w - xc[i].w * k);
+        }
+        if (dyr) {
+          const float4 dy = __ldg(dyr + v);
+          float4 r4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (rs) r4 = __ldg(reinterpret_cast<const float4*>(rs) + v);
+          o.x += dy.x * r4.x, o.y += dy.y * r4.y, o.z += dy.z * r4.z, o.w += dy.w * r4.w;
+          rs_acc[i].x += dy.x * xc[i].x, rs_acc[i].y += dy.y * xc[i].y, rs_acc[i].z += dy.z * xc[i].z, rs_acc[i].w += dy.w * xc[i].w;
+        }
+        if (dx_in) reinterpret_cast<float4*>(dx_in + row * dim)[v] = o;
+        if (dx_in_bf16) reinterpret_cast<uint2*>(dx_in_bf16 + row * dim)[v] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  if (d_rs) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < nvec) {
+        atomicAdd(d_rs + 4 * v, rs_acc[i].x), atomicAdd(d_rs + 4 * v + 1, rs_acc[i].y);
+        atomicAdd(d_rs + 4 * v + 2, rs_acc[i].z), atomicAdd(d_rs + 4 * v + 3, rs_acc[i].w);
+      }
+    }
+  }
+  if (d_g && threadIdx.x == 0) atomicAdd(d_g, sqrt_dim * dg_acc);
+}
+
+// ------------------------------------------------------------------------------------------------ softmax
+// One warp per row.  s fp32 (rows, ld) -> p bf16 (rows, ld); fp32 softmax as in x_transformers (dtype=float32).
+template <int ITER>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int64_t rows,
+                                                          int n_valid, int ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* sr = s + row * ld;
+  float v[ITER];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < n_valid ? __ldg(sr + c) : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < n_valid ? __expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* pr = p + row * ld;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = lane + i * 32;
+    if (c < ld) pr[c] = __float2bfloat16(v[i] * inv);
+  }
+}
+
+// ds = p * (dp - sum_j p_j dp_j) * scale
+template <int ITER>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
+                                                          __nv_bfloat16* __restrict__ ds, float scale, int64_t rows, int n_valid,
+                                                          int ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* pr = p + row * ld;
+  const float* dpr = dp + row * ld;
+  float pv[ITER], dv[ITER];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = lane + i * 32;
+    pv[i] = c < n_valid ? __bfloat162float(pr[c]) : 0.f;
+    dv[i] = c < n_valid ? __ldg(dpr + c) : 0.f;
+    dot += pv[i] * dv[i];
+  }
+  dot = warp_sum(dot);
+  __nv_bfloat16* dr = ds + row * ld;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = lane + i * 32;
+    if (c < ld) dr[c] = __float2bfloat16(pv[i] * (dv[i] - dot) * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+template <typename TX, typename TY, bool HAS_Y>
+__global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, const TY* __restrict__ y, float* __restrict__ out,
+                                                     int64_t rows, int64_t cols, int64_t ld, int64_t rows_per_block) {
+  // block = 32 (columns, x4 each) x 8 (row lanes); grid.x = column strips of 128, grid.y = row chunks
+  __shared__ float red[8][128];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 128 + tx * 4;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c0 < cols) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c0 + j < cols) {
+          float v = to_f32<TX>(x[r * ld + c0 + j]);
+          if (HAS_Y) v *= to_f32<TY>(y[r * ld + c0 + j]);
+          acc[j] += v;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[ty][tx * 4 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
+    if (c < cols) atomicAdd(out + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ casts / axpby
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+  for (int64_t i = (nvec << 3) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ src, float* __restrict__ dst, float a, int accumulate,
+                                                    int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = a * src[i] + (accumulate ? dst[i] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ adaptive avg pool
+__device__ __forceinline__ int win_start(int i, int t_in, int t_out) { return static_cast<int>((static_cast<int64_t>(i) * t_in) / t_out); }
+__device__ __forceinline__ int win_end(int i, int t_in, int t_out) {
+  return static_cast<int>((static_cast<int64_t>(i + 1) * t_in + t_out - 1) / t_out);
+}
+
+// x fp32 (rows, t_in) -> y fp32 (rows, t_out); a block stages R consecutive rows (contiguous in memory) in smem.
+// reference: nn.AdaptiveAvgPool1d(n_output_timesteps), algonauts2025/model.py:60,119-122.
+template <int R>
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int t_in,
+                                                       int t_out) {
+  extern __shared__ float sm[];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * R;
+  const int nr = static_cast<int>(min(static_cast<int64_t>(R), rows - r0));
+  const int64_t n_in = static_cast<int64_t>(nr) * t_in;
+  const float* src = x + r0 * t_in;
+  if (((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    const int64_t nv = n_in >> 2;
+    for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(sm)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int64_t i = (nv << 2) + threadIdx.x; i < n_in; i += blockDim.x) sm[i] = __ldg(src + i);
+  } else {
+    for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x) sm[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int n_out = nr * t_out;
+  float* dst = y + r0 * t_out;
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    const int r = o / t_out, i = o - r * t_out;
+    const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
+    float acc = 0.f;
+    for (int t = s; t < e; ++t) acc += sm[r * t_in + t];
+    dst[o] = acc / static_cast<float>(e - s);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t rows, int t_in,
+                                                       int t_out) {
+  extern __shared__ float sm[];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * R;
+  const int nr = static_cast<int>(min(static_cast<int64_t>(R), rows - r0));
+  const int n_o = nr * t_out;
+  for (int i = threadIdx.x; i < n_o; i += blockDim.x) sm[i] = __ldg(dy + r0 * t_out + i);
+  __syncthreads();
+  const int n_i = nr * t_in;
+  for (int o = threadIdx.x; o < n_i; o += blockDim.x) {
+    const int r = o / t_in, t = o - r * t_in;
+    int i_lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
+    int i_hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);  // exclusive upper bound
+    if (i_hi > t_out) i_hi = t_out;
+    float acc = 0.f;
+    for (int i = i_lo; i < i_hi; ++i) {
+      const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
+      if (t >= s && t < e) acc += sm[r * t_out + i] / static_cast<float>(e - s);
+    }
+    dx[r0 * t_in + o] = acc;
+  }
+}
+
+// token-major pooling: x bf16 (B, t_in, C) -> y bf16 (B, t_out, C); 8 channels (16 B) per thread.
+__global__ void __launch_bounds__(256) token_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int t_in,
+                                                             int t_out, int64_t C) {
+  const int b = blockIdx.y, i = blockIdx.x;
+  const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
+  const float inv = 1.0f / static_cast<float>(e - s);
+  const int64_t nvec = C >> 3;
+  for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = s; t < e; ++t) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * t_in + t) * C) + v);
+      const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x, acc[1] += a.y, acc[2] += bb.x, acc[3] += bb.y, acc[4] += c.x, acc[5] += c.y, acc[6] += d.x, acc[7] += d.y;
+    }
+    reinterpret_cast<uint4*>(y + (static_cast<int64_t>(b) * t_out + i) * C)[v] =
+        make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv), pack_bf16x2(acc[4] * inv, acc[5] * inv),
+                   pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int t_in, int t_out, int64_t C) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  int i_lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
+  int i_hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);
+  if (i_hi > t_out) i_hi = t_out;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = i_lo; i < i_hi; ++i) {
+      const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
+      if (t >= s && t < e) acc += to_f32<T>(dy[(static_cast<int64_t>(b) * t_out + i) * C + c]) / static_cast<float>(e - s);
+    }
+    dx[(static_cast<int64_t>(b) * t_in + t) * C + c] = acc;
+  }
+}
+
+// (B, O, T) fp32 -> (B, T, O) bf16
+__global__ void __launch_bounds__(256) transpose_cast_bot_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t O,
+                                                                 int64_t Tn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t o0 = static_cast<int64_t>(blockIdx.y) * 32, t0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < 32; r += 8) {
+    const int64_t o = o0 + r, t = t0 + lane;
+    tile[r][lane] = (o < O && t < Tn) ? __ldg(x + (static_cast<int64_t>(b) * O + o) * Tn + t) : 0.f;
+  }
+  __syncthreads();
+  for (int r = warp; r < 32; r += 8) {
+    const int64_t t = t0 + r, o = o0 + lane;
+    if (t < Tn && o < O) y[(static_cast<int64_t>(b) * Tn + t) * O + o] = __float2bfloat16(tile[lane][r]);
+  }
+}
+
+__global__ void __launch_bounds__(256) subject_bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, const long long* __restrict__ subjects,
+                                                                float* __restrict__ d_bias, int64_t Tn, int64_t O, int64_t n_subjects) {
+  const int b = blockIdx.y;
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  const long long s = subjects[b];
+  if (s < 0 || s >= n_subjects) return;
+  float acc = 0.f;
+  for (int64_t t = 0; t < Tn; ++t) acc += __bfloat162float(dy[(static_cast<int64_t>(b) * Tn + t) * O + o]);
+  atomicAdd(d_bias + s * O + o, acc);
+}
+
+__global__ void check_subjects_kernel(const long long* __restrict__ subjects, int64_t n, int64_t n_subjects, int* __restrict__ flag) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (subjects[i] >= n_subjects || subjects[i] < 0) atomicExch(flag, 1);
+}
+
+}  // namespace tribe
+
+using namespace tribe;
+
+extern "C" int tribe_ingest_features(const void* x, int32_t src_dtype, int64_t B, int64_t L, int64_t D, int64_t T, int32_t layer_mean,
+                                     void* out_bf16, int64_t ld_out, int64_t col_off, void* stream) {
+  if (!x || !out_bf16 || B <= 0 || L <= 0 || D <= 0 || T <= 0) return set_error(TRIBE_EINVAL, "ingest: bad arguments");
+  if (B > 65535) return set_error(TRIBE_EINVAL, "ingest: B > 65535");
+  const int64_t feats = layer_mean ? D : L * D;
+  dim3 grid(static_cast<unsigned>((T + 63) / 64), static_cast<unsigned>((feats + 63) / 64), static_cast<unsigned>(B));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  switch (src_dtype) {
+    case 0: ingest_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), L, D, T, layer_mean, o, ld_out, col_off); break;
+    case 1: ingest_kernel<double><<<grid, 256, 0, s>>>(reinterpret_cast<const double*>(x), L, D, T, layer_mean, o, ld_out, col_off); break;
+    case 2: ingest_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), L, D, T, layer_mean, o, ld_out, col_off); break;
+    case 3: ingest_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(x), L, D, T, layer_mean, o, ld_out, col_off); break;
+    default: return set_error(TRIBE_EINVAL, "ingest: unsupported source dtype");
+  }
+  TRIBE_CHECK_LAUNCH("ingest");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, void* stream) {
+  if (!x || !g || !y_bf16 || rows <= 0 || dim <= 0 || dim % 4) return set_error(TRIBE_EINVAL, "scalenorm_fwd: bad arguments (dim % 4)");
+  const int grid = grid_for(rows, 1, kMaxBlocks * 4);
+  scalenorm_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, g, reinterpret_cast<__nv_bfloat16*>(y_bf16), rnorm, rows,
+                                                                                  static_cast<int>(dim));
+  TRIBE_CHECK_LAUNCH("scalenorm_fwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, const float* x_in, const float* rnorm, const float* g,
+                                  const float* rs, float* dx_in, void* dx_in_bf16, float* d_rs, float* d_g, int64_t rows, int64_t dim,
+                                  void* stream) {
+  if (!x_in || rows <= 0 || dim <= 0 || dim % 4 || dim > 4096) return set_error(TRIBE_EINVAL, "sublayer_bwd: bad arguments (dim % 4, dim <= 4096)");
+  if (d_xn_bf16 && (!rnorm || !g)) return set_error(TRIBE_EINVAL, "sublayer_bwd: d_xn needs rnorm and g");
+  const int grid = grid_for(rows, 8, 148 * 4);
+  sublayer_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dy_out, reinterpret_cast<const __nv_bfloat16*>(d_xn_bf16), x_in, rnorm, g, rs, dx_in, reinterpret_cast<__nv_bfloat16*>(dx_in_bf16), d_rs, d_g,
+      rows, static_cast<int>(dim));
+  TRIBE_CHECK_LAUNCH("sublayer_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_softmax_fwd(const float* s, void* p_bf16, int64_t rows, int64_t n_valid, int64_t ld, void* stream) {
+  if (!s || !p_bf16 || rows <= 0 || n_valid <= 0 || n_valid > ld || ld > 1024) return set_error(TRIBE_EINVAL, "softmax_fwd: bad arguments (ld <= 1024)");
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(p_bf16);
+  const int nv = static_cast<int>(n_valid), l = static_cast<int>(ld);
+  if (ld <= 128) softmax_fwd_kernel<4><<<grid, 256, 0, st>>>(s, p, rows, nv, l);
+  else if (ld <= 320) softmax_fwd_kernel<10><<<grid, 256, 0, st>>>(s, p, rows, nv, l);
+  else if (ld <= 512) softmax_fwd_kernel<16><<<grid, 256, 0, st>>>(s, p, rows, nv, l);
+  else softmax_fwd_kernel<32><<<grid, 256, 0, st>>>(s, p, rows, nv, l);
+  TRIBE_CHECK_LAUNCH("softmax_fwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_softmax_bwd(const void* p_bf16, const float* dp, void* ds_bf16, float scale, int64_t rows, int64_t n_valid, int64_t ld,
+                                 void* stream) {
+  if (!p_bf16 || !dp || !ds_bf16 || rows <= 0 || n_valid <= 0 || n_valid > ld || ld > 1024) return set_error(TRIBE_EINVAL, "softmax_bwd: bad arguments");
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(p_bf16);
+  __nv_bfloat16* ds = reinterpret_cast<__nv_bfloat16*>(ds_bf16);
+  const int nv = static_cast<int>(n_valid), l = static_cast<int>(ld);
+  if (ld <= 128) softmax_bwd_kernel<4><<<grid, 256, 0, st>>>(p, dp, ds, scale, rows, nv, l);
+  else if (ld <= 320) softmax_bwd_kernel<10><<<grid, 256, 0, st>>>(p, dp, ds, scale, rows, nv, l);
+  else if (ld <= 512) softmax_bwd_kernel<16><<<grid, 256, 0, st>>>(p, dp, ds, scale, rows, nv, l);
+  else softmax_bwd_kernel<32><<<grid, 256, 0, st>>>(p, dp, ds, scale, rows, nv, l);
+  TRIBE_CHECK_LAUNCH("softmax_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_colsum(const void* x, int32_t x_dtype, const void* y, int32_t y_dtype, float* out, int64_t rows, int64_t cols, int64_t ld,
+                            int32_t accumulate, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || ld < cols) return set_error(TRIBE_EINVAL, "colsum: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * cols, s);
+    if (e != cudaSuccess) return set_cuda_error(e, "colsum memset");
+  }
+  const int64_t strips = (cols + 127) / 128;
+  int64_t chunks = (148 * 4 + strips - 1) / strips;
+  if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
+  if (chunks < 1) chunks = 1;
+  const int64_t rpb = (rows + chunks - 1) / chunks;
+  dim3 grid(static_cast<unsigned>(strips), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  using bf = __nv_bfloat16;
+  if (x_dtype == 0 && !y) colsum_kernel<float, float, false><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), nullptr, out, rows, cols, ld, rpb);
+  else if (x_dtype == 2 && !y) colsum_kernel<bf, bf, false><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), nullptr, out, rows, cols, ld, rpb);
+  else if (x_dtype == 0 && y_dtype == 0) colsum_kernel<float, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb);
+  else if (x_dtype == 2 && y_dtype == 2) colsum_kernel<bf, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb);
+  else if (x_dtype == 0 && y_dtype == 2) colsum_kernel<float, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb);
+  else if (x_dtype == 2 && y_dtype == 0) colsum_kernel<bf, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb);
+  else return set_error(TRIBE_EINVAL, "colsum: unsupported dtype combination");
+  TRIBE_CHECK_LAUNCH("colsum");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
+  if (!src || !dst_bf16 || n <= 0) return set_error(TRIBE_EINVAL, "cast: bad arguments");
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_bf16) & 15)) return set_error(TRIBE_EINVAL, "cast: 16-byte alignment required");
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256, kMaxBlocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  TRIBE_CHECK_LAUNCH("cast_f32_bf16");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_axpby_f32(const float* src, float* dst, float a, int32_t accumulate, int64_t n, void* stream) {
+  if (!src || !dst || n <= 0) return set_error(TRIBE_EINVAL, "axpby: bad arguments");
+  axpby_kernel<<<grid_for(n, 256, kMaxBlocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, a, accumulate, n);
+  TRIBE_CHECK_LAUNCH("axpby");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_adaptive_avg_pool_fwd(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, void* stream) {
+  if (!x || !y || rows <= 0 || t_in <= 0 || t_out <= 0) return set_error(TRIBE_EINVAL, "pool_fwd: bad arguments");
+  constexpr int R = 8;
+  const size_t smem = sizeof(float) * R * t_in;
+  if (smem > 200 * 1024) return set_error(TRIBE_EINVAL, "pool_fwd: t_in too large");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pool_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  pool_fwd_kernel<R><<<static_cast<unsigned>((rows + R - 1) / R), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, y, rows, static_cast<int>(t_in), static_cast<int>(t_out));
+  TRIBE_CHECK_LAUNCH("pool_fwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_adaptive_avg_pool_bwd(const float* dy, float* dx, int64_t rows, int64_t t_in, int64_t t_out, void* stream) {
+  if (!dy || !dx || rows <= 0 || t_in <= 0 || t_out <= 0) return set_error(TRIBE_EINVAL, "pool_bwd: bad arguments");
+  constexpr int R = 8;
+  const size_t smem = sizeof(float) * R * t_out;
+  if (smem > 200 * 1024) return set_error(TRIBE_EINVAL, "pool_bwd: t_out too large");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pool_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  pool_bwd_kernel<R><<<static_cast<unsigned>((rows + R - 1) / R), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dy, dx, rows, static_cast<int>(t_in), static_cast<int>(t_out));
+  TRIBE_CHECK_LAUNCH("pool_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_token_pool_fwd(const void* x_bf16, void* y_bf16, int64_t B, int64_t t_in, int64_t t_out, int64_t C, void* stream) {
+  if (!x_bf16 || !y_bf16 || B <= 0 || t_in <= 0 || t_out <= 0 || C <= 0 || C % 8 || B > 65535) return set_error(TRIBE_EINVAL, "token_pool_fwd: bad arguments (C % 8)");
+  dim3 grid(static_cast<unsigned>(t_out), static_cast<unsigned>(B));
+  token_pool_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), reinterpret_cast<__nv_bfloat16*>(y_bf16), static_cast<int>(t_in), static_cast<int>(t_out), C);
+  TRIBE_CHECK_LAUNCH("token_pool_fwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, float* dx, int64_t B, int64_t t_in, int64_t t_out, int64_t C, void* stream) {
+  if (!dy || !dx || B <= 0 || t_in <= 0 || t_out <= 0 || C <= 0 || B > 65535) return set_error(TRIBE_EINVAL, "token_pool_bwd: bad arguments");
+  dim3 grid(static_cast<unsigned>(t_in), static_cast<unsigned>(B));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dy_dtype == 0) token_pool_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dy), dx, static_cast<int>(t_in), static_cast<int>(t_out), C);
+  else if (dy_dtype == 2) token_pool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dx, static_cast<int>(t_in), static_cast<int>(t_out), C);
+  else return set_error(TRIBE_EINVAL, "token_pool_bwd: unsupported dtype");
+  TRIBE_CHECK_LAUNCH("token_pool_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_transpose_cast_bot(const float* x, void* y_bf16, int64_t B, int64_t O, int64_t T, void* stream) {
+  if (!x || !y_bf16 || B <= 0 || O <= 0 || T <= 0 || B > 65535) return set_error(TRIBE_EINVAL, "transpose_cast_bot: bad arguments");
+  dim3 grid(static_cast<unsigned>((T + 31) / 32), static_cast<unsigned>((O + 31) / 32), static_cast<unsigned>(B));
+  transpose_cast_bot_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y_bf16), O, T);
+  TRIBE_CHECK_LAUNCH("transpose_cast_bot");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_subject_bias_grad(const void* dy_bf16, const int64_t* subjects, float* d_bias, int64_t B, int64_t T, int64_t O,
+                                       int64_t n_subjects, void* stream) {
+  if (!dy_bf16 || !subjects || !d_bias || B <= 0 || T <= 0 || O <= 0 || B > 65535) return set_error(TRIBE_EINVAL, "subject_bias_grad: bad arguments");
+  dim3 grid(static_cast<unsigned>((O + 255) / 256), static_cast<unsigned>(B));
+  subject_bias_grad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const long long*>(subjects), d_bias, T, O, n_subjects);
+  TRIBE_CHECK_LAUNCH("subject_bias_grad");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_check_subjects(const int64_t* subjects, int64_t n, int64_t n_subjects, int32_t* flag_out, void* stream) {
+  if (!subjects || !flag_out || n <= 0) return set_error(TRIBE_EINVAL, "check_subjects: bad arguments");
+  check_subjects_kernel<<<grid_for(n, 256, 64), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(subjects), n,
+                                                                                                   n_subjects, flag_out);
+  TRIBE_CHECK_LAUNCH("check_subjects");
+  return TRIBE_OK;
+}

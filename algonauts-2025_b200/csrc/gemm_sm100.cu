@@ -1,0 +1,618 @@
+// tcgen05 / TMEM / TMA batched GEMM for sm_100a:  D[z] = epilogue(alpha * A[z] * B[z]^T), bf16 in, fp32 accumulate.
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor.3d into a SWIZZLE_128B smem ring, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one thread issues tcgen05.mma 128 x BN x 16 into a double-buffered TMEM accumulator)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Both operands may be K-major or MN-major (canonical SWIZZLE_128B UMMA layouts), so forward, dgrad and wgrad GEMMs and
+// the attention / SubjectLayers contractions all run through this one kernel without materialised transposes.
+//
+// Replaces (reference, relative to /root/reference): projector nn.Linear algonauts2025/model.py:157; the encoder's
+// linears and attention einsums behind model.py:173 (x_transformers, restated in oracle/xt_encoder.py); SubjectLayers
+// index_select + einsum modeling_utils/modeling_utils/models/common.py:61-66; InfoNCE logits model.py:216.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "ptx_sm100.cuh"
+#include "tribe_b200.h"
+#include "tribe_internal.h"
+
+namespace tribe {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct alignas(64) GemmKParams {
+  CUtensorMap tma, tmb;
+  int m, n, k, batch, z_inner;
+  int a_inner_off, a_zin_stride, a_zdiv;
+  int b_inner_off, b_zin_stride, b_zdiv;
+  const long long* a_gather;
+  const long long* b_gather;
+  const long long* kgroup;
+  int kgroup_len;
+  void* d;
+  int d_f32, d_transposed, vec_ok;
+  long long ldd, d_zo, d_zi;
+  int epilogue;
+  float alpha;
+  const float* bias;
+  int bias_gathered;
+  long long bias_z_stride;
+  const float* res;
+  long long ld_res;
+  int res_row_mod;
+  const float* rscale;
+  const __nv_bfloat16* aux_in;
+  __nv_bfloat16* aux_out;
+  long long ld_aux;
+  const float2* rope;
+  int rope_t, rope_dim, head_dim, rope_cols;
+  float rope_sign;
+  uint32_t k_lbo, k_sbo, mn_lbo, mn_sbo;
+  int m_blocks, n_blocks, num_tiles, num_kb;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+struct TileCoord {
+  int z, zi, zo, m0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int bn) {
+  TileCoord t;
+  int mb = tile % p.m_blocks;
+  int rest = tile / p.m_blocks;
+  int nb = rest % p.n_blocks;
+  t.z = rest / p.n_blocks;
+  t.zi = t.z % p.z_inner;
+  t.zo = t.z / p.z_inner;
+  t.m0 = mb * BM;
+  t.n0 = nb * bn;
+  return t;
+}
+
+__device__ __forceinline__ int batch_coord(const long long* gather, int z, int zdiv) {
+  int zz = z / zdiv;
+  return gather ? static_cast<int>(gather[zz]) : zz;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are loaded in 64-wide chunks");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma);
+    prefetch_tmap(&p.tmb);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull_bar[s], 1);
+        mbar_init(&tempty_bar[s], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const int n_kouter = p.kgroup ? p.kgroup_len : 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        const int a_in = p.a_inner_off + t.zi * p.a_zin_stride;
+        const int b_in = p.b_inner_off + t.zi * p.b_zin_stride;
+        for (int ko = 0; ko < n_kouter; ++ko) {
+          int za, zb;
+          if (p.kgroup) {
+            if (static_cast<int>(p.kgroup[ko]) != t.z) continue;
+            za = zb = ko;
+          } else {
+            za = batch_coord(p.a_gather, t.z, p.a_zdiv);
+            zb = batch_coord(p.b_gather, t.z, p.b_zdiv);
+          }
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_3d(sa, &p.tma, &full_bar[stage], a_in + kb * BK, t.m0, za);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_3d(sa + j * (BK * 128), &p.tma, &full_bar[stage], a_in + t.m0 + j * 64, kb * BK, za);
+            }
+            if (!B_MN) {
+              tma_load_3d(sb, &p.tmb, &full_bar[stage], b_in + kb * BK, t.n0, zb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_3d(sb + j * (BK * 128), &p.tmb, &full_bar[stage], b_in + t.n0 + j * 64, kb * BK, zb);
+            }
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      const uint32_t a_lbo = A_MN ? p.mn_lbo : p.k_lbo, a_sbo = A_MN ? p.mn_sbo : p.k_sbo;
+      const uint32_t b_lbo = B_MN ? p.mn_lbo : p.k_lbo, b_sbo = B_MN ? p.mn_sbo : p.k_sbo;
+      constexpr uint32_t a_kstep = A_MN ? 16 * 128 : 32;  // bytes per UMMA_K = 16 along K
+      constexpr uint32_t b_kstep = B_MN ? 16 * 128 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int ko = 0; ko < n_kouter; ++ko) {
+          if (p.kgroup && static_cast<int>(p.kgroup[ko]) != t.z) continue;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo);
+              const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo);
+              umma_bf16(d_tmem, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      bool has_k = true;
+      if (p.kgroup) {
+        has_k = false;
+        for (int ko = 0; ko < p.kgroup_len; ++ko) has_k |= (static_cast<int>(p.kgroup[ko]) == t.z);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = t.m0 + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      const long long zoff = static_cast<long long>(t.zo) * p.d_zo + static_cast<long long>(t.zi) * p.d_zi;
+      const float* bias = p.bias;
+      if (bias && p.bias_gathered) bias += static_cast<long long>(batch_coord(p.b_gather, t.z, p.b_zdiv)) * p.bias_z_stride;
+      const int res_row = p.res_row_mod ? row % p.res_row_mod : row;
+      const int pos = p.rope ? row % p.rope_t : 0;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = t.n0 + c * 32;
+        if (col0 >= p.n) break;  // warp-uniform
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(raw[j]) * p.alpha : 0.0f;
+        const int nvalid = min(32, p.n - col0);
+        const bool full = (nvalid == 32) && p.vec_ok;
+
+        if (bias) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += __ldg(bias + col0 + j);
+          }
+        }
+
+        if (p.epilogue == TRIBE_EPI_GELU) {
+          if (row_ok) {
+            __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(ap + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) ap[j] = __float2bfloat16(v[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.epilogue == TRIBE_EPI_GELU_BWD) {
+          if (row_ok) {
+            const __nv_bfloat16* ap = p.aux_in + static_cast<long long>(row) * p.ld_aux + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(ap + j));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[j + 2 * e] *= gelu_erf_grad(f.x);
+                  v[j + 2 * e + 1] *= gelu_erf_grad(f.y);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] *= gelu_erf_grad(__bfloat162float(ap[j]));
+            }
+          }
+        } else if (p.epilogue == TRIBE_EPI_RESIDUAL) {
+          if (row_ok) {
+            const float* rp = p.res + static_cast<long long>(res_row) * p.ld_res + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (p.rscale) s4 = __ldg(reinterpret_cast<const float4*>(p.rscale + col0 + j));
+                v[j] += r4.x * s4.x, v[j + 1] += r4.y * s4.y, v[j + 2] += r4.z * s4.z, v[j + 3] += r4.w * s4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += __ldg(rp + j) * (p.rscale ? __ldg(p.rscale + col0 + j) : 1.0f);
+            }
+          }
+        } else if (p.epilogue == TRIBE_EPI_ROPE) {
+          const int cih = col0 % p.head_dim;  // chunk-uniform: head_dim, rope_dim are multiples of 32
+          if (col0 < p.rope_cols && cih < p.rope_dim) {
+            const float2* tab = p.rope + static_cast<long long>(pos) * (p.rope_dim >> 1) + (cih >> 1);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(tab + j));  // (cos, sin) of two pairs
+              const float s0 = cs.y * p.rope_sign, s1 = cs.w * p.rope_sign;
+              const float x0 = v[2 * j], x1 = v[2 * j + 1], y0 = v[2 * j + 2], y1 = v[2 * j + 3];
+              v[2 * j] = x0 * cs.x - x1 * s0;
+              v[2 * j + 1] = x1 * cs.x + x0 * s0;
+              v[2 * j + 2] = y0 * cs.z - y1 * s1;
+              v[2 * j + 3] = y1 * cs.z + y0 * s1;
+            }
+          }
+        }
+
+        if (row_ok) {
+          if (p.d_transposed) {
+            if (p.d_f32) {
+              float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = v[j];
+            } else {
+              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = __float2bfloat16(v[j]);
+            }
+          } else if (p.d_f32) {
+            float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) dp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(dp + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int64_t inner, rows, batch, row_stride, batch_stride;
+  int box_rows;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+
+static int encode_operand(const TribeOperand& op, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = op.ptr, key.inner = op.inner, key.rows = op.rows, key.batch = op.batch, key.row_stride = op.row_stride;
+  key.batch_stride = op.batch > 1 ? op.batch_stride : 0, key.box_rows = box_rows;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return TRIBE_OK;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(TRIBE_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (op.row_stride * 2) % 16 || (op.batch > 1 && (op.batch_stride * 2) % 16))
+    return set_error(TRIBE_EINVAL, "GEMM operand: pointer and strides must be 16-byte aligned");
+  if (op.inner <= 0 || op.rows <= 0 || op.batch <= 0) return set_error(TRIBE_EINVAL, "GEMM operand: empty extent");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(op.inner), static_cast<cuuint64_t>(op.rows), static_cast<cuuint64_t>(op.batch)};
+  cuuint64_t bstride = op.batch > 1 ? static_cast<cuuint64_t>(op.batch_stride) * 2 : static_cast<cuuint64_t>(op.row_stride) * 2 * op.rows;
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(op.row_stride) * 2, bstride};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  alignas(64) CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[200];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld batch=%lld rs=%lld bs=%lld box=%d",
+             static_cast<int>(r), (long long)op.inner, (long long)op.rows, (long long)op.batch, (long long)op.row_stride,
+             (long long)op.batch_stride, box_rows);
+    return set_error(TRIBE_ETMAP, msg);
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = tm;
+  }
+  *out = tm;
+  return TRIBE_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
+    attr_set = true;
+  }
+  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
+  return TRIBE_OK;
+}
+
+template <int BN>
+static int dispatch_major(const GemmKParams& kp, bool a_mn, bool b_mn, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(kp, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(kp, s);
+  if constexpr (BN % 64 == 0) {
+    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(kp, s);
+    return launch_gemm<BN, true, true>(kp, s);
+  } else {
+    return set_error(TRIBE_EINVAL, "block_n=160 requires a K-major B operand");
+  }
+}
+
+static int pick_block_n(const TribeGemm& g) {
+  if (g.block_n) return g.block_n;
+  const bool b_mn = g.b.mn_major != 0;
+  if (g.n <= 128) return 128;
+  if (g.n <= 160 && !b_mn) return 160;
+  if (g.n <= 192) return 192;
+  if (g.n <= 256) return 256;
+  if (g.n <= 320 && !b_mn) return 160;
+  if (g.n <= 384) return 192;
+  return 256;
+}
+
+static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t k_sbo, uint32_t mn_lbo, uint32_t mn_sbo) {
+  if (!g || !g->a.ptr || !g->b.ptr || !g->d) return set_error(TRIBE_EINVAL, "gemm: null pointer");
+  if (g->m <= 0 || g->n <= 0 || g->k <= 0 || g->batch <= 0) return set_error(TRIBE_EINVAL, "gemm: empty problem");
+  const int bn = pick_block_n(*g);
+  if (bn != 128 && bn != 160 && bn != 192 && bn != 256) return set_error(TRIBE_EINVAL, "gemm: block_n must be 128/160/192/256");
+  if (g->epilogue == TRIBE_EPI_ROPE) {
+    if (!g->rope || g->rope_t <= 0 || g->head_dim % 32 || g->rope_dim % 32 || g->rope_dim > g->head_dim)
+      return set_error(TRIBE_EINVAL, "gemm: rope epilogue needs a table and head_dim/rope_dim multiples of 32");
+  }
+  if (g->epilogue == TRIBE_EPI_GELU && !g->aux_out) return set_error(TRIBE_EINVAL, "gemm: GELU epilogue needs aux_out");
+  if (g->epilogue == TRIBE_EPI_GELU_BWD && !g->aux_in) return set_error(TRIBE_EINVAL, "gemm: GELU_BWD epilogue needs aux_in");
+  if (g->epilogue == TRIBE_EPI_RESIDUAL && !g->res) return set_error(TRIBE_EINVAL, "gemm: RESIDUAL epilogue needs res");
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const bool a_mn = g->a.mn_major != 0, b_mn = g->b.mn_major != 0;
+  int rc = encode_operand(g->a, a_mn ? BK : BM, &kp.tma);
+  if (rc) return rc;
+  rc = encode_operand(g->b, b_mn ? BK : bn, &kp.tmb);
+  if (rc) return rc;
+  kp.m = g->m, kp.n = g->n, kp.k = g->k, kp.batch = g->batch, kp.z_inner = g->z_inner > 0 ? g->z_inner : 1;
+  kp.a_inner_off = g->a.inner_off, kp.a_zin_stride = g->a.zin_stride, kp.a_zdiv = g->a.zdiv > 0 ? g->a.zdiv : 1;
+  kp.b_inner_off = g->b.inner_off, kp.b_zin_stride = g->b.zin_stride, kp.b_zdiv = g->b.zdiv > 0 ? g->b.zdiv : 1;
+  kp.a_gather = reinterpret_cast<const long long*>(g->a.gather);
+  kp.b_gather = reinterpret_cast<const long long*>(g->b.gather);
+  kp.kgroup = reinterpret_cast<const long long*>(g->kgroup), kp.kgroup_len = g->kgroup_len;
+  kp.d = g->d, kp.d_f32 = g->d_f32, kp.d_transposed = g->d_transposed;
+  kp.ldd = g->ldd, kp.d_zo = g->d_zo_stride, kp.d_zi = g->d_zi_stride;
+  kp.epilogue = g->epilogue, kp.alpha = g->alpha;
+  kp.bias = g->bias, kp.bias_gathered = g->bias_gathered, kp.bias_z_stride = g->bias_z_stride;
+  kp.res = g->res, kp.ld_res = g->ld_res, kp.res_row_mod = g->res_row_mod, kp.rscale = g->rscale;
+  kp.aux_in = reinterpret_cast<const __nv_bfloat16*>(g->aux_in);
+  kp.aux_out = reinterpret_cast<__nv_bfloat16*>(g->aux_out), kp.ld_aux = g->ld_aux;
+  kp.rope = reinterpret_cast<const float2*>(g->rope);
+  kp.rope_t = g->rope_t, kp.rope_dim = g->rope_dim, kp.head_dim = g->head_dim > 0 ? g->head_dim : 32;
+  kp.rope_cols = g->rope_cols, kp.rope_sign = g->rope_sign;
+  kp.k_lbo = k_lbo ? k_lbo : 16, kp.k_sbo = k_sbo ? k_sbo : 1024;
+  kp.mn_lbo = mn_lbo ? mn_lbo : BK * 128, kp.mn_sbo = mn_sbo ? mn_sbo : 1024;
+  kp.m_blocks = (g->m + BM - 1) / BM, kp.n_blocks = (g->n + bn - 1) / bn;
+  kp.num_tiles = kp.m_blocks * kp.n_blocks * g->batch, kp.num_kb = (g->k + BK - 1) / BK;
+  // 16-byte vector epilogue accesses need aligned bases / leading dimensions.
+  const int esz = g->d_f32 ? 4 : 2;
+  auto al16 = [](const void* p_) { return (reinterpret_cast<uintptr_t>(p_) & 15) == 0; };
+  bool vec = al16(g->d) && (g->ldd * esz) % 16 == 0 && (g->d_zo_stride * esz) % 16 == 0 && (g->d_zi_stride * esz) % 16 == 0;
+  if (g->bias) vec = vec && al16(g->bias) && (g->bias_z_stride * 4) % 16 == 0;
+  if (g->res) vec = vec && al16(g->res) && (g->ld_res * 4) % 16 == 0;
+  if (g->rscale) vec = vec && al16(g->rscale);
+  if (g->aux_in) vec = vec && al16(g->aux_in) && (g->ld_aux * 2) % 16 == 0;
+  if (g->aux_out) vec = vec && al16(g->aux_out) && (g->ld_aux * 2) % 16 == 0;
+  if (g->rope && !al16(g->rope)) return set_error(TRIBE_EINVAL, "gemm: rope table must be 16-byte aligned");
+  kp.vec_ok = vec ? 1 : 0;
+
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 128: return dispatch_major<128>(kp, a_mn, b_mn, s);
+    case 160: return dispatch_major<160>(kp, a_mn, b_mn, s);
+    case 192: return dispatch_major<192>(kp, a_mn, b_mn, s);
+    default: return dispatch_major<256>(kp, a_mn, b_mn, s);
+  }
+}
+
+}  // namespace tribe
+
+extern "C" int tribe_gemm_bf16(const TribeGemm* g, void* stream) { return tribe::gemm_impl(g, stream, 0, 0, 0, 0); }
+
+extern "C" int tribe_gemm_bf16_probe(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t k_sbo, uint32_t mn_lbo,
+                                     uint32_t mn_sbo) {
+  return tribe::gemm_impl(g, stream, k_lbo, k_sbo, mn_lbo, mn_sbo);
+}

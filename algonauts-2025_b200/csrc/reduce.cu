@@ -1,0 +1,282 @@
+// Loss / evaluation reductions of the TRIBE hot path (sm_100a): fused MSE forward+gradient and per-parcel Pearson
+// sufficient statistics.  HBM-bound (8 B per parcel-TR: one fp32 prediction + one fp32 target, single pass);
+// warp-shuffle + shared-memory reductions, fp64 cross-chunk accumulation.
+//
+// reference: nn.MSELoss at algonauts2025/pl_module.py:56; torchmetrics PearsonCorrCoef updates at pl_module.py:93-106
+// (restated in oracle/tm_pearson.py); the final scipy.stats.pearsonr loop at algonauts2025/main.py:459-477.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tribe_b200.h"
+#include "tribe_internal.h"
+
+namespace tribe {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ MSE
+constexpr int kMsePartials = 1024;
+
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                          float* __restrict__ grad, float gscale, int64_t n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+  double acc = 0.0;
+  if (vec) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pred) + i);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(target) + i);
+      const float dx = p.x - t.x, dy = p.y - t.y, dz = p.z - t.z, dw = p.w - t.w;
+      acc += static_cast<double>(dx * dx + dy * dy + dz * dz + dw * dw);
+      if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(dx * gscale, dy * gscale, dz * gscale, dw * gscale);
+    }
+    for (int64_t i = (nvec << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float d = pred[i] - target[i];
+      acc += static_cast<double>(d * d);
+      if (grad) grad[i] = d * gscale;
+    }
+  } else {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float d = pred[i] - target[i];
+      acc += static_cast<double>(d * d);
+      if (grad) grad[i] = d * gscale;
+    }
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) mse_final_kernel(const double* __restrict__ partial, int nparts, int64_t n, float* __restrict__ loss) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) loss[0] = static_cast<float>(v / static_cast<double>(n));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Pearson statistics
+// Fast path: row-major (n_rows, n_parcels) fp32 matrices.  Thread = 4 consecutive parcels (one float4 of pred and one of
+// target per row), block = one row-chunk x 1024 parcels; fp32 partial sums over kInner rows are folded into fp64
+// accumulators, block results are added to stats[6][n_parcels] with fp64 atomics.
+constexpr int kInner = 8;
+
+__global__ void __launch_bounds__(256) pearson_rowmajor_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_rows,
+                                                               int64_t n_parcels, int64_t rows_per_block, const long long* __restrict__ group,
+                                                               double* __restrict__ stats) {
+  const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (p0 >= n_parcels) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(n_rows, r0 + rows_per_block);
+  if (r0 >= r1) return;
+  const bool full4 = p0 + 4 <= n_parcels;
+  double sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0}, sxy[4] = {0, 0, 0, 0};
+  long long cur_group = group ? group[r0] : 0;
+  int64_t n_in_group = 0;
+  auto flush = [&](long long gsel, int64_t count) {
+    double* st = stats + gsel * 6 * n_parcels;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p0 + j < n_parcels) {
+        atomicAdd(st + 0 * n_parcels + p0 + j, static_cast<double>(count));
+        atomicAdd(st + 1 * n_parcels + p0 + j, sx[j]);
+        atomicAdd(st + 2 * n_parcels + p0 + j, sy[j]);
+        atomicAdd(st + 3 * n_parcels + p0 + j, sxx[j]);
+        atomicAdd(st + 4 * n_parcels + p0 + j, syy[j]);
+        atomicAdd(st + 5 * n_parcels + p0 + j, sxy[j]);
+      }
+      sx[j] = sy[j] = sxx[j] = syy[j] = sxy[j] = 0.0;
+    }
+  };
+  for (int64_t r = r0; r < r1; r += kInner) {
+    const int nr = static_cast<int>(min(static_cast<int64_t>(kInner), r1 - r));
+    if (group) {
+      // a chunk of rows never straddles groups in the accumulators: flush when the group id changes
+      bool same = true;
+      for (int k = 0; k < nr; ++k) same &= (group[r + k] == cur_group);
+      if (!same) {
+        for (int k = 0; k < nr; ++k) {
+          const long long gk = group[r + k];
+          if (gk != cur_group) {
+            flush(cur_group, n_in_group);
+            cur_group = gk, n_in_group = 0;
+          }
+          float x[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0};
+          for (int j = 0; j < 4; ++j)
+            if (p0 + j < n_parcels) x[j] = pred[(r + k) * n_parcels + p0 + j], y[j] = target[(r + k) * n_parcels + p0 + j];
+          for (int j = 0; j < 4; ++j) sx[j] += x[j], sy[j] += y[j], sxx[j] += (double)x[j] * x[j], syy[j] += (double)y[j] * y[j], sxy[j] += (double)x[j] * y[j];
+          ++n_in_group;
+        }
+        continue;
+      }
+    }
+    float fx[4] = {0, 0, 0, 0}, fy[4] = {0, 0, 0, 0}, fxx[4] = {0, 0, 0, 0}, fyy[4] = {0, 0, 0, 0}, fxy[4] = {0, 0, 0, 0};
+    if (full4 && ((n_parcels & 3) == 0)) {
+      float4 xs[kInner], ys[kInner];
+#pragma unroll
+      for (int k = 0; k < kInner; ++k) {
+        if (k < nr) {
+          xs[k] = __ldg(reinterpret_cast<const float4*>(pred + (r + k) * n_parcels + p0));
+          ys[k] = __ldg(reinterpret_cast<const float4*>(target + (r + k) * n_parcels + p0));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kInner; ++k) {
+        if (k < nr) {
+          const float x[4] = {xs[k].x, xs[k].y, xs[k].z, xs[k].w}, y[4] = {ys[k].x, ys[k].y, ys[k].z, ys[k].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            fx[j] += x[j], fy[j] += y[j];
+            fxx[j] = fmaf(x[j], x[j], fxx[j]), fyy[j] = fmaf(y[j], y[j], fyy[j]), fxy[j] = fmaf(x[j], y[j], fxy[j]);
+          }
+        }
+      }
+    } else {
+      for (int k = 0; k < nr; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p0 + j < n_parcels) {
+            const float x = pred[(r + k) * n_parcels + p0 + j], y = target[(r + k) * n_parcels + p0 + j];
+            fx[j] += x, fy[j] += y, fxx[j] = fmaf(x, x, fxx[j]), fyy[j] = fmaf(y, y, fyy[j]), fxy[j] = fmaf(x, y, fxy[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sx[j] += fx[j], sy[j] += fy[j], sxx[j] += fxx[j], syy[j] += fyy[j], sxy[j] += fxy[j];
+    n_in_group += nr;
+  }
+  flush(cur_group, n_in_group);
+}
+
+// Strided path: element(r, p) = base[(r / t_len) * stride_b + p * stride_p + (r % t_len) * stride_t]  (the flattened
+// "(b t) d" view of a (B, D, T) prediction tensor, pl_module.py:54-55).  One warp per (b, parcel): lanes run along t.
+__global__ void __launch_bounds__(256) pearson_strided_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_b,
+                                                              int64_t n_parcels, int64_t t_len, int64_t stride_b, int64_t stride_p, int64_t stride_t,
+                                                              const long long* __restrict__ group, double* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t b = blockIdx.y;
+  if (p >= n_parcels || b >= n_b) return;
+  const float* xp = pred + b * stride_b + p * stride_p;
+  const float* yp = target + b * stride_b + p * stride_p;
+  float fx = 0, fy = 0, fxx = 0, fyy = 0, fxy = 0;
+  double dx = 0, dy = 0, dxx = 0, dyy = 0, dxy = 0;
+  int cnt = 0;
+  for (int64_t t = lane; t < t_len; t += 32) {
+    const float x = __ldg(xp + t * stride_t), y = __ldg(yp + t * stride_t);
+    fx += x, fy += y, fxx = fmaf(x, x, fxx), fyy = fmaf(y, y, fyy), fxy = fmaf(x, y, fxy);
+    if (++cnt == 16) {
+      dx += fx, dy += fy, dxx += fxx, dyy += fyy, dxy += fxy;
+      fx = fy = fxx = fyy = fxy = 0.f, cnt = 0;
+    }
+  }
+  dx += fx, dy += fy, dxx += fxx, dyy += fyy, dxy += fxy;
+  dx = warp_sum_d(dx), dy = warp_sum_d(dy), dxx = warp_sum_d(dxx), dyy = warp_sum_d(dyy), dxy = warp_sum_d(dxy);
+  if (lane == 0) {
+    double* st = stats + (group ? group[b] : 0) * 6 * n_parcels;
+    atomicAdd(st + 0 * n_parcels + p, static_cast<double>(t_len));
+    atomicAdd(st + 1 * n_parcels + p, dx);
+    atomicAdd(st + 2 * n_parcels + p, dy);
+    atomicAdd(st + 3 * n_parcels + p, dxx);
+    atomicAdd(st + 4 * n_parcels + p, dyy);
+    atomicAdd(st + 5 * n_parcels + p, dxy);
+  }
+}
+
+__global__ void __launch_bounds__(256) pearson_finalize_kernel(const double* __restrict__ stats, int64_t n_parcels, float* __restrict__ r_out,
+                                                               float* __restrict__ mean_out) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t p = threadIdx.x; p < n_parcels; p += blockDim.x) {
+    const double n = stats[p], sx = stats[n_parcels + p], sy = stats[2 * n_parcels + p];
+    const double sxx = stats[3 * n_parcels + p], syy = stats[4 * n_parcels + p], sxy = stats[5 * n_parcels + p];
+    const double cov = sxy - sx * sy / n, vx = sxx - sx * sx / n, vy = syy - sy * sy / n;
+    double r = cov / sqrt(vx * vy);
+    r = fmin(1.0, fmax(-1.0, r));  // NaN (constant input) propagates like scipy / torchmetrics
+    if (r_out) r_out[p] = static_cast<float>(r);
+    acc += r;
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0 && mean_out) mean_out[0] = static_cast<float>(v / static_cast<double>(n_parcels));
+  }
+}
+
+}  // namespace tribe
+
+using namespace tribe;
+
+extern "C" int tribe_mse_fwd_bwd(const float* pred, const float* target, float* loss_out, float* grad, float grad_scale, int64_t n,
+                                 double* partial, void* stream) {
+  if (!pred || !target || !loss_out || !partial || n <= 0) return set_error(TRIBE_EINVAL, "mse: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n / 4 + 1, 256 * 4, kMsePartials);
+  const float gscale = grad_scale * 2.0f / static_cast<float>(n);
+  mse_partial_kernel<<<grid, 256, 0, s>>>(pred, target, grad, gscale, n, partial);
+  TRIBE_CHECK_LAUNCH("mse_partial");
+  mse_final_kernel<<<1, 256, 0, s>>>(partial, grid, n, loss_out);
+  TRIBE_CHECK_LAUNCH("mse_final");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_pearson_stats(const float* pred, const float* target, int64_t n_rows, int64_t n_parcels, int64_t t_len, int64_t stride_b,
+                                   int64_t stride_p, int64_t stride_t, const int64_t* group, int64_t n_groups, double* stats, void* stream) {
+  if (!pred || !target || !stats || n_rows <= 0 || n_parcels <= 0 || t_len <= 0 || n_rows % t_len)
+    return set_error(TRIBE_EINVAL, "pearson_stats: bad arguments (n_rows must be a multiple of t_len)");
+  if (group && n_groups <= 0) return set_error(TRIBE_EINVAL, "pearson_stats: group given without n_groups");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long* g = reinterpret_cast<const long long*>(group);
+  if (t_len == 1 && stride_p == 1 && stride_b == n_parcels) {
+    const int64_t pblocks = (n_parcels + 1023) / 1024;
+    int64_t chunks = (148 * 8 + pblocks - 1) / pblocks;
+    const int64_t max_chunks = (n_rows + 4 * kInner - 1) / (4 * kInner);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > 65535) chunks = 65535;
+    int64_t rpb = (n_rows + chunks - 1) / chunks;
+    rpb = (rpb + kInner - 1) / kInner * kInner;
+    dim3 grid(static_cast<unsigned>(pblocks), static_cast<unsigned>((n_rows + rpb - 1) / rpb));
+    pearson_rowmajor_kernel<<<grid, 256, 0, s>>>(pred, target, n_rows, n_parcels, rpb, g, stats);
+    TRIBE_CHECK_LAUNCH("pearson_rowmajor");
+  } else {
+    const int64_t n_b = n_rows / t_len;
+    if (n_b > 65535) return set_error(TRIBE_EINVAL, "pearson_stats: more than 65535 strided blocks per call");
+    dim3 grid(static_cast<unsigned>((n_parcels + 7) / 8), static_cast<unsigned>(n_b));
+    pearson_strided_kernel<<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, t_len, stride_b, stride_p, stride_t, g, stats);
+    TRIBE_CHECK_LAUNCH("pearson_strided");
+  }
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_pearson_finalize(const double* stats, int64_t n_parcels, float* r, float* mean_out, void* stream) {
+  if (!stats || n_parcels <= 0 || (!r && !mean_out)) return set_error(TRIBE_EINVAL, "pearson_finalize: bad arguments");
+  pearson_finalize_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stats, n_parcels, r, mean_out);
+  TRIBE_CHECK_LAUNCH("pearson_finalize");
+  return TRIBE_OK;
+}

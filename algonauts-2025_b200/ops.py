@@ -1,0 +1,244 @@
+"""Thin torch-tensor wrappers over the C ABI (``include/tribe_b200.h``).  Every function launches hand-written sm_100a
+kernels on ``torch.cuda.current_stream()``; tensors must live on the current CUDA device.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+
+import torch
+
+from . import _lib
+from ._lib import TribeError, TribeGemm, TribeOperand, check
+
+EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_ROPE = 0, 1, 2, 3, 4
+_DT = {torch.float32: 0, torch.float64: 1, torch.bfloat16: 2, torch.float16: 3}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TribeError("tribe ops need CUDA tensors (there is no CPU path)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _need(t, dtype, name):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise TribeError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
+
+
+@dataclasses.dataclass
+class Operand:
+    """bf16 GEMM operand viewed as (inner, rows, batch); see TribeOperand in include/tribe_b200.h."""
+
+    t: torch.Tensor
+    inner: int
+    rows: int
+    row_stride: int
+    batch: int = 1
+    batch_stride: int = 0
+    mn_major: bool = False
+    inner_off: int = 0
+    zin_stride: int = 0
+    zdiv: int = 1
+    gather: torch.Tensor | None = None
+    elem_off: int = 0  # element offset added to the base pointer
+
+    def c(self) -> TribeOperand:
+        if self.t.dtype != torch.bfloat16:
+            raise TribeError("GEMM operands must be bf16")
+        o = TribeOperand()
+        o.ptr = self.t.data_ptr() + 2 * self.elem_off
+        o.inner, o.rows, o.batch = self.inner, self.rows, self.batch
+        o.row_stride, o.batch_stride = self.row_stride, self.batch_stride
+        o.mn_major, o.inner_off, o.zin_stride, o.zdiv = int(self.mn_major), self.inner_off, self.zin_stride, self.zdiv
+        o.gather = self.gather.data_ptr() if self.gather is not None else None
+        return o
+
+
+def kmajor(t: torch.Tensor, **kw) -> Operand:
+    """2-D row-major (rows, K) bf16 tensor as a K-major operand."""
+    assert t.dim() == 2 and t.stride(1) == 1
+    return Operand(t, inner=t.shape[1], rows=t.shape[0], row_stride=t.stride(0), **kw)
+
+
+def mnmajor(t: torch.Tensor, **kw) -> Operand:
+    """2-D row-major (K, MN) bf16 tensor as an MN-major operand (contraction along rows)."""
+    assert t.dim() == 2 and t.stride(1) == 1
+    return Operand(t, inner=t.shape[1], rows=t.shape[0], row_stride=t.stride(0), mn_major=True, **kw)
+
+
+def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, ldd: int, batch: int = 1, z_inner: int = 1,
+         d_zo: int = 0, d_zi: int = 0, d_off: int = 0, transposed: bool = False, epilogue: int = EPI_STORE, alpha: float = 1.0,
+         bias: torch.Tensor | None = None, bias_gathered: bool = False, bias_z_stride: int = 0,
+         res: torch.Tensor | None = None, ld_res: int = 0, res_row_mod: int = 0, rscale: torch.Tensor | None = None,
+         aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None, ld_aux: int = 0,
+         rope: torch.Tensor | None = None, rope_t: int = 0, rope_dim: int = 0, head_dim: int = 0, rope_cols: int = 0,
+         rope_sign: float = 1.0, kgroup: torch.Tensor | None = None, block_n: int = 0, probe=None) -> None:
+    """D[z] = epilogue(alpha * A[z] @ B[z]^T) on the tcgen05 GEMM.  ``out`` is bf16 or fp32."""
+    if out.dtype not in (torch.bfloat16, torch.float32) or not out.is_cuda:
+        raise TribeError("gemm output must be a CUDA bf16/fp32 tensor")
+    g = TribeGemm()
+    g.a, g.b = a.c(), b.c()
+    g.m, g.n, g.k, g.batch, g.z_inner = m, n, k, batch, z_inner
+    if kgroup is not None:
+        g.kgroup, g.kgroup_len = kgroup.data_ptr(), kgroup.numel()
+    g.d = out.data_ptr() + d_off * out.element_size()
+    g.d_f32, g.d_transposed = int(out.dtype == torch.float32), int(transposed)
+    g.ldd, g.d_zo_stride, g.d_zi_stride = ldd, d_zo, d_zi
+    g.epilogue, g.alpha = epilogue, alpha
+    for name, t, dt in (("bias", bias, torch.float32), ("res", res, torch.float32), ("rscale", rscale, torch.float32),
+                        ("aux_in", aux_in, torch.bfloat16), ("aux_out", aux_out, torch.bfloat16), ("rope", rope, torch.float32)):
+        if t is not None:
+            if t.dtype != dt or not t.is_cuda:
+                raise TribeError(f"gemm {name}: expected CUDA {dt}")
+            setattr(g, name, t.data_ptr())
+    g.bias_gathered, g.bias_z_stride = int(bias_gathered), bias_z_stride
+    g.ld_res, g.res_row_mod, g.ld_aux = ld_res, res_row_mod, ld_aux
+    g.rope_t, g.rope_dim, g.head_dim, g.rope_cols, g.rope_sign = rope_t, rope_dim, head_dim, rope_cols, rope_sign
+    g.block_n = block_n
+    lib = _lib.load()
+    if probe is None:
+        check(lib.tribe_gemm_bf16(ctypes.byref(g), _stream()), "tribe_gemm_bf16")
+    else:
+        check(lib.tribe_gemm_bf16_probe(ctypes.byref(g), _stream(), *probe), "tribe_gemm_bf16_probe")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> None:
+    """out (M, N) = x (M, K) @ w (N, K)^T (+ epilogue): the nn.Linear forward shape."""
+    gemm(kmajor(x), kmajor(w), out, x.shape[0], w.shape[0], x.shape[1], ldd=kw.pop("ldd", out.stride(0)), **kw)
+
+
+def ingest_features(x: torch.Tensor, out: torch.Tensor, col_off: int, layer_mean: bool) -> None:
+    """(B, L, D, T) any float dtype -> bf16 rows of out (B*T, ld) at column col_off (model.py:147-155)."""
+    if x.dim() == 3:
+        x = x.unsqueeze(1)
+    x = x.contiguous()
+    B, L, D, T = x.shape
+    _need(out, torch.bfloat16, "ingest out")
+    check(_lib.load().tribe_ingest_features(_ptr(x), _DT[x.dtype], B, L, D, T, int(layer_mean), _ptr(out), out.stride(0), col_off,
+                                            _stream()), "tribe_ingest_features")
+
+
+def scalenorm_fwd(x, g, y, rnorm) -> None:
+    _need(x, torch.float32, "scalenorm x"), _need(y, torch.bfloat16, "scalenorm y")
+    rows, dim = x.shape
+    check(_lib.load().tribe_scalenorm_fwd(_ptr(x), _ptr(g), _ptr(y), _ptr(rnorm), rows, dim, _stream()), "tribe_scalenorm_fwd")
+
+
+def sublayer_bwd(dy_out, d_xn, x_in, rnorm, g, rs, dx_in, dx_in_bf16, d_rs, d_g) -> None:
+    rows, dim = x_in.shape
+    check(_lib.load().tribe_sublayer_bwd(_ptr(dy_out), _ptr(d_xn), _ptr(x_in), _ptr(rnorm), _ptr(g), _ptr(rs), _ptr(dx_in),
+                                         _ptr(dx_in_bf16), _ptr(d_rs), _ptr(d_g), rows, dim, _stream()), "tribe_sublayer_bwd")
+
+
+def softmax_fwd(s, p, n_valid) -> None:
+    _need(s, torch.float32, "softmax s"), _need(p, torch.bfloat16, "softmax p")
+    ld = s.shape[-1]
+    check(_lib.load().tribe_softmax_fwd(_ptr(s), _ptr(p), s.numel() // ld, n_valid, ld, _stream()), "tribe_softmax_fwd")
+
+
+def softmax_bwd(p, dp, ds, scale, n_valid) -> None:
+    ld = p.shape[-1]
+    check(_lib.load().tribe_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), scale, p.numel() // ld, n_valid, ld, _stream()), "tribe_softmax_bwd")
+
+
+def colsum(x, out, y=None, accumulate=False) -> None:
+    """out[c] (+)= sum_r x[r, c] (* y[r, c])."""
+    rows, cols = x.shape
+    check(_lib.load().tribe_colsum(_ptr(x), _DT[x.dtype], _ptr(y), _DT[y.dtype] if y is not None else 0, _ptr(out), rows, cols,
+                                   x.stride(0), int(accumulate), _stream()), "tribe_colsum")
+
+
+def cast_f32_bf16(src, dst) -> None:
+    _need(src, torch.float32, "cast src"), _need(dst, torch.bfloat16, "cast dst")
+    check(_lib.load().tribe_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "tribe_cast_f32_bf16")
+
+
+def axpby(src, dst, a=1.0, accumulate=False) -> None:
+    check(_lib.load().tribe_axpby_f32(_ptr(src), _ptr(dst), a, int(accumulate), src.numel(), _stream()), "tribe_axpby_f32")
+
+
+def adaptive_avg_pool_fwd(x, t_out) -> torch.Tensor:
+    """fp32 (..., T) -> (..., t_out) with nn.AdaptiveAvgPool1d windows (model.py:60)."""
+    x = x.contiguous()
+    _need(x, torch.float32, "pool x")
+    y = torch.empty(*x.shape[:-1], t_out, device=x.device, dtype=torch.float32)
+    check(_lib.load().tribe_adaptive_avg_pool_fwd(_ptr(x), _ptr(y), x.numel() // x.shape[-1], x.shape[-1], t_out, _stream()),
+          "tribe_adaptive_avg_pool_fwd")
+    return y
+
+
+def adaptive_avg_pool_bwd(dy, t_in) -> torch.Tensor:
+    dy = dy.contiguous()
+    _need(dy, torch.float32, "pool dy")
+    dx = torch.empty(*dy.shape[:-1], t_in, device=dy.device, dtype=torch.float32)
+    check(_lib.load().tribe_adaptive_avg_pool_bwd(_ptr(dy), _ptr(dx), dy.numel() // dy.shape[-1], t_in, dy.shape[-1], _stream()),
+          "tribe_adaptive_avg_pool_bwd")
+    return dx
+
+
+def token_pool_fwd(x, y, B, t_in, t_out, C) -> None:
+    check(_lib.load().tribe_token_pool_fwd(_ptr(x), _ptr(y), B, t_in, t_out, C, _stream()), "tribe_token_pool_fwd")
+
+
+def token_pool_bwd(dy, dx, B, t_in, t_out, C) -> None:
+    check(_lib.load().tribe_token_pool_bwd(_ptr(dy), _DT[dy.dtype], _ptr(dx), B, t_in, t_out, C, _stream()), "tribe_token_pool_bwd")
+
+
+def transpose_cast_bot(x, y) -> None:
+    B, O, T = x.shape
+    _need(x, torch.float32, "transpose x")
+    check(_lib.load().tribe_transpose_cast_bot(_ptr(x), _ptr(y), B, O, T, _stream()), "tribe_transpose_cast_bot")
+
+
+def subject_bias_grad(dy, subjects, d_bias, B, T, O, n_subjects) -> None:
+    check(_lib.load().tribe_subject_bias_grad(_ptr(dy), _ptr(subjects), _ptr(d_bias), B, T, O, n_subjects, _stream()),
+          "tribe_subject_bias_grad")
+
+
+def check_subjects(subjects, n_subjects, flag) -> None:
+    check(_lib.load().tribe_check_subjects(_ptr(subjects), subjects.numel(), n_subjects, _ptr(flag), _stream()), "tribe_check_subjects")
+
+
+def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):
+    """nn.MSELoss forward (+ gradient wrt pred in the same pass).  Returns (loss[1] fp32, grad or None)."""
+    _need(pred, torch.float32, "mse pred"), _need(target, torch.float32, "mse target")
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if want_grad else None
+    partial = torch.empty(1024, device=pred.device, dtype=torch.float64)
+    check(_lib.load().tribe_mse_fwd_bwd(_ptr(pred), _ptr(target), _ptr(loss), _ptr(grad), grad_scale, pred.numel(), _ptr(partial),
+                                        _stream()), "tribe_mse_fwd_bwd")
+    return loss, grad
+
+
+def pearson_stats(pred, target, stats, *, layout: str, group=None, n_groups: int = 1) -> None:
+    """Accumulate per-parcel sufficient statistics into ``stats`` (fp64 [n_groups, 6, O]).
+
+    layout "no": pred/target are row-major (N, O).  layout "bdt": they are (B, D, T) and rows are the flattened
+    ``(b t)`` of ``rearrange(x, "b d t -> (b t) d")`` (pl_module.py:54-55, main.py:472-473) without materialising it."""
+    _need(pred, torch.float32, "pearson pred"), _need(target, torch.float32, "pearson target")
+    if stats.dtype != torch.float64:
+        raise TribeError("pearson stats must be fp64")
+    if layout == "no":
+        n, o = pred.shape
+        args = (n, o, 1, o, 1, 1)
+    elif layout == "bdt":
+        b, d, t = pred.shape
+        args = (b * t, d, t, d * t, t, 1)
+    else:
+        raise TribeError(f"unknown layout {layout}")
+    check(_lib.load().tribe_pearson_stats(_ptr(pred), _ptr(target), *args, _ptr(group), n_groups if group is not None else 0,
+                                          _ptr(stats), _stream()), "tribe_pearson_stats")
+
+
+def pearson_finalize(stats_one_group, want_mean=False):
+    o = stats_one_group.shape[-1]
+    r = torch.empty(o, device=stats_one_group.device, dtype=torch.float32)
+    mean = torch.empty(1, device=r.device, dtype=torch.float32) if want_mean else None
+    check(_lib.load().tribe_pearson_finalize(_ptr(stats_one_group), o, _ptr(r), _ptr(mean), _stream()), "tribe_pearson_finalize")
+    return r, mean

@@ -1,0 +1,194 @@
+/* tribe_b200.h — C ABI of libtribe_b200.so: the B200 (sm_100a) kernels behind TRIBE's FmriEncoder hot path.
+ *
+ * The reference (vovw/algonauts-2025) is pure Python/PyTorch and has no FFI; every entry point below replaces one
+ * implicit ATen/cuBLAS call sequence of the reference (cited per function, paths relative to the reference root).
+ * Conventions:
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless the name says host; no torch types;
+ *   - buffers are owned by the caller (torch's caching allocator on the Python side); kernels never allocate;
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, a negative TRIBE_E* code or a positive cudaError_t otherwise; no exceptions cross
+ *     the ABI; tribe_last_error() returns a static description of the last failure on the calling thread;
+ *   - bf16 buffers are `uint16_t`-sized elements (__nv_bfloat16), row-major unless stated.
+ */
+#ifndef TRIBE_B200_H_
+#define TRIBE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRIBE_OK 0
+#define TRIBE_EINVAL (-1)   /* bad argument (shape / alignment / unsupported combination) */
+#define TRIBE_EDRIVER (-2)  /* CUDA driver entry point (cuTensorMapEncodeTiled) unavailable */
+#define TRIBE_ETMAP (-3)    /* tensor-map encoding failed */
+
+const char* tribe_last_error(void);
+int tribe_abi_version(void);
+/* Number of kernels launched through this library since load (bench.py's `gpu_launches`). */
+int64_t tribe_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM / TMA GEMM:  D[z] = epilogue( alpha * A[z] (M x K) * B[z]^T (N x K) )
+ * Replaces every dense contraction of the path: projector nn.Linear (algonauts2025/model.py:157), the
+ * x_transformers Encoder's to_q/to_k/to_v/to_out/ff linears and attention einsums (model.py:173), the SubjectLayers
+ * gather + einsum (modeling_utils/modeling_utils/models/common.py:61-66), InfoNCE logits (model.py:216), and their
+ * autograd backward GEMMs.
+ *
+ * Operands are bf16 in global memory described as 3-D tensors (inner, row, batch):
+ *   K-major  operand (mn_major=0): inner = K (contiguous), row = M or N index.
+ *   MN-major operand (mn_major=1): inner = M or N (contiguous), row = K index.
+ * `inner_off` / `zin_stride` shift the inner coordinate (e.g. head h of a packed [tokens, 3*H*dh] qkv buffer);
+ * batch coordinate of z is  gather ? gather[z / zdiv] : z / zdiv.
+ */
+typedef struct TribeOperand {
+  const void* ptr;       /* bf16 */
+  int64_t inner;         /* extent of the contiguous dimension (elements) */
+  int64_t rows;          /* extent of dim 1 */
+  int64_t batch;         /* extent of dim 2 (>= 1) */
+  int64_t row_stride;    /* elements; *2 bytes must be a multiple of 16 */
+  int64_t batch_stride;  /* elements; *2 bytes must be a multiple of 16 (ignored when batch == 1) */
+  int32_t mn_major;      /* 0: K-major, 1: MN-major */
+  int32_t inner_off;     /* added to the inner coordinate */
+  int32_t zin_stride;    /* inner coordinate += (z % z_inner) * zin_stride */
+  int32_t zdiv;          /* batch coordinate = z / zdiv (>= 1) */
+  const int64_t* gather; /* optional: batch coordinate = gather[z / zdiv] (subject ids, common.py:61) */
+} TribeOperand;
+
+enum TribeEpilogue {
+  TRIBE_EPI_STORE = 0,     /* D = alpha*acc (+bias)                                                     */
+  TRIBE_EPI_GELU = 1,      /* aux_out = bf16(acc+bias); D = gelu_erf(acc+bias)        (FF up-projection) */
+  TRIBE_EPI_RESIDUAL = 2,  /* D = acc (+bias) + res[row % res_row_mod] * (rscale ? rscale[col] : 1)      */
+  TRIBE_EPI_GELU_BWD = 3,  /* D = acc * gelu_erf'(aux_in)                                                */
+  TRIBE_EPI_ROPE = 4       /* D = rotate(acc): interleaved-pair rotary on the first rope_dim dims of every
+                              head_dim-wide head for columns < rope_cols; rope_sign=-1 applies the transpose */
+};
+
+typedef struct TribeGemm {
+  TribeOperand a, b;
+  int32_t m, n, k;        /* per-batch problem size */
+  int32_t batch;          /* number of z */
+  int32_t z_inner;        /* z = zo * z_inner + zi (>= 1) */
+  /* K-gather (grouped wgrad of SubjectLayers): when kgroup != NULL the contraction runs over kgroup_len batches of
+   * K each, taking batch j only if kgroup[j] == z; operands' batch coordinate is then j (zdiv/gather ignored). */
+  const int64_t* kgroup;
+  int32_t kgroup_len;
+  /* output */
+  void* d;
+  int32_t d_f32;          /* 0: bf16, 1: fp32 */
+  int32_t d_transposed;   /* 0: d[row*ldd + col], 1: d[col*ldd + row] */
+  int64_t ldd, d_zo_stride, d_zi_stride; /* elements */
+  /* epilogue */
+  int32_t epilogue;       /* enum TribeEpilogue */
+  float alpha;
+  const float* bias;      /* optional fp32 [n] (+ bias_z_stride * batch coordinate of B when bias_gathered) */
+  int32_t bias_gathered;
+  int64_t bias_z_stride;
+  const float* res;       /* fp32 residual, row-major ld_res */
+  int64_t ld_res;
+  int32_t res_row_mod;    /* residual row = row % res_row_mod (0: row) */
+  const float* rscale;    /* optional fp32 [n] */
+  const void* aux_in;     /* bf16 [m, ld_aux] (GELU_BWD) */
+  void* aux_out;          /* bf16 [m, ld_aux] (GELU) */
+  int64_t ld_aux;
+  const float* rope;      /* fp32 (cos, sin) pairs [rope_t][rope_dim/2][2] */
+  int32_t rope_t;         /* position = row % rope_t */
+  int32_t rope_dim, head_dim, rope_cols;
+  float rope_sign;
+  int32_t block_n;        /* 0: auto; else one of 128, 160, 192, 256 */
+} TribeGemm;
+
+int tribe_gemm_bf16(const TribeGemm* g, void* stream);
+
+/* Descriptor-probe variant used by tests only: overrides the UMMA shared-memory descriptor byte offsets
+ * (lbo/sbo for K-major and MN-major operands); pass 0 to keep the defaults. */
+int tribe_gemm_bf16_probe(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t k_sbo, uint32_t mn_lbo, uint32_t mn_sbo);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bandwidth kernels
+ */
+
+/* Feature ingest (model.py:147-155): x (B, L, D, T) fp32/fp64/bf16, T contiguous  ->  out bf16 (B*T, ld_out) with
+ * out[b*T+t, col_off + l*D + d] = x[b,l,d,t]  (layer_mean=0, "cat")  or  mean_l x[b,l,d,t] at col_off + d (layer_mean=1).
+ * src_dtype: 0 fp32, 1 fp64, 2 bf16, 3 fp16. */
+int tribe_ingest_features(const void* x, int32_t src_dtype, int64_t B, int64_t L, int64_t D, int64_t T, int32_t layer_mean,
+                          void* out_bf16, int64_t ld_out, int64_t col_off, void* stream);
+
+/* ScaleNorm forward (x_transformers ScaleNorm, see oracle/xt_encoder.py): y = x / max(||x||, 1e-12) * sqrt(dim) * g[0].
+ * x fp32 (rows, dim) -> y bf16 (rows, dim), rnorm fp32 (rows) = 1 / max(||x||, eps). */
+int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, void* stream);
+
+/* Sub-layer backward tail: given dy_out (fp32 grad wrt the sub-layer output x_out = branch + x_in*rs) and d_xn (bf16
+ * grad wrt the ScaleNorm output), produces dx_in (fp32 and bf16 copies), and accumulates d_rs (fp32 [dim]) and d_g
+ * (fp32 [1]) atomically.  d_xn may be NULL (final norm handled by tribe_scalenorm_bwd). rs may be NULL (=1). */
+int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, const float* x_in, const float* rnorm, const float* g,
+                       const float* rs, float* dx_in, void* dx_in_bf16, float* d_rs, float* d_g, int64_t rows, int64_t dim,
+                       void* stream);
+
+/* Row softmax over the first n_valid of ld columns: s fp32 (rows, ld) -> p bf16 (rows, ld), columns >= n_valid zeroed. */
+int tribe_softmax_fwd(const float* s, void* p_bf16, int64_t rows, int64_t n_valid, int64_t ld, void* stream);
+/* ds = p * (dp - sum_j p_j dp_j) * scale -> bf16 (rows, ld), padded columns zeroed. */
+int tribe_softmax_bwd(const void* p_bf16, const float* dp, void* ds_bf16, float scale, int64_t rows, int64_t n_valid, int64_t ld,
+                      void* stream);
+
+/* Column sums (bias / residual-scale gradients): out[c] (+)= sum_r x[r, c] (* y[r, c] when y != NULL).
+ * x_dtype/y_dtype: 0 fp32, 2 bf16.  accumulate: 0 overwrite (out must be zeroed by the call), 1 add. */
+int tribe_colsum(const void* x, int32_t x_dtype, const void* y, int32_t y_dtype, float* out, int64_t rows, int64_t cols,
+                 int64_t ld, int32_t accumulate, void* stream);
+
+/* fp32 -> bf16 cast of a flat parameter buffer (bf16 shadow weights after the optimizer step). */
+int tribe_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* dst_f32[i] = a * src[i] (+ dst when accumulate) — gradient bucket scaling / accumulation. */
+int tribe_axpby_f32(const float* src, float* dst, float a, int32_t accumulate, int64_t n, void* stream);
+
+/* AdaptiveAvgPool1d over the LAST dim (nn.AdaptiveAvgPool1d, model.py:60,119-122): x fp32 (rows, t_in) ->
+ * y fp32 (rows, t_out), window i = [floor(i*t_in/t_out), ceil((i+1)*t_in/t_out)). */
+int tribe_adaptive_avg_pool_fwd(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, void* stream);
+int tribe_adaptive_avg_pool_bwd(const float* dy, float* dx, int64_t rows, int64_t t_in, int64_t t_out, void* stream);
+/* Same windows along the TOKEN dim of a token-major activation: x bf16 (B, t_in, C) -> y bf16 (B, t_out, C)
+ * (pool-before-readout: pool and SubjectLayers commute). */
+int tribe_token_pool_fwd(const void* x_bf16, void* y_bf16, int64_t B, int64_t t_in, int64_t t_out, int64_t C, void* stream);
+/* dx fp32 (B, t_in, C) = scatter of dy (bf16 or fp32; B, t_out, C) / window length. */
+int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, float* dx, int64_t B, int64_t t_in, int64_t t_out, int64_t C,
+                         void* stream);
+
+/* (B, O, T) fp32 -> (B, T, O) bf16 transpose-cast (gradient of the predictions into the readout's GEMM layout). */
+int tribe_transpose_cast_bot(const float* x, void* y_bf16, int64_t B, int64_t O, int64_t T, void* stream);
+
+/* SubjectLayers bias gradient: d_bias[subject[b], o] += sum_t dy[b, t, o]   (dy bf16 (B, T, O)). */
+int tribe_subject_bias_grad(const void* dy_bf16, const int64_t* subjects, float* d_bias, int64_t B, int64_t T, int64_t O,
+                            int64_t n_subjects, void* stream);
+
+/* max(subjects) >= n_subjects check of SubjectLayers.forward (common.py:53-55) without a host sync on the hot path:
+ * writes 1 into *flag_out (device int32) when violated. */
+int tribe_check_subjects(const int64_t* subjects, int64_t n, int64_t n_subjects, int32_t* flag_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Loss / evaluation reductions
+ */
+
+/* nn.MSELoss (pl_module.py:56 via losses/base.py:43-59), fused forward + gradient:
+ * loss_out[0] = mean((pred-target)^2);  grad (optional, fp32, same shape) = grad_scale * 2 (pred-target) / n.
+ * partial: workspace of >= 1024 doubles. */
+int tribe_mse_fwd_bwd(const float* pred, const float* target, float* loss_out, float* grad, float grad_scale, int64_t n,
+                      double* partial, void* stream);
+
+/* Per-parcel Pearson sufficient statistics over rows of (n_rows, n_parcels)-shaped matrices (evaluation path:
+ * main.py:459-477 scipy loop and pl_module.py:93-106 torchmetrics update).  The matrices are addressed as
+ * element(r, p) = base[(r / t_len) * stride_b + p * stride_p + (r % t_len) * stride_t], which covers both the
+ * flattened (b t) x d view of a (B, D, T) tensor (stride_b=D*T, stride_p=T, stride_t=1, t_len=T) and a plain
+ * row-major (N, O) matrix (t_len=1, stride_b=O, stride_p=1).
+ * stats: fp64 [6][n_parcels] = n, sum_x, sum_y, sum_xx, sum_yy, sum_xy (shifted by `shift_x/shift_y` per parcel when
+ * non-NULL for conditioning); accumulated (+=) so that batches can be streamed; group: optional int64 per row/t_len
+ * block selecting stats + group*6*n_parcels (GroupedMetric, metrics/base.py:52-78). */
+int tribe_pearson_stats(const float* pred, const float* target, int64_t n_rows, int64_t n_parcels, int64_t t_len,
+                        int64_t stride_b, int64_t stride_p, int64_t stride_t, const int64_t* group, int64_t n_groups,
+                        double* stats, void* stream);
+/* r[p] = clamp(cov / sqrt(var_x var_y), -1, 1) from the statistics; r fp32 [n_parcels]; mean_out optional fp32 [1]. */
+int tribe_pearson_finalize(const double* stats, int64_t n_parcels, float* r, float* mean_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIBE_B200_H_ */

@@ -30,6 +30,15 @@ def assert_close_bf16(out, ref, rtol=1e-2, atol=None):
 
 
 # ------------------------------------------------------------------------------------------------------------ GEMM
+def _mn_operand(x):
+    """(MN, K) matrix stored transposed as (K, MN) with a 16-byte aligned (padded) row stride: an MN-major operand."""
+    mn, k = x.shape
+    pad = (mn + 7) // 8 * 8
+    store = torch.zeros(k, pad, device=x.device, dtype=x.dtype)
+    store[:, :mn] = x.t()
+    return ops.Operand(store, inner=mn, rows=k, row_stride=pad, mn_major=True)
+
+
 @pytest.mark.parametrize("a_mn", [False, True])
 @pytest.mark.parametrize("b_mn", [False, True])
 @pytest.mark.parametrize("bn", [0, 128, 160, 192, 256])
@@ -39,8 +48,8 @@ def test_gemm_majors_and_tiles(a_mn, b_mn, bn):
     torch.manual_seed(1)
     m, n, k = 333, 520, 200  # ragged in every dimension
     A, B = bf(torch.randn(m, k, device=DEV)), bf(torch.randn(n, k, device=DEV))
-    a_op = ops.mnmajor(A.t().contiguous()) if a_mn else ops.kmajor(A)
-    b_op = ops.mnmajor(B.t().contiguous()) if b_mn else ops.kmajor(B)
+    a_op = _mn_operand(A) if a_mn else ops.kmajor(A)
+    b_op = _mn_operand(B) if b_mn else ops.kmajor(B)
     out = torch.full((m, n), float("nan"), device=DEV)
     ops.gemm(a_op, b_op, out, m, n, k, ldd=n, block_n=bn)
     assert_close_bf16(out, A.float() @ B.float().t())

@@ -49,8 +49,15 @@ def child(start: int):
         A = torch.randn(m, k, device="cuda").bfloat16()
         B = torch.randn(n, k, device="cuda").bfloat16()
         ref = A.float() @ B.float().t()
-        a_op = ops.mnmajor(A.t().contiguous()) if c["a_mn"] else ops.kmajor(A)
-        b_op = ops.mnmajor(B.t().contiguous()) if c["b_mn"] else ops.kmajor(B)
+        def mn_op(x):
+            mn, kk = x.shape
+            pad = (mn + 7) // 8 * 8
+            store = torch.zeros(kk, pad, device="cuda", dtype=x.dtype)
+            store[:, :mn] = x.t()
+            return ops.Operand(store, inner=mn, rows=kk, row_stride=pad, mn_major=True)
+
+        a_op = mn_op(A) if c["a_mn"] else ops.kmajor(A)
+        b_op = mn_op(B) if c["b_mn"] else ops.kmajor(B)
         out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.float32)
         ops.gemm(a_op, b_op, out, m, n, k, ldd=n, block_n=c["bn"], probe=c["probe"])
         torch.cuda.synchronize()

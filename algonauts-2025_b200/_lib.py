@@ -34,13 +34,27 @@ def _nvcc() -> str:
     raise TribeError("nvcc not found: cannot build libtribe_b200.so")
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+HASH_PATH = os.path.join(CSRC, "libtribe_b200.srchash")
+
+
+def _source_hash() -> str:
+    import hashlib
+
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     deps.append(os.path.join(INCLUDE, "tribe_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    h = hashlib.sha1(" ".join(NVCC_FLAGS[:8]).encode())
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    """True when the library is missing or was built from different sources (content hash, not mtimes: the snapshot
+    copied to the GPU box does not preserve them)."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    return open(HASH_PATH).read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -68,6 +82,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise TribeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(_source_hash())
     return LIB_PATH
 
 
@@ -85,7 +101,7 @@ class TribeGemm(ctypes.Structure):
                 ("z_inner", c_i32), ("kgroup", c_vp), ("kgroup_len", c_i32), ("d", c_vp), ("d_f32", c_i32),
                 ("d_transposed", c_i32), ("ldd", c_i64), ("d_zo_stride", c_i64), ("d_zi_stride", c_i64),
                 ("epilogue", c_i32), ("alpha", c_f32), ("bias", c_vp), ("bias_gathered", c_i32),
-                ("bias_z_stride", c_i64), ("res", c_vp), ("ld_res", c_i64), ("res_row_mod", c_i32), ("rscale", c_vp),
+                ("bias_z_stride", c_i64), ("res", c_vp), ("ld_res", c_i64), ("res_row_mod", c_i32), ("res_batched", c_i32), ("rscale", c_vp),
                 ("aux_in", c_vp), ("aux_out", c_vp), ("ld_aux", c_i64), ("rope", c_vp), ("rope_t", c_i32),
                 ("rope_dim", c_i32), ("head_dim", c_i32), ("rope_cols", c_i32), ("rope_sign", c_f32),
                 ("block_n", c_i32)]
@@ -106,7 +122,8 @@ _SIGS = {
     "tribe_adaptive_avg_pool_fwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
     "tribe_adaptive_avg_pool_bwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
     "tribe_token_pool_fwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
-    "tribe_token_pool_bwd": [c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
+    "tribe_token_pool_bwd": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp],
+    "tribe_add_rows_periodic": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
     "tribe_transpose_cast_bot": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
     "tribe_subject_bias_grad": [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
     "tribe_check_subjects": [c_vp, c_i64, c_i64, c_vp, c_vp],

@@ -419,8 +419,15 @@ __global__ void __launch_bounds__(256) token_pool_fwd_kernel(const __nv_bfloat16
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict__ dy, float* __restrict__ dx, int t_in, int t_out, int64_t C) {
+template <typename TO>
+__device__ __forceinline__ TO from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict__ dy, TO* __restrict__ dx, int t_in, int t_out, int64_t C) {
   const int b = blockIdx.y, t = blockIdx.x;
   int i_lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
   int i_hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);
@@ -431,7 +438,19 @@ __global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict
       const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
       if (t >= s && t < e) acc += to_f32<T>(dy[(static_cast<int64_t>(b) * t_out + i) * C + c]) / static_cast<float>(e - s);
     }
-    dx[(static_cast<int64_t>(b) * t_in + t) * C + c] = acc;
+    dx[(static_cast<int64_t>(b) * t_in + t) * C + c] = from_f32<TO>(acc);
+  }
+}
+
+// out[r, c] = (x ? x[r, c] : 0) + pos[r % row_mod, c]   for c in [0, cols)   (positional embedding add, model.py:169-170)
+__global__ void __launch_bounds__(256) add_rows_periodic_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ pos,
+                                                                int64_t ld_pos, float* __restrict__ out, int64_t ld_out, int64_t rows,
+                                                                int64_t cols, int64_t row_mod) {
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const float base = x ? x[r * ld_x + c] : 0.f;
+    out[r * ld_out + c] = base + __ldg(pos + (r % row_mod) * ld_pos + c);
   }
 }
 
@@ -628,14 +647,28 @@ extern "C" int tribe_token_pool_fwd(const void* x_bf16, void* y_bf16, int64_t B,
   return TRIBE_OK;
 }
 
-extern "C" int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, float* dx, int64_t B, int64_t t_in, int64_t t_out, int64_t C, void* stream) {
+extern "C" int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype, int64_t B, int64_t t_in, int64_t t_out,
+                                    int64_t C, void* stream) {
   if (!dy || !dx || B <= 0 || t_in <= 0 || t_out <= 0 || C <= 0 || B > 65535) return set_error(TRIBE_EINVAL, "token_pool_bwd: bad arguments");
   dim3 grid(static_cast<unsigned>(t_in), static_cast<unsigned>(B));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dy_dtype == 0) token_pool_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dy), dx, static_cast<int>(t_in), static_cast<int>(t_out), C);
-  else if (dy_dtype == 2) token_pool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), dx, static_cast<int>(t_in), static_cast<int>(t_out), C);
+  using bf = __nv_bfloat16;
+  const int ti = static_cast<int>(t_in), to = static_cast<int>(t_out);
+  if (dy_dtype == 0 && dx_dtype == 0) token_pool_bwd_kernel<float, float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dy), reinterpret_cast<float*>(dx), ti, to, C);
+  else if (dy_dtype == 2 && dx_dtype == 0) token_pool_bwd_kernel<bf, float><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(dy), reinterpret_cast<float*>(dx), ti, to, C);
+  else if (dy_dtype == 0 && dx_dtype == 2) token_pool_bwd_kernel<float, bf><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dy), reinterpret_cast<bf*>(dx), ti, to, C);
+  else if (dy_dtype == 2 && dx_dtype == 2) token_pool_bwd_kernel<bf, bf><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(dy), reinterpret_cast<bf*>(dx), ti, to, C);
   else return set_error(TRIBE_EINVAL, "token_pool_bwd: unsupported dtype");
   TRIBE_CHECK_LAUNCH("token_pool_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_add_rows_periodic(const float* x, int64_t ld_x, const float* pos, int64_t ld_pos, float* out, int64_t ld_out, int64_t rows,
+                                       int64_t cols, int64_t row_mod, void* stream) {
+  if (!pos || !out || rows <= 0 || cols <= 0 || row_mod <= 0) return set_error(TRIBE_EINVAL, "add_rows_periodic: bad arguments");
+  add_rows_periodic_kernel<<<grid_for(rows * cols, 256, kMaxBlocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ld_x, pos, ld_pos, out, ld_out,
+                                                                                                                 rows, cols, row_mod);
+  TRIBE_CHECK_LAUNCH("add_rows_periodic");
   return TRIBE_OK;
 }
 

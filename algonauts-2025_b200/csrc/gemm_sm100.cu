@@ -50,7 +50,7 @@ struct alignas(64) GemmKParams {
   long long bias_z_stride;
   const float* res;
   long long ld_res;
-  int res_row_mod;
+  int res_row_mod, res_batched;
   const float* rscale;
   const __nv_bfloat16* aux_in;
   __nv_bfloat16* aux_out;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           }
         } else if (p.epilogue == TRIBE_EPI_RESIDUAL) {
           if (row_ok) {
-            const float* rp = p.res + static_cast<long long>(res_row) * p.ld_res + col0;
+            const float* rp = p.res + (p.res_batched ? zoff : 0) + static_cast<long long>(res_row) * p.ld_res + col0;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -577,7 +577,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.ldd = g->ldd, kp.d_zo = g->d_zo_stride, kp.d_zi = g->d_zi_stride;
   kp.epilogue = g->epilogue, kp.alpha = g->alpha;
   kp.bias = g->bias, kp.bias_gathered = g->bias_gathered, kp.bias_z_stride = g->bias_z_stride;
-  kp.res = g->res, kp.ld_res = g->ld_res, kp.res_row_mod = g->res_row_mod, kp.rscale = g->rscale;
+  kp.res = g->res, kp.ld_res = g->ld_res, kp.res_row_mod = g->res_row_mod, kp.res_batched = g->res_batched, kp.rscale = g->rscale;
   kp.aux_in = reinterpret_cast<const __nv_bfloat16*>(g->aux_in);
   kp.aux_out = reinterpret_cast<__nv_bfloat16*>(g->aux_out), kp.ld_aux = g->ld_aux;
   kp.rope = reinterpret_cast<const float2*>(g->rope);

@@ -1,0 +1,152 @@
+"""Evaluation metrics of the hot path on the Pearson-statistics kernels.
+
+Mirrors (reference paths): ``MultidimPearsonCorrCoef`` and ``GroupedMetric`` modeling_utils/modeling_utils/metrics/
+base.py:26-29, 39-91 (torchmetrics ``PearsonCorrCoef`` semantics, oracle/tm_pearson.py); ``compute_multidim_pearson``
+algonauts2025/main.py:459-477 (the per-parcel ``scipy.stats.pearsonr`` loop).  State = per-parcel fp64 sufficient
+statistics [n, Σx, Σy, Σx², Σy², Σxy] accumulated on the device by ``tribe_pearson_stats``; under ``torch.distributed``
+the statistics are all-reduced (one 48 KB message) instead of torchmetrics' state gather."""
+from __future__ import annotations
+
+import typing as tp
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import TribeError
+
+
+def _dist_sum_(t: torch.Tensor) -> None:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+class MultidimPearsonCorrCoef(nn.Module):
+    """``torchmetrics.PearsonCorrCoef(num_outputs=O)`` whose ``compute()`` returns the mean over outputs."""
+
+    is_differentiable = False
+    higher_is_better = True
+
+    def __init__(self, num_outputs: int = 1, **kwargs: tp.Any) -> None:
+        super().__init__()
+        self.num_outputs = num_outputs
+        self.register_buffer("stats", torch.zeros(1, 6, num_outputs, dtype=torch.float64), persistent=False)
+
+    def _dev(self, like: torch.Tensor):
+        if not like.is_cuda:
+            raise TribeError("Pearson metric needs CUDA tensors (no CPU fallback)")
+        if self.stats.device != like.device:
+            self.stats = self.stats.to(like.device)
+
+    def update(self, preds: torch.Tensor, target: torch.Tensor) -> None:
+        """preds/target: (N, O) — the flattened ``(b t) d`` matrices of pl_module.py:54-55."""
+        self._dev(preds)
+        if preds.ndim == 1:
+            preds, target = preds[:, None], target[:, None]
+        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="no")
+
+    def update_bdt(self, preds: torch.Tensor, target: torch.Tensor) -> None:
+        """Same statistics straight from (B, D, T) tensors (no materialised rearrange)."""
+        self._dev(preds)
+        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="bdt")
+
+    def per_output(self) -> torch.Tensor:
+        st = self.stats.clone()
+        _dist_sum_(st)
+        r, _ = ops.pearson_finalize(st[0])
+        return r
+
+    def compute(self) -> torch.Tensor:
+        st = self.stats.clone()
+        _dist_sum_(st)
+        _, mean = ops.pearson_finalize(st[0], want_mean=True)
+        return mean[0]
+
+    def reset(self) -> None:
+        self.stats.zero_()
+
+    def forward(self, preds, target):
+        self.update(preds, target)
+        return self.compute()
+
+
+class GroupedMetric(nn.Module):
+    """Per-group (subject) Pearson: one statistics block per group id (metrics/base.py:39-91).  ``compute()`` returns
+    ``{str(group_id): float}`` for every group that received samples."""
+
+    MAX_GROUPS = 64
+
+    def __init__(self, metric_name: str = "MultidimPearsonCorrCoef", kwargs: dict[str, tp.Any] | None = None) -> None:
+        super().__init__()
+        if metric_name != "MultidimPearsonCorrCoef":
+            raise NotImplementedError(f"GroupedMetric({metric_name}) is not on the TRIBE path (defaults.py:113-118)")
+        self.metric_kwargs = kwargs or {}
+        self.num_outputs = int(self.metric_kwargs.get("num_outputs", 1))
+        self.register_buffer("stats", torch.zeros(self.MAX_GROUPS, 6, self.num_outputs, dtype=torch.float64), persistent=False)
+        self.register_buffer("bad_group", torch.zeros(1, dtype=torch.int32), persistent=False)
+
+    def _prep(self, preds, groups, n_expected):
+        if not preds.is_cuda:
+            raise TribeError("GroupedMetric needs CUDA tensors (no CPU fallback)")
+        if self.stats.device != preds.device:
+            self.stats, self.bad_group = self.stats.to(preds.device), self.bad_group.to(preds.device)
+        if groups is None:
+            groups = torch.zeros(n_expected, dtype=torch.int64, device=preds.device)
+        groups = groups.flatten().to(preds.device, torch.int64).contiguous()
+        assert len(groups) == n_expected, f"Groups must be the same shape as preds/target, got {groups.shape} and {preds.shape}"
+        ops.check_subjects(groups, self.MAX_GROUPS, self.bad_group)
+        return groups
+
+    def update(self, preds: torch.Tensor, target: torch.Tensor, groups: tp.Optional[torch.Tensor] = None) -> None:
+        groups = self._prep(preds, groups, preds.shape[0])
+        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="no",
+                          group=groups, n_groups=self.MAX_GROUPS)
+
+    def update_bdt(self, preds: torch.Tensor, target: torch.Tensor, groups: tp.Optional[torch.Tensor] = None) -> None:
+        groups = self._prep(preds, groups, preds.shape[0])
+        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="bdt",
+                          group=groups, n_groups=self.MAX_GROUPS)
+
+    def compute(self) -> dict[str, float]:
+        if int(self.bad_group.item()):
+            raise TribeError(f"GroupedMetric saw a group id outside [0, {self.MAX_GROUPS})")
+        st = self.stats.clone()
+        _dist_sum_(st)
+        counts = st[:, 0, 0].cpu()
+        out = {}
+        for gid in torch.nonzero(counts > 0).flatten().tolist():
+            _, mean = ops.pearson_finalize(st[gid], want_mean=True)
+            out[str(gid)] = mean.item()
+        return out
+
+    def reset(self) -> None:
+        self.stats.zero_()
+        self.bad_group.zero_()
+
+    def __repr__(self) -> str:
+        return "GroupedMetric(MultidimPearsonCorrCoef)"
+
+
+@torch.no_grad()
+def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice: slice | None = None) -> np.ndarray:
+    """``Experiment.compute_multidim_pearson`` (main.py:459-477): eval-mode batched predict, then per-parcel Pearson r
+    over all (window, TR) rows.  Predictions never leave the device; the 1000-iteration scipy loop becomes one
+    statistics kernel per batch + one finalize.  ``parcel_slice`` restricts the statistics to a shard of parcels
+    (parcel-sharded evaluation, see parallel.py)."""
+    model.eval()
+    stats = None
+    for batch in loader:
+        y_pred = model(batch)
+        y_true = batch.data["fmri"].to(y_pred.device, torch.float32)
+        if y_true.ndim == 4:
+            y_true = y_true.squeeze(-1)
+        if parcel_slice is not None:
+            y_pred, y_true = y_pred[:, parcel_slice].contiguous(), y_true[:, parcel_slice].contiguous()
+        if stats is None:
+            stats = torch.zeros(1, 6, y_pred.shape[1], device=y_pred.device, dtype=torch.float64)
+        ops.pearson_stats(y_pred.float().contiguous(), y_true.contiguous(), stats, layout="bdt")
+    r, _ = ops.pearson_finalize(stats[0])
+    return r.cpu().numpy().astype(np.float32)

@@ -75,7 +75,7 @@ def mnmajor(t: torch.Tensor, **kw) -> Operand:
 def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, ldd: int, batch: int = 1, z_inner: int = 1,
          d_zo: int = 0, d_zi: int = 0, d_off: int = 0, transposed: bool = False, epilogue: int = EPI_STORE, alpha: float = 1.0,
          bias: torch.Tensor | None = None, bias_gathered: bool = False, bias_z_stride: int = 0,
-         res: torch.Tensor | None = None, ld_res: int = 0, res_row_mod: int = 0, rscale: torch.Tensor | None = None,
+         res: torch.Tensor | None = None, ld_res: int = 0, res_row_mod: int = 0, res_batched: bool = False, rscale: torch.Tensor | None = None,
          aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None, ld_aux: int = 0,
          rope: torch.Tensor | None = None, rope_t: int = 0, rope_dim: int = 0, head_dim: int = 0, rope_cols: int = 0,
          rope_sign: float = 1.0, kgroup: torch.Tensor | None = None, block_n: int = 0, probe=None) -> None:
@@ -98,14 +98,25 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
                 raise TribeError(f"gemm {name}: expected CUDA {dt}")
             setattr(g, name, t.data_ptr())
     g.bias_gathered, g.bias_z_stride = int(bias_gathered), bias_z_stride
-    g.ld_res, g.res_row_mod, g.ld_aux = ld_res, res_row_mod, ld_aux
+    g.ld_res, g.res_row_mod, g.res_batched, g.ld_aux = ld_res, res_row_mod, int(res_batched), ld_aux
     g.rope_t, g.rope_dim, g.head_dim, g.rope_cols, g.rope_sign = rope_t, rope_dim, head_dim, rope_cols, rope_sign
     g.block_n = block_n
     lib = _lib.load()
+    log = GEMM_LOG
+    if log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     if probe is None:
         check(lib.tribe_gemm_bf16(ctypes.byref(g), _stream()), "tribe_gemm_bf16")
     else:
         check(lib.tribe_gemm_bf16_probe(ctypes.byref(g), _stream(), *probe), "tribe_gemm_bf16_probe")
+    if log is not None:
+        e1.record()
+        log.append((e0, e1, 2.0 * m * n * k * (kgroup.numel() if kgroup is not None else batch)))
+
+
+# bench.py sets this to a list to collect (start event, end event, algorithmic FLOPs) per GEMM launch
+GEMM_LOG = None
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> None:
@@ -187,7 +198,16 @@ def token_pool_fwd(x, y, B, t_in, t_out, C) -> None:
 
 
 def token_pool_bwd(dy, dx, B, t_in, t_out, C) -> None:
-    check(_lib.load().tribe_token_pool_bwd(_ptr(dy), _DT[dy.dtype], _ptr(dx), B, t_in, t_out, C, _stream()), "tribe_token_pool_bwd")
+    check(_lib.load().tribe_token_pool_bwd(_ptr(dy), _DT[dy.dtype], _ptr(dx), _DT[dx.dtype], B, t_in, t_out, C, _stream()),
+          "tribe_token_pool_bwd")
+
+
+def add_rows_periodic(x, pos, out, rows, cols, row_mod, *, ld_x=0, ld_pos, ld_out, x_off=0, pos_off=0, out_off=0) -> None:
+    """out[r, c] = (x[r, c] if x is not None else 0) + pos[r % row_mod, c]; offsets are in elements."""
+    xp = ctypes.c_void_p(x.data_ptr() + 4 * x_off) if x is not None else None
+    check(_lib.load().tribe_add_rows_periodic(xp, ld_x, ctypes.c_void_p(pos.data_ptr() + 4 * pos_off), ld_pos,
+                                              ctypes.c_void_p(out.data_ptr() + 4 * out_off), ld_out, rows, cols, row_mod, _stream()),
+          "tribe_add_rows_periodic")
 
 
 def transpose_cast_bot(x, y) -> None:

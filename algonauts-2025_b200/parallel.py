@@ -1,0 +1,159 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, ``torch.distributed`` (NCCL over NVLink 5 / NVSwitch).
+
+* ``GradAllReduce``       data-parallel training (reference: Lightning DDP, algonauts2025/main.py:388-394): each layer's
+                          contiguous gradient bucket is all-reduced (mean) as soon as that layer's backward has written
+                          it, overlapping the rest of the backward.
+* ``parcel_bounds`` / ``exchange_parcel_shards`` / ``sharded_pearson``
+                          evaluation sharded by parcel (BASELINE.json config 5): every rank predicts its own windows,
+                          one all-to-all re-lays (windows-shard x all parcels) into (all windows x parcel-shard), each
+                          rank reduces its parcels with the Pearson kernel, r is all-gathered.
+* ``ensemble_weights`` / ``ensemble_average``
+                          one ensemble member per GPU (algonauts2025/grids/average_submissions.py:107-125): per-parcel
+                          softmax(r / tau) weights, weighted all-reduce of the members' predictions.
+Shard-exchange logic is backend-agnostic (tested on CPU with gloo, world_size 2); the reductions are CUDA kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel grads
+class GradAllReduce:
+    """Attach to an ``FmriEncoder``: ``engine.backward`` calls ``bucket_ready(i)`` when bucket ``i`` of the flat gradient
+    buffer is final; the all-reduce runs on NCCL's stream while the main stream continues with earlier layers."""
+
+    def __init__(self, model, group=None):
+        self.engine = model._engine
+        self.engine.comm = self
+        self.group = group
+        self.works = []
+        self.passes = 1
+        self.counts = {}
+
+    def begin_step(self, backward_passes: int = 1):
+        """``backward_passes``: how many encoder backward passes feed this step's gradients (2 with the contrastive
+        branch, pl_module.py:59-77); a bucket is reduced after its last contribution."""
+        self.works, self.counts, self.passes = [], {}, backward_passes
+
+    def bucket_ready(self, idx: int):
+        _, ws = world()
+        if ws == 1:
+            return
+        self.counts[idx] = self.counts.get(idx, 0) + 1
+        if self.counts[idx] < self.passes:
+            return
+        start, end = self.engine.flat.bucket_ranges[idx]
+        g = self.engine.flat.grad[start:end]
+        self.works.append(dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+
+    def finish_step(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
+# ------------------------------------------------------------------------------------------------ parcel-sharded eval
+def parcel_bounds(n_parcels: int, world_size: int) -> list[tuple[int, int]]:
+    """Contiguous, balanced parcel shards (first ``n % G`` shards get one extra parcel)."""
+    base, extra = divmod(n_parcels, world_size)
+    bounds, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < extra else 0)
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+def exchange_parcel_shards(local: torch.Tensor, group=None) -> tuple[torch.Tensor, tuple[int, int]]:
+    """local: (n_local_rows, O) rows owned by this rank -> (n_total_rows, O_shard): every rank's rows for THIS rank's
+    parcel shard, ordered by source rank.  One all-gather of row counts + one all-to-all."""
+    rank, ws = world()
+    n_local, O = local.shape
+    bounds = parcel_bounds(O, ws)
+    lo, hi = bounds[rank]
+    if ws == 1:
+        return local, (lo, hi)
+    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(ws)]
+    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=local.device), group=group)
+    counts = [int(c.item()) for c in counts]
+    send = [local[:, a:b].contiguous() for a, b in bounds]
+    recv = [torch.empty(counts[src], hi - lo, dtype=local.dtype, device=local.device) for src in range(ws)]
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+    else:  # gloo (CPU tests) has no all-to-all: the same blocks move as point-to-point sends
+        recv[rank].copy_(send[rank])
+        reqs = [dist.isend(send[dst], dst, group=group) for dst in range(ws) if dst != rank]
+        reqs += [dist.irecv(recv[src], src, group=group) for src in range(ws) if src != rank]
+        for req in reqs:
+            req.wait()
+    return torch.cat(recv, dim=0), (lo, hi)
+
+
+def gather_parcels(r_shard: torch.Tensor, n_parcels: int, group=None) -> torch.Tensor:
+    rank, ws = world()
+    if ws == 1:
+        return r_shard
+    bounds = parcel_bounds(n_parcels, ws)
+    width = max(b - a for a, b in bounds)  # shards differ by at most one parcel: pad to a common width
+    mine = torch.zeros(width, dtype=r_shard.dtype, device=r_shard.device)
+    mine[: r_shard.numel()] = r_shard
+    parts = [torch.empty(width, dtype=r_shard.dtype, device=r_shard.device) for _ in bounds]
+    dist.all_gather(parts, mine, group=group)
+    return torch.cat([p[: b - a] for p, (a, b) in zip(parts, bounds)])
+
+
+def sharded_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=None) -> torch.Tensor:
+    """Per-parcel Pearson r over ALL ranks' rows, parcels sharded across ranks.  (n_local, O) fp32 CUDA -> (O,) fp32."""
+    from . import ops
+
+    O = preds_local.shape[1]
+    p_shard, _ = exchange_parcel_shards(preds_local, group)
+    t_shard, _ = exchange_parcel_shards(trues_local, group)
+    stats = torch.zeros(1, 6, p_shard.shape[1], device=p_shard.device, dtype=torch.float64)
+    ops.pearson_stats(p_shard.contiguous(), t_shard.contiguous(), stats, layout="no")
+    r, _ = ops.pearson_finalize(stats[0])
+    return gather_parcels(r, O, group)
+
+
+def allreduced_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=None) -> torch.Tensor:
+    """Alternative without re-laying the data: local statistics over all parcels + one all-reduce of 6 x O fp64."""
+    from . import ops
+
+    stats = torch.zeros(1, 6, preds_local.shape[1], device=preds_local.device, dtype=torch.float64)
+    ops.pearson_stats(preds_local.contiguous(), trues_local.contiguous(), stats, layout="no")
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(stats, group=group)
+    r, _ = ops.pearson_finalize(stats[0])
+    return r
+
+
+# ------------------------------------------------------------------------------------------------ ensembles
+def ensemble_weights(member_r: torch.Tensor, temperature: float = 0.3) -> torch.Tensor:
+    """member_r (N, O) -> per-parcel softmax(r / tau) over members (average_submissions.py:107-125)."""
+    return torch.softmax(member_r / temperature, dim=0)
+
+
+def ensemble_average(pred_member: torch.Tensor, r_member: torch.Tensor, temperature: float = 0.3, group=None) -> torch.Tensor:
+    """One member per rank: pred_member (..., O, T) or (N_rows, O) predictions of THIS rank's model on the shared
+    evaluation set, r_member (O,) its per-parcel validation Pearson.  Returns the softmax-weighted ensemble
+    prediction (identical on every rank): all-gather of r (O floats per rank) + one all-reduce of the predictions."""
+    rank, ws = world()
+    if ws == 1:
+        return pred_member
+    rs = [torch.empty_like(r_member) for _ in range(ws)]
+    dist.all_gather(rs, r_member.contiguous(), group=group)
+    w = ensemble_weights(torch.stack(rs), temperature)[rank]  # (O,)
+    parcel_dim = 1
+    shape = [1] * pred_member.dim()
+    shape[parcel_dim] = -1
+    out = pred_member * w.view(shape)
+    dist.all_reduce(out, group=group)
+    return out

@@ -1,0 +1,47 @@
+"""``SegmentData`` — the batch type the hot path consumes (mirror of reference ``data_utils/dataloader.py:27-53``).
+The reference's own class is accepted too (duck-typed: ``.data`` dict of tensors, ``.segments`` list, ``.to``)."""
+from __future__ import annotations
+
+import dataclasses
+import typing as tp
+
+import torch
+
+
+@dataclasses.dataclass
+class SegmentData:
+    data: tp.Dict[str, torch.Tensor]
+    segments: tp.List[tp.Any]
+
+    def __post_init__(self) -> None:
+        if not isinstance(self.data, dict):
+            raise TypeError(f"'features' need to be a dict, got: {type(self.data)}")
+        if not self.data:
+            raise ValueError(f"No data in {self}")
+        if not isinstance(self.segments, list):
+            raise TypeError(f"'segments' needs to be a list, got {self.segments}")
+        batch_size = next(iter(self.data.values())).shape[0]
+        if len(self.segments) != batch_size:
+            raise RuntimeError(f"Incoherent batch size {batch_size} for {len(self.segments)} segments in {self}")
+
+    def to(self, device: str) -> "SegmentData":
+        out = {name: d.to(device) for name, d in self.data.items()}
+        return SegmentData(data=out, segments=self.segments)
+
+    def pin_memory(self) -> "SegmentData":
+        return SegmentData(data={k: v.pin_memory() for k, v in self.data.items()}, segments=self.segments)
+
+    def __getitem__(self, key: str) -> None:
+        raise RuntimeError("New SegmentData batch is not a dict, use batch.data instead")
+
+
+def synthetic_batch(batch_size=16, t=298, t_out=100, n_outputs=1000, n_subjects=4, seed=1234,
+                    dims=(("text", 2, 3072), ("audio", 2, 1024), ("video", 2, 1408)), dtype=torch.float32, pin=False) -> SegmentData:
+    """Synthetic window batch of the named shapes: N(0,1) features and fMRI, uniform subject ids.
+    Same generator call order as ``oracle.tribe_oracle.synthetic_batch`` so both produce identical tensors."""
+    g = torch.Generator().manual_seed(seed)
+    data = {name: torch.randn(batch_size, l, d, t, generator=g).to(dtype) for name, l, d in dims}
+    data["fmri"] = torch.randn(batch_size, n_outputs, t_out, generator=g)
+    data["subject_id"] = torch.randint(0, n_subjects, (batch_size, 1), generator=g)
+    batch = SegmentData(data=data, segments=[None] * batch_size)
+    return batch.pin_memory() if pin else batch

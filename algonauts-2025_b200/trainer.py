@@ -1,0 +1,54 @@
+"""Minimal stand-in for the slice of ``lightning.pytorch.Trainer`` the hot path runs under (lightning is not
+installed here): Lightning's *automatic optimisation* for one batch is
+``zero_grad(set_to_none=True) -> training_step -> loss.backward() -> optimizer.step() -> scheduler.step()`` with no
+gradient clipping / accumulation and precision 32-true (reference: algonauts2025/main.py:388-404)."""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+
+
+def default_optimizer(params, total_steps: int, lr: float = 1e-4):
+    """Adam(lr=1e-4, weight_decay=0) + OneCycleLR(max_lr=1e-4, pct_start=0.1), stepped per batch
+    (algonauts2025/grids/defaults.py:126-141, modeling_utils/optimizers/base.py:84-96).  Stock torch optimizer."""
+    params = list(params)
+    opt = torch.optim.Adam(params, lr=lr, weight_decay=0.0, fused=params[0].is_cuda)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=lr, pct_start=0.1, total_steps=max(total_steps, 2))
+    return opt, sched
+
+
+class MiniTrainer:
+    def __init__(self, module, optimizer, scheduler=None, grad_sync=None):
+        self.module, self.optimizer, self.scheduler, self.grad_sync = module, optimizer, scheduler, grad_sync
+        self.global_step = 0
+
+    def train_step(self, batch) -> torch.Tensor:
+        self.module.train()
+        self.optimizer.zero_grad(set_to_none=True)
+        if self.grad_sync is not None:
+            self.grad_sync.begin_step()
+        loss = self.module.training_step(batch, self.global_step)
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync.finish_step()
+        self.optimizer.step()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        self.global_step += 1
+        return loss.detach()
+
+    @torch.no_grad()
+    def validate(self, batches: tp.Iterable) -> dict:
+        self.module.eval()
+        for name, metric in self.module.metrics.items():
+            if name.startswith("val"):
+                metric.reset()
+        for i, batch in enumerate(batches):
+            self.module.validation_step(batch, i)
+        self.module.on_validation_epoch_end()
+        out = dict(getattr(self.module, "logged", {}))
+        for name, metric in self.module.metrics.items():
+            if name.startswith("val") and "grouped" not in metric.__class__.__name__.lower():
+                out[name] = metric.compute()
+        return out

@@ -1,0 +1,270 @@
+"""bench.py — TRIBE FmriEncoder train step on B200 (BASELINE.json metric: train windows/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contrastive 0|1] [--batch 16]
+
+One "step" = one Lightning-style automatic-optimisation step of ``BrainModule`` (zero_grad -> training_step: forward,
+MSE loss [-> contrastive branch] -> backward -> Adam -> OneCycleLR) on one batch of 16 synthetic windows per GPU of the
+full TRIBE shape (text 2x3072, audio 2x1024, video 2x1408 feature stacks at T=298, 1000 parcels x 100 TRs, 4 subjects).
+`value`  : windows/s with the inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same metric through the public API from pinned HOST batches (H2D inside the timed region, loss read back).
+`roofline`: all tcgen05 GEMM launches of the timed steps, algorithmic FLOPs / summed CUDA-event time, against the
+            measured sustained bf16 peak (MEASURED_PEAKS.json).
+`cpu_baseline` / `--impl reference`: the CPU oracle port of the reference path (oracle/) on the host cores.
+Under torchrun (N > 1) every rank trains its own 16 windows and gradients are all-reduced over NCCL (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FEATURE_DIMS = {"text": (2, 3072), "audio": (2, 1024), "video": (2, 1408)}
+WORKLOAD = "TRIBE FmriEncoder train step: 4 subjects, 16 windows/GPU x (text 2x3072 + audio 2x1024 + video 2x1408) x T=298 -> 1000 parcels x 100 TRs"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))), "hbm": float(p.get("hbm_gbs", 6650.0)), "src": "measured"}
+    return {"tflops": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])), (mx := float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops_per_window(contrastive: bool) -> float:
+    """forward 557.3 GFLOP/window, train step = 3x; the contrastive branch adds a second projector +
+    encoder pass, the head GEMM and the InfoNCE logits."""
+    t, h, depth, n_out, k_proj = 298, 3072, 8, 1000, 11008
+    proj = 2 * t * k_proj * (h // 3)
+    enc = depth * (4 * 2 * t * h * h + 2 * 2 * t * h * 4 * h)
+    attn = depth * 2 * (2 * t * t * h)
+    readout = 2 * t * h * n_out
+    fwd = proj + enc + attn + readout
+    if not contrastive:
+        return 3.0 * fwd
+    return 3.0 * (fwd + proj + enc + attn + 2 * t * 2816 * h + 2 * (16 * t) * t * h)
+
+
+# ------------------------------------------------------------------------------------------------------ CPU (oracle) arm
+def cpu_reference_steps(steps: int, warmup: int, windows_per_step: int, contrastive: bool):
+    """The reference's own CPU path (PyTorch fp32): oracle port of model.py / pl_module.py / x_transformers, stock
+    torch.optim.Adam, all host threads."""
+    from oracle import tribe_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(33)
+    cfg = O.OracleConfig(n_subjects=4, modality_dropout=0.3, contrastive_enabled=contrastive)
+    model = O.OracleFmriEncoder(FEATURE_DIMS, 1000, 100, cfg)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    batch = O.synthetic_batch(batch_size=windows_per_step, seed=1234)
+    model.train()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, *_ = O.run_step(model, batch)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"windows_per_s": windows_per_step * steps / total, "ms_per_step": 1e3 * total / steps, "cores": torch.get_num_threads(),
+            "sample": f"{steps} train step(s) of {windows_per_step} window(s) each after {warmup} warm-up, fp32, torch CPU, Adam"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.steps, args.warmup, 1, bool(args.contrastive))
+    line = {"impl": "reference", "metric": "train windows/s", "value": r["windows_per_s"], "unit": "windows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "windows_per_step": 1, "contrastive": bool(args.contrastive)},
+            "cpu_baseline": {"value": r["windows_per_s"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["windows_per_s"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    import algonauts2025_b200
+    from algonauts2025_b200 import ops, parallel
+    from algonauts2025_b200.model import FmriEncoderConfig
+    from algonauts2025_b200.pl_module import BrainModule
+    from algonauts2025_b200.segment import SegmentData, synthetic_batch
+    from algonauts2025_b200.trainer import MiniTrainer, default_optimizer
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    algonauts2025_b200.load()
+    B, K, W = args.batch, args.steps, args.warmup
+    contrastive = bool(args.contrastive)
+
+    torch.manual_seed(33)  # identical seeds on every rank -> identical weights and dropout masks (main.py:492-495)
+    cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3, feature_aggregation="cat", layer_aggregation="cat", contrastive_enabled=contrastive)
+    model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
+    module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=15)
+    opt, sched = default_optimizer(model.parameters(), total_steps=2 * (K + W) + 8)
+    sync = parallel.GradAllReduce(model) if world > 1 else None
+    trainer = MiniTrainer(module, opt, sched, grad_sync=sync)
+    if sync is not None:
+        passes = 2 if contrastive else 1
+        orig_begin = sync.begin_step
+        sync.begin_step = lambda: orig_begin(passes)
+
+    # two distinct host batches (pinned) alternate; 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
+    host = [synthetic_batch(batch_size=B, seed=1234 + 17 * rank + i, pin=True) for i in range(2)]
+    dev = [SegmentData(data={k: v.cuda(non_blocking=True) for k, v in b.data.items()}, segments=b.segments) for b in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].data.values())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        trainer.train_step(dev[i % 2])
+    barrier()
+
+    # ---- timed region 1: device-resident inputs
+    gemm_log = []
+    ops.GEMM_LOG = gemm_log
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = algonauts2025_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        trainer.train_step(dev[i % 2])
+    e1.record()
+    barrier()
+    ops.GEMM_LOG = None
+    clk = clocks.stop()
+    launches = algonauts2025_b200.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_log)
+    gemm_flops = sum(f for _, _, f in gemm_log)
+
+    # ---- timed region 2: end to end through the public API from pinned host memory
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for i in range(K):
+        last = trainer.train_step(host[i % 2]).item()  # D2H read of the step's loss
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e, gemm_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, gemm_ms = (float(x) for x in t.cpu())
+    if rank == 0:
+        peaks = measured_peaks()
+        value = world * B * K / (ms / 1e3)
+        e2e = world * B * K / (ms_e2e / 1e3)
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        step_tflops = algorithmic_flops_per_window(contrastive) * B * K / (ms / 1e3) / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_steps(1, 1, 1, contrastive)
+            cpu = {"value": r["windows_per_s"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line = {"metric": "train windows/s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
+                           "optimizer": "Adam(fused)+OneCycleLR, fp32 master weights", "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
+                           "last_loss": last},
+                "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                             "traffic": None, "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of the timed steps)",
+                             "peak_source": peaks["src"] + " sustained bf16", "gemm_share_of_step": gemm_ms / ms if ms else None,
+                             "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peaks["tflops"]},
+                "clocks": clk}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--contrastive", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

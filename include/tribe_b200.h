@@ -88,6 +88,7 @@ typedef struct TribeGemm {
   const float* res;       /* fp32 residual, row-major ld_res */
   int64_t ld_res;
   int32_t res_row_mod;    /* residual row = row % res_row_mod (0: row) */
+  int32_t res_batched;    /* 1: the residual shares the output's batch offsets (in-place accumulation D += acc) */
   const float* rscale;    /* optional fp32 [n] */
   const void* aux_in;     /* bf16 [m, ld_aux] (GELU_BWD) */
   void* aux_out;          /* bf16 [m, ld_aux] (GELU) */
@@ -149,9 +150,14 @@ int tribe_adaptive_avg_pool_bwd(const float* dy, float* dx, int64_t rows, int64_
 /* Same windows along the TOKEN dim of a token-major activation: x bf16 (B, t_in, C) -> y bf16 (B, t_out, C)
  * (pool-before-readout: pool and SubjectLayers commute). */
 int tribe_token_pool_fwd(const void* x_bf16, void* y_bf16, int64_t B, int64_t t_in, int64_t t_out, int64_t C, void* stream);
-/* dx fp32 (B, t_in, C) = scatter of dy (bf16 or fp32; B, t_out, C) / window length. */
-int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, float* dx, int64_t B, int64_t t_in, int64_t t_out, int64_t C,
-                         void* stream);
+/* dx (B, t_in, C) = scatter of dy (B, t_out, C) / window length; dtypes 0 fp32 / 2 bf16 on either side. */
+int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype, int64_t B, int64_t t_in, int64_t t_out,
+                         int64_t C, void* stream);
+
+/* out[r, c] = (x ? x[r, c] : 0) + pos[r % row_mod, c], c < cols: the `x + time_pos_embed[:, :T]` of model.py:169-170 for
+ * the stand-alone transformer_forward entry and for column blocks of dropped / absent modalities (model.py:143-144,158-159). */
+int tribe_add_rows_periodic(const float* x, int64_t ld_x, const float* pos, int64_t ld_pos, float* out, int64_t ld_out, int64_t rows,
+                            int64_t cols, int64_t row_mod, void* stream);
 
 /* (B, O, T) fp32 -> (B, T, O) bf16 transpose-cast (gradient of the predictions into the readout's GEMM layout). */
 int tribe_transpose_cast_bot(const float* x, void* y_bf16, int64_t B, int64_t O, int64_t T, void* stream);

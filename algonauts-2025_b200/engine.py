@@ -20,6 +20,21 @@ from ._lib import TribeError
 
 ALIGN = 64  # elements; keeps every parameter view 16-byte aligned in fp32 and bf16
 
+# Bumped by a global optimizer post-step hook: fused CUDA optimizers update parameters through raw pointers, so the
+# per-tensor version counters alone are not a reliable "weights changed" signal for the bf16 shadow copy.
+_OPT_STEPS = [0]
+_HOOK = []
+
+
+def _install_optimizer_hook():
+    if not _HOOK:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+
+        def _bump(optimizer, args, kwargs):
+            _OPT_STEPS[0] += 1
+
+        _HOOK.append(register_optimizer_step_post_hook(_bump))
+
 
 def _round_up(x: int, a: int) -> int:
     return (x + a - 1) // a * a
@@ -53,6 +68,7 @@ class FlatParams:
         self.grad = None
         self.bf16 = None
         self._sig = None
+        _install_optimizer_hook()
 
     def intact(self) -> bool:
         base = self.flat.data_ptr()
@@ -75,7 +91,7 @@ class FlatParams:
 
     def refresh_bf16(self):
         """Re-cast the bf16 shadow when any parameter changed in place (optimizer step, load_state_dict, SWA)."""
-        sig = sum(p._version for p in self.params.values())
+        sig = (sum(p._version for p in self.params.values()), _OPT_STEPS[0])
         if self.bf16 is None:
             self.bf16 = torch.empty(self.total, device=self.device, dtype=torch.bfloat16)
             self._sig = None

@@ -172,7 +172,7 @@ def test_two_steps_of_adam_track_the_oracle():
     model, oracle = small_pair()
     batch = small_batch()
     model.train(), oracle.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)  # raw-pointer update: shadow refresh must still fire
     opt_ref = torch.optim.Adam(oracle.parameters(), lr=1e-3)
     losses, ref_losses = [], []
     for _ in range(3):
@@ -186,6 +186,10 @@ def test_two_steps_of_adam_track_the_oracle():
         losses.append(loss.item()), ref_losses.append(ref.item())
     assert losses[2] < losses[0]
     np.testing.assert_allclose(losses, ref_losses, rtol=2e-2)
+    flat = model._engine.flat
+    flat.refresh_bf16()
+    for name, p in model.named_parameters():
+        assert torch.equal(flat.view16(name), p.detach().to(torch.bfloat16)), f"stale bf16 shadow for {name}"
 
 
 # ----------------------------------------------------------------------------------------------- metrics / BrainModule

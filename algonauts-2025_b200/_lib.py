@@ -42,7 +42,7 @@ def _source_hash() -> str:
 
     deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     deps.append(os.path.join(INCLUDE, "tribe_b200.h"))
-    h = hashlib.sha1(" ".join(NVCC_FLAGS[:8]).encode())
+    h = hashlib.sha1(" ".join(NVCC_FLAGS[:7]).encode())  # path-independent flags only: the GPU box mounts the repo elsewhere
     for d in deps:
         h.update(os.path.basename(d).encode())
         h.update(open(d, "rb").read())
@@ -61,6 +61,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link ``libtribe_b200.so`` (no GPU needed: nvcc cross-compiles)."""
     if not force and not _stale():
         return LIB_PATH
+    import fcntl
+
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:  # ranks of one torchrun job must not build concurrently
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or _stale():
+            _build_locked(verbose)
+    return LIB_PATH
+
+
+def _build_locked(verbose: bool) -> None:
     nvcc = _nvcc()
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -77,14 +87,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
     r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise TribeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
     with open(HASH_PATH, "w") as f:
         f.write(_source_hash())
-    return LIB_PATH
 
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p

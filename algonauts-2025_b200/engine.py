@@ -316,7 +316,9 @@ class Engine:
         ops.scalenorm_fwd(ws.xs[2 * self.depth], self._p("encoder.final_norm.g"), ws.xnf, ws.rnf)
 
         if plan.mode == "latents":
-            return ws.xnf.view(B, T, H).float()
+            lat = torch.empty(B, T, H, device=self.device, dtype=torch.float32)
+            ops.cast_bf16_f32(ws.xnf, lat)
+            return lat
         return self._readout_fwd(plan, ws)
 
     def _readout_fwd(self, plan, ws):

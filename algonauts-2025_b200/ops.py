@@ -262,3 +262,20 @@ def pearson_finalize(stats_one_group, want_mean=False):
     mean = torch.empty(1, device=r.device, dtype=torch.float32) if want_mean else None
     check(_lib.load().tribe_pearson_finalize(_ptr(stats_one_group), o, _ptr(r), _ptr(mean), _stream()), "tribe_pearson_finalize")
     return r, mean
+
+
+def cast_bf16_f32(src, dst) -> None:
+    check(_lib.load().tribe_cast_bf16_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), "tribe_cast_bf16_f32")
+
+
+def nce_expsums(logits, n, shift, row_sum, col_sum) -> None:
+    check(_lib.load().tribe_nce_expsums(_ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _stream()), "tribe_nce_expsums")
+
+
+def nce_loss(logits, n, shift, row_sum, col_sum, loss) -> None:
+    check(_lib.load().tribe_nce_loss(_ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(loss), _stream()), "tribe_nce_loss")
+
+
+def nce_grad(logits, n, shift, row_sum, col_sum, upstream, scale, g) -> None:
+    check(_lib.load().tribe_nce_grad(_ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(upstream), scale, _ptr(g),
+                                     g.stride(0), _stream()), "tribe_nce_grad")

@@ -34,20 +34,21 @@ class GradAllReduce:
         self.engine.comm = self
         self.group = group
         self.works = []
-        self.passes = 1
+        self.passes, self.head_passes = 1, 0
         self.counts = {}
 
-    def begin_step(self, backward_passes: int = 1):
-        """``backward_passes``: how many encoder backward passes feed this step's gradients (2 with the contrastive
-        branch, pl_module.py:59-77); a bucket is reduced after its last contribution."""
-        self.works, self.counts, self.passes = [], {}, backward_passes
+    def begin_step(self, backward_passes: int = 1, head_passes: int = 0):
+        """``backward_passes``: encoder backward passes feeding this step's gradients (2 with the contrastive branch,
+        pl_module.py:59-77); ``head_passes``: extra writers of the head bucket (one per contrastive head).  A bucket is
+        reduced after its last contribution."""
+        self.works, self.counts, self.passes, self.head_passes = [], {}, backward_passes, head_passes
 
     def bucket_ready(self, idx: int):
         _, ws = world()
         if ws == 1:
             return
         self.counts[idx] = self.counts.get(idx, 0) + 1
-        if self.counts[idx] < self.passes:
+        if self.counts[idx] < self.passes + (self.head_passes if idx == 0 else 0):
             return
         start, end = self.engine.flat.bucket_ranges[idx]
         g = self.engine.flat.grad[start:end]

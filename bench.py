@@ -165,9 +165,9 @@ def run_ours(args):
     sync = parallel.GradAllReduce(model) if world > 1 else None
     trainer = MiniTrainer(module, opt, sched, grad_sync=sync)
     if sync is not None:
-        passes = 2 if contrastive else 1
+        passes, heads = (2, 1) if contrastive else (1, 0)
         orig_begin = sync.begin_step
-        sync.begin_step = lambda: orig_begin(passes)
+        sync.begin_step = lambda: orig_begin(passes, heads)
 
     # two distinct host batches (pinned) alternate; 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
     host = [synthetic_batch(batch_size=B, seed=1234 + 17 * rank + i, pin=True) for i in range(2)]

@@ -194,6 +194,21 @@ int tribe_pearson_stats(const float* pred, const float* target, int64_t n_rows, 
 /* r[p] = clamp(cov / sqrt(var_x var_y), -1, 1) from the statistics; r fp32 [n_parcels]; mean_out optional fp32 [1]. */
 int tribe_pearson_finalize(const double* stats, int64_t n_parcels, float* r, float* mean_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Contrastive branch: symmetric InfoNCE over flattened (B*T) rows (algonauts2025/model.py:208-221).  The logits
+ * (n, ld) fp32 = q^ k^T / tau come from tribe_gemm_bf16 on row-normalised operands; |logit| <= shift = 1/tau.
+ */
+/* row_sum[i] = sum_j exp(l_ij - shift); col_sum[j] = sum_i exp(l_ij - shift) (col_sum is zeroed by the call). n <= 8192. */
+int tribe_nce_expsums(const float* logits, int64_t n, int64_t ld, float shift, float* row_sum, float* col_sum, void* stream);
+/* loss = 0.5 * (CE(logits, arange) + CE(logits^T, arange)) from the sums above. */
+int tribe_nce_loss(const float* logits, int64_t n, int64_t ld, float shift, const float* row_sum, const float* col_sum, float* loss_out,
+                   void* stream);
+/* g[i, j] = scale * upstream[0] * (softmax_row(i)_j + softmax_col(j)_i - 2 delta_ij) as bf16 (n, ldg), pad columns zeroed. */
+int tribe_nce_grad(const float* logits, int64_t n, int64_t ld, float shift, const float* row_sum, const float* col_sum,
+                   const float* upstream, float scale, void* g_bf16, int64_t ldg, void* stream);
+/* bf16 -> fp32 cast (latents handed back to torch as fp32, model.py:178-183). */
+int tribe_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

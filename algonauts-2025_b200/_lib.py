@@ -113,7 +113,7 @@ class TribeGemm(ctypes.Structure):
                 ("bias_z_stride", c_i64), ("res", c_vp), ("ld_res", c_i64), ("res_row_mod", c_i32), ("res_batched", c_i32), ("rscale", c_vp),
                 ("aux_in", c_vp), ("aux_out", c_vp), ("ld_aux", c_i64), ("rope", c_vp), ("rope_t", c_i32),
                 ("rope_dim", c_i32), ("head_dim", c_i32), ("rope_cols", c_i32), ("rope_sign", c_f32),
-                ("block_n", c_i32)]
+                ("block_n", c_i32), ("splitk_ws", c_vp), ("splitk_ws_bytes", c_i64)]
 
 
 # name -> (argtypes); every function returns int except the three introspection calls.

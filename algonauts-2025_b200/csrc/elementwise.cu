@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restr
 //   dx_in[c] = sqrt(dim) g rnorm (d_xn[c] - x_in[c] rnorm dot) + dy_out[c] * rs[c]
 //   d_rs[c] += dy_out[c] * x_in[c]        d_g += sqrt(dim) * dot
 // Each block walks a strided set of rows and keeps its d_rs column partials in registers (dim <= 4096).
-__global__ void __launch_bounds__(256) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
+__global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
                                                            const float* __restrict__ x_in, const float* __restrict__ rnorm,
                                                            const float* __restrict__ g, const float* __restrict__ rs,
                                                            float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
@@ -165,16 +165,25 @@ __global__ void __launch_bounds__(256) sublayer_bwd_kernel(const float* __restri
     const float4* xr = reinterpret_cast<const float4*>(x_in + row * dim);
     const float4* dyr = dy_out ? reinterpret_cast<const float4*>(dy_out + row * dim) : nullptr;
     const uint2* dnr = d_xn ? reinterpret_cast<const uint2*>(d_xn + row * dim) : nullptr;
-    float4 xc[4], dn[4];
-    float dot = 0.f;
+    // issue every global load of this row before the block reduction (memory-level parallelism)
+    float4 xc[4], dn[4], dyv[4];
+    uint2 dnraw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int v = threadIdx.x + i * 256;
       if (v < nvec) {
         xc[i] = __ldg(xr + v);
-        if (dnr) {
-          const uint2 u = __ldg(dnr + v);
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        if (dnr) dnraw[i] = __ldg(dnr + v);
+        if (dyr) dyv[i] = __ldg(dyr + v);
+      }
+    }
+    float dot = 0.f;
+    if (dnr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int v = threadIdx.x + i * 256;
+        if (v < nvec) {
+          const float2 a = unpack_bf16x2(dnraw[i].x), b = unpack_bf16x2(dnraw[i].y);
           dn[i] = make_float4(a.x, a.y, b.x, b.y);
           dot += dn[i].x * xc[i].x + dn[i].y * xc[i].y + dn[i].z * xc[i].z + dn[i].w * xc[i].w;
         }
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(256) sublayer_bwd_kernel(const float* __restri
           o.z = coef * (dn[i].z - xc[i].z * k), o.w = coef * (dn[i].w - xc[i].w * k);
         }
         if (dyr) {
-          const float4 dy = __ldg(dyr + v);
+          const float4 dy = dyv[i];
           float4 r4 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (rs) r4 = __ldg(reinterpret_cast<const float4*>(rs) + v);
           o.x += dy.x * r4.x, o.y += dy.y * r4.y, o.z += dy.z * r4.z, o.w += dy.w * r4.w;
@@ -286,9 +295,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+
 template <typename TX, typename TY, bool HAS_Y>
 __global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, const TY* __restrict__ y, float* __restrict__ out,
-                                                     int64_t rows, int64_t cols, int64_t ld, int64_t rows_per_block) {
+                                                     int64_t rows, int64_t cols, int64_t ld, int64_t rows_per_block, int vec_ok) {
   // block = 32 (columns, x4 each) x 8 (row lanes); grid.x = column strips of 128, grid.y = row chunks
   __shared__ float red[8][128];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -297,13 +316,36 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, c
   const int64_t r1 = min(rows, r0 + rows_per_block);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (c0 < cols) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
+    if (vec_ok && c0 + 4 <= cols) {  // one 8/16-byte load per row and operand, 4 rows in flight
+      int64_t r = r0 + ty;
+      for (; r + 24 < r1; r += 32) {
+        float a[4][4], b[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (c0 + j < cols) {
-          float v = to_f32<TX>(x[r * ld + c0 + j]);
-          if (HAS_Y) v *= to_f32<TY>(y[r * ld + c0 + j]);
-          acc[j] += v;
+        for (int u = 0; u < 4; ++u) {
+          load4(x + (r + 8 * u) * ld + c0, a[u]);
+          if (HAS_Y) load4(y + (r + 8 * u) * ld + c0, b[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] += HAS_Y ? a[u][j] * b[u][j] : a[u][j];
+      }
+      for (; r < r1; r += 8) {
+        float a[4], b[4];
+        load4(x + r * ld + c0, a);
+        if (HAS_Y) load4(y + r * ld + c0, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += HAS_Y ? a[j] * b[j] : a[j];
+      }
+    } else {
+      for (int64_t r = r0 + ty; r < r1; r += 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (c0 + j < cols) {
+            float v = to_f32<TX>(x[r * ld + c0 + j]);
+            if (HAS_Y) v *= to_f32<TY>(y[r * ld + c0 + j]);
+            acc[j] += v;
+          }
         }
       }
     }
@@ -346,56 +388,92 @@ __device__ __forceinline__ int win_end(int i, int t_in, int t_out) {
   return static_cast<int>((static_cast<int64_t>(i + 1) * t_in + t_out - 1) / t_out);
 }
 
-// x fp32 (rows, t_in) -> y fp32 (rows, t_out); a block stages R consecutive rows (contiguous in memory) in smem.
+// x fp32 (rows, t_in) -> y fp32 (rows, t_out).  A block stages R consecutive rows (contiguous in memory: one coalesced
+// float4 stream) in shared memory next to a per-block window table, then emits R*t_out contiguous outputs.
 // reference: nn.AdaptiveAvgPool1d(n_output_timesteps), algonauts2025/model.py:60,119-122.
 template <int R>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int t_in,
                                                        int t_out) {
   extern __shared__ float sm[];
+  float* data = sm;                                             // R * t_in
+  int* wstart = reinterpret_cast<int*>(sm + R * t_in);          // t_out
+  int* wlen = wstart + t_out;                                   // t_out
+  for (int i = threadIdx.x; i < t_out; i += blockDim.x) {
+    const int s0 = win_start(i, t_in, t_out), e0 = win_end(i, t_in, t_out);
+    wstart[i] = s0;
+    wlen[i] = e0 - s0;
+  }
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * R;
   const int nr = static_cast<int>(min(static_cast<int64_t>(R), rows - r0));
-  const int64_t n_in = static_cast<int64_t>(nr) * t_in;
+  const int n_in = nr * t_in;
   const float* src = x + r0 * t_in;
   if (((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    const int64_t nv = n_in >> 2;
-    for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(sm)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-    for (int64_t i = (nv << 2) + threadIdx.x; i < n_in; i += blockDim.x) sm[i] = __ldg(src + i);
+    const int nv = n_in >> 2;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(data)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int i = (nv << 2) + threadIdx.x; i < n_in; i += blockDim.x) data[i] = __ldg(src + i);
   } else {
-    for (int64_t i = threadIdx.x; i < n_in; i += blockDim.x) sm[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n_in; i += blockDim.x) data[i] = __ldg(src + i);
   }
   __syncthreads();
   const int n_out = nr * t_out;
   float* dst = y + r0 * t_out;
+  // o = r * t_out + i walks in steps of blockDim.x without divisions
+  int r = threadIdx.x / t_out, i = threadIdx.x - r * t_out;
+  const int dr = blockDim.x / t_out, di = blockDim.x - dr * t_out;
   for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-    const int r = o / t_out, i = o - r * t_out;
-    const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
+    const int s0 = wstart[i], len = wlen[i];
+    const float* row = data + r * t_in + s0;
     float acc = 0.f;
-    for (int t = s; t < e; ++t) acc += sm[r * t_in + t];
-    dst[o] = acc / static_cast<float>(e - s);
+    for (int t = 0; t < len; ++t) acc += row[t];
+    dst[o] = acc / static_cast<float>(len);
+    r += dr, i += di;
+    if (i >= t_out) i -= t_out, ++r;
   }
 }
 
+// dx[r, t] = sum over the (contiguous) run of windows containing t of dy[r, i] / len_i.
 template <int R>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t rows, int t_in,
                                                        int t_out) {
   extern __shared__ float sm[];
+  float* dyv = sm;                                              // R * t_out
+  float* winv = sm + R * t_out;                                 // t_out : 1 / len_i
+  int* ilo = reinterpret_cast<int*>(winv + t_out);              // t_in  : first window containing t
+  int* icnt = ilo + t_in;                                       // t_in  : number of windows containing t
+  for (int i = threadIdx.x; i < t_out; i += blockDim.x) winv[i] = 1.0f / static_cast<float>(win_end(i, t_in, t_out) - win_start(i, t_in, t_out));
+  for (int t = threadIdx.x; t < t_in; t += blockDim.x) {
+    int lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
+    int hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);  // exclusive upper bound of candidates
+    if (hi > t_out) hi = t_out;
+    while (lo < hi && !(t >= win_start(lo, t_in, t_out) && t < win_end(lo, t_in, t_out))) ++lo;
+    while (hi > lo && !(t >= win_start(hi - 1, t_in, t_out) && t < win_end(hi - 1, t_in, t_out))) --hi;
+    ilo[t] = lo;
+    icnt[t] = hi - lo;
+  }
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * R;
   const int nr = static_cast<int>(min(static_cast<int64_t>(R), rows - r0));
   const int n_o = nr * t_out;
-  for (int i = threadIdx.x; i < n_o; i += blockDim.x) sm[i] = __ldg(dy + r0 * t_out + i);
+  const float* src = dy + r0 * t_out;
+  if (((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    const int nv = n_o >> 2;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(dyv)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int i = (nv << 2) + threadIdx.x; i < n_o; i += blockDim.x) dyv[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < n_o; i += blockDim.x) dyv[i] = __ldg(src + i);
+  }
   __syncthreads();
   const int n_i = nr * t_in;
+  float* dst = dx + r0 * t_in;
+  int r = threadIdx.x / t_in, t = threadIdx.x - r * t_in;
+  const int dr = blockDim.x / t_in, dt = blockDim.x - dr * t_in;
   for (int o = threadIdx.x; o < n_i; o += blockDim.x) {
-    const int r = o / t_in, t = o - r * t_in;
-    int i_lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
-    int i_hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);  // exclusive upper bound
-    if (i_hi > t_out) i_hi = t_out;
+    const int lo = ilo[t], cnt = icnt[t];
+    const float* row = dyv + r * t_out;
     float acc = 0.f;
-    for (int i = i_lo; i < i_hi; ++i) {
-      const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
-      if (t >= s && t < e) acc += sm[r * t_out + i] / static_cast<float>(e - s);
-    }
-    dx[r0 * t_in + o] = acc;
+    for (int k = 0; k < cnt; ++k) acc += row[lo + k] * winv[lo + k];
+    dst[o] = acc;
+    r += dr, t += dt;
+    if (t >= t_in) t -= t_in, ++r;
   }
 }
 
@@ -526,7 +604,7 @@ extern "C" int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, co
                                   void* stream) {
   if (!x_in || rows <= 0 || dim <= 0 || dim % 4 || dim > 4096) return set_error(TRIBE_EINVAL, "sublayer_bwd: bad arguments (dim % 4, dim <= 4096)");
   if (d_xn_bf16 && (!rnorm || !g)) return set_error(TRIBE_EINVAL, "sublayer_bwd: d_xn needs rnorm and g");
-  const int grid = grid_for(rows, 8, 148 * 4);
+  const int grid = grid_for(rows, 2, 148 * 2);
   sublayer_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       dy_out, reinterpret_cast<const __nv_bfloat16*>(d_xn_bf16), x_in, rnorm, g, rs, dx_in, reinterpret_cast<__nv_bfloat16*>(dx_in_bf16), d_rs, d_g,
       rows, static_cast<int>(dim));
@@ -579,12 +657,13 @@ extern "C" int tribe_colsum(const void* x, int32_t x_dtype, const void* y, int32
   const int64_t rpb = (rows + chunks - 1) / chunks;
   dim3 grid(static_cast<unsigned>(strips), static_cast<unsigned>((rows + rpb - 1) / rpb));
   using bf = __nv_bfloat16;
-  if (x_dtype == 0 && !y) colsum_kernel<float, float, false><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), nullptr, out, rows, cols, ld, rpb);
-  else if (x_dtype == 2 && !y) colsum_kernel<bf, bf, false><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), nullptr, out, rows, cols, ld, rpb);
-  else if (x_dtype == 0 && y_dtype == 0) colsum_kernel<float, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb);
-  else if (x_dtype == 2 && y_dtype == 2) colsum_kernel<bf, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb);
-  else if (x_dtype == 0 && y_dtype == 2) colsum_kernel<float, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb);
-  else if (x_dtype == 2 && y_dtype == 0) colsum_kernel<bf, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb);
+  const int vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (!y || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  if (x_dtype == 0 && !y) colsum_kernel<float, float, false><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), nullptr, out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 2 && !y) colsum_kernel<bf, bf, false><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), nullptr, out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 0 && y_dtype == 0) colsum_kernel<float, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 2 && y_dtype == 2) colsum_kernel<bf, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 0 && y_dtype == 2) colsum_kernel<float, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 2 && y_dtype == 0) colsum_kernel<bf, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb, vec_ok);
   else return set_error(TRIBE_EINVAL, "colsum: unsupported dtype combination");
   TRIBE_CHECK_LAUNCH("colsum");
   return TRIBE_OK;
@@ -608,8 +687,8 @@ extern "C" int tribe_axpby_f32(const float* src, float* dst, float a, int32_t ac
 
 extern "C" int tribe_adaptive_avg_pool_fwd(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, void* stream) {
   if (!x || !y || rows <= 0 || t_in <= 0 || t_out <= 0) return set_error(TRIBE_EINVAL, "pool_fwd: bad arguments");
-  constexpr int R = 8;
-  const size_t smem = sizeof(float) * R * t_in;
+  constexpr int R = 32;
+  const size_t smem = sizeof(float) * (R * t_in + 2 * t_out);
   if (smem > 200 * 1024) return set_error(TRIBE_EINVAL, "pool_fwd: t_in too large");
   static bool attr = false;
   if (!attr) {
@@ -624,8 +703,8 @@ extern "C" int tribe_adaptive_avg_pool_fwd(const float* x, float* y, int64_t row
 
 extern "C" int tribe_adaptive_avg_pool_bwd(const float* dy, float* dx, int64_t rows, int64_t t_in, int64_t t_out, void* stream) {
   if (!dy || !dx || rows <= 0 || t_in <= 0 || t_out <= 0) return set_error(TRIBE_EINVAL, "pool_bwd: bad arguments");
-  constexpr int R = 8;
-  const size_t smem = sizeof(float) * R * t_out;
+  constexpr int R = 32;
+  const size_t smem = sizeof(float) * (R * t_out + t_out + 2 * t_in);
   if (smem > 200 * 1024) return set_error(TRIBE_EINVAL, "pool_bwd: t_out too large");
   static bool attr = false;
   if (!attr) {

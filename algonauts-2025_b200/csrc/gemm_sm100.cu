@@ -7,6 +7,11 @@
 // Both operands may be K-major or MN-major (canonical SWIZZLE_128B UMMA layouts), so forward, dgrad and wgrad GEMMs and
 // the attention / SubjectLayers contractions all run through this one kernel without materialised transposes.
 //
+// Scheduling: tiles are dealt round-robin to the persistent CTAs.  When the last wave is ragged (e.g. 456 tiles on 148
+// SMs = 3.08 waves for every N = 3072 GEMM of the encoder) the tiles of that partial wave are split along K across
+// the otherwise idle CTAs: each CTA reduces its K-slice into an fp32 workspace with vector atomics and the last
+// arriver of a tile (atomic ticket) runs the real epilogue ("data-parallel + split-K tail").
+//
 // Replaces (reference, relative to /root/reference): projector nn.Linear algonauts2025/model.py:157; the encoder's
 // linears and attention einsums behind model.py:173 (x_transformers, restated in oracle/xt_encoder.py); SubjectLayers
 // index_select + einsum modeling_utils/modeling_utils/models/common.py:61-66; InfoNCE logits model.py:216.
@@ -30,6 +35,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;
+constexpr int kMaxTailTiles = 160;  // split-K counters reserved at the head of the workspace
 
 struct alignas(64) GemmKParams {
   CUtensorMap tma, tmb;
@@ -60,6 +66,10 @@ struct alignas(64) GemmKParams {
   float rope_sign;
   uint32_t k_lbo, k_sbo, mn_lbo, mn_sbo;
   int m_blocks, n_blocks, num_tiles, num_kb;
+  // split-K tail
+  int full_tiles, tail_units, split, kb_per;
+  float* ws;
+  int* counters;
 };
 
 template <int BN>
@@ -100,6 +110,162 @@ __device__ __forceinline__ int batch_coord(const long long* gather, int z, int z
   return gather ? static_cast<int>(gather[zz]) : zz;
 }
 
+// One unit of work of a persistent CTA: a whole tile, or one K-slice of a tile of the ragged last wave.
+struct Work {
+  int tile, kb0, kb1;
+  bool partial;
+};
+
+__device__ __forceinline__ bool next_work(const GemmKParams& p, int it, Work& w) {
+  const int idx = blockIdx.x + it * gridDim.x;
+  if (idx < p.full_tiles) {
+    w.tile = idx, w.kb0 = 0, w.kb1 = p.num_kb, w.partial = false;
+    return true;
+  }
+  const int u = idx - p.full_tiles;
+  if (u >= p.tail_units) return false;
+  w.tile = p.full_tiles + u / p.split;
+  const int slice = u % p.split;
+  w.kb0 = slice * p.kb_per;
+  w.kb1 = min(p.num_kb, w.kb0 + p.kb_per);
+  w.partial = true;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Fused epilogue of 32 consecutive columns of one output row (v already scaled by alpha).
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
+                                               const float* bias, int res_row, int pos) {
+  const int nvalid = min(32, p.n - col0);
+  const bool full = (nvalid == 32) && p.vec_ok;
+
+  if (bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+        v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += __ldg(bias + col0 + j);
+    }
+  }
+
+  if (p.epilogue == TRIBE_EPI_GELU) {
+    if (row_ok) {
+      __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(ap + j) = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) ap[j] = __float2bfloat16(v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.epilogue == TRIBE_EPI_GELU_BWD) {
+    if (row_ok) {
+      const __nv_bfloat16* ap = p.aux_in + static_cast<long long>(row) * p.ld_aux + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 pk = __ldg(reinterpret_cast<const uint4*>(ap + j));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[j + 2 * e] *= gelu_erf_grad(f.x);
+            v[j + 2 * e + 1] *= gelu_erf_grad(f.y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] *= gelu_erf_grad(__bfloat162float(ap[j]));
+      }
+    }
+  } else if (p.epilogue == TRIBE_EPI_RESIDUAL) {
+    if (row_ok) {
+      const float* rp = p.res + (p.res_batched ? zoff : 0) + static_cast<long long>(res_row) * p.ld_res + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.rscale) s4 = __ldg(reinterpret_cast<const float4*>(p.rscale + col0 + j));
+          v[j] += r4.x * s4.x, v[j + 1] += r4.y * s4.y, v[j + 2] += r4.z * s4.z, v[j + 3] += r4.w * s4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __ldg(rp + j) * (p.rscale ? __ldg(p.rscale + col0 + j) : 1.0f);
+      }
+    }
+  } else if (p.epilogue == TRIBE_EPI_ROPE) {
+    const int cih = col0 % p.head_dim;  // chunk-uniform: head_dim, rope_dim are multiples of 32
+    if (col0 < p.rope_cols && cih < p.rope_dim) {
+      const float2* tab = p.rope + static_cast<long long>(pos) * (p.rope_dim >> 1) + (cih >> 1);
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(tab + j));  // (cos, sin) of two pairs
+        const float s0 = cs.y * p.rope_sign, s1 = cs.w * p.rope_sign;
+        const float x0 = v[2 * j], x1 = v[2 * j + 1], y0 = v[2 * j + 2], y1 = v[2 * j + 3];
+        v[2 * j] = x0 * cs.x - x1 * s0;
+        v[2 * j + 1] = x1 * cs.x + x0 * s0;
+        v[2 * j + 2] = y0 * cs.z - y1 * s1;
+        v[2 * j + 3] = y1 * cs.z + y0 * s1;
+      }
+    }
+  }
+
+  if (!row_ok) return;
+  if (p.d_transposed) {
+    if (p.d_f32) {
+      float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = v[j];
+    } else {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = __float2bfloat16(v[j]);
+    }
+  } else if (p.d_f32) {
+    float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(dp + j) = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -112,6 +278,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile uint32_t* epi_flag = tmem_holder + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,8 +314,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      Work w;
+      for (int it = 0; next_work(p, it, w); ++it) {
+        const TileCoord t = decode_tile(p, w.tile, BN);
         const int a_in = p.a_inner_off + t.zi * p.a_zin_stride;
         const int b_in = p.b_inner_off + t.zi * p.b_zin_stride;
         for (int ko = 0; ko < n_kouter; ++ko) {
@@ -160,7 +328,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             za = batch_coord(p.a_gather, t.z, p.a_zdiv);
             zb = batch_coord(p.b_gather, t.z, p.b_zdiv);
           }
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = w.kb0; kb < w.kb1; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
@@ -200,15 +368,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
+      Work w;
+      for (int it = 0; next_work(p, it, w); ++it) {
+        const TileCoord t = decode_tile(p, w.tile, BN);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accumulate = 0;
         for (int ko = 0; ko < n_kouter; ++ko) {
           if (p.kgroup && static_cast<int>(p.kgroup[ko]) != t.z) continue;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = w.kb0; kb < w.kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -236,10 +405,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BN);
+    Work w;
+    for (int it = 0; next_work(p, it, w); ++it) {
+      const TileCoord t = decode_tile(p, w.tile, BN);
       bool has_k = true;
       if (p.kgroup) {
         has_k = false;
@@ -247,162 +418,74 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = t.m0 + q * 32 + lane;
+      const int row = t.m0 + row_in_tile;
       const bool row_ok = row < p.m;
       const long long zoff = static_cast<long long>(t.zo) * p.d_zo + static_cast<long long>(t.zi) * p.d_zi;
       const float* bias = p.bias;
       if (bias && p.bias_gathered) bias += static_cast<long long>(batch_coord(p.b_gather, t.z, p.b_zdiv)) * p.bias_z_stride;
       const int res_row = p.res_row_mod ? row % p.res_row_mod : row;
       const int pos = p.rope ? row % p.rope_t : 0;
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 
+      if (!w.partial) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = t.n0 + c * 32;
-        if (col0 >= p.n) break;  // warp-uniform
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), raw);
-        tmem_ld_wait();
-        float v[32];
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = t.n0 + c * 32;
+          if (col0 >= p.n) break;  // warp-uniform
+          uint32_t raw[32];
+          tmem_ld_32x32(t_addr + c * 32, raw);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(raw[j]) * p.alpha : 0.0f;
-        const int nvalid = min(32, p.n - col0);
-        const bool full = (nvalid == 32) && p.vec_ok;
-
-        if (bias) {
-          if (full) {
+          for (int j = 0; j < 32; ++j) v[j] = has_k ? __uint_as_float(raw[j]) * p.alpha : 0.0f;
+          epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      } else {
+        // K-slice of a tail tile: reduce into the fp32 workspace, last arriver finishes the tile.
+        const int ti = w.tile - p.full_tiles;
+        float* wrow = p.ws + (static_cast<size_t>(ti) * BM + row_in_tile) * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (t.n0 + c * 32 >= p.n) break;
+          uint32_t raw[32];
+          tmem_ld_32x32(t_addr + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(wrow + c * 32 + j),
+                      make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])));
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        __threadfence();
+        epi_bar_sync();
+        if (warp == 2 && lane == 0) {
+          const int old = atomicAdd(p.counters + ti, 1);
+          *epi_flag = (old == p.split - 1) ? 1u : 0u;
+          if (old == p.split - 1) p.counters[ti] = 0;  // ready for the next launch
+        }
+        epi_bar_sync();
+        if (*epi_flag) {
+          __threadfence();
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = t.n0 + c * 32;
+            if (col0 >= p.n) break;
+            float v[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+              float4* wp = reinterpret_cast<float4*>(wrow + c * 32 + j);
+              const float4 s4 = __ldcg(wp);
+              __stcg(wp, make_float4(0.f, 0.f, 0.f, 0.f));  // leave the workspace zeroed for the next launch
+              v[j] = s4.x * p.alpha, v[j + 1] = s4.y * p.alpha, v[j + 2] = s4.z * p.alpha, v[j + 3] = s4.w * p.alpha;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) v[j] += __ldg(bias + col0 + j);
+            epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
           }
         }
-
-        if (p.epilogue == TRIBE_EPI_GELU) {
-          if (row_ok) {
-            __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(ap + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) ap[j] = __float2bfloat16(v[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.epilogue == TRIBE_EPI_GELU_BWD) {
-          if (row_ok) {
-            const __nv_bfloat16* ap = p.aux_in + static_cast<long long>(row) * p.ld_aux + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(ap + j));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h[e]);
-                  v[j + 2 * e] *= gelu_erf_grad(f.x);
-                  v[j + 2 * e + 1] *= gelu_erf_grad(f.y);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] *= gelu_erf_grad(__bfloat162float(ap[j]));
-            }
-          }
-        } else if (p.epilogue == TRIBE_EPI_RESIDUAL) {
-          if (row_ok) {
-            const float* rp = p.res + (p.res_batched ? zoff : 0) + static_cast<long long>(res_row) * p.ld_res + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
-                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (p.rscale) s4 = __ldg(reinterpret_cast<const float4*>(p.rscale + col0 + j));
-                v[j] += r4.x * s4.x, v[j + 1] += r4.y * s4.y, v[j + 2] += r4.z * s4.z, v[j + 3] += r4.w * s4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += __ldg(rp + j) * (p.rscale ? __ldg(p.rscale + col0 + j) : 1.0f);
-            }
-          }
-        } else if (p.epilogue == TRIBE_EPI_ROPE) {
-          const int cih = col0 % p.head_dim;  // chunk-uniform: head_dim, rope_dim are multiples of 32
-          if (col0 < p.rope_cols && cih < p.rope_dim) {
-            const float2* tab = p.rope + static_cast<long long>(pos) * (p.rope_dim >> 1) + (cih >> 1);
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float4 cs = __ldg(reinterpret_cast<const float4*>(tab + j));  // (cos, sin) of two pairs
-              const float s0 = cs.y * p.rope_sign, s1 = cs.w * p.rope_sign;
-              const float x0 = v[2 * j], x1 = v[2 * j + 1], y0 = v[2 * j + 2], y1 = v[2 * j + 3];
-              v[2 * j] = x0 * cs.x - x1 * s0;
-              v[2 * j + 1] = x1 * cs.x + x0 * s0;
-              v[2 * j + 2] = y0 * cs.z - y1 * s1;
-              v[2 * j + 3] = y1 * cs.z + y0 * s1;
-            }
-          }
-        }
-
-        if (row_ok) {
-          if (p.d_transposed) {
-            if (p.d_f32) {
-              float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = v[j];
-            } else {
-              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = __float2bfloat16(v[j]);
-            }
-          } else if (p.d_f32) {
-            float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dp[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0), pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2), pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(dp + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
-            }
-          }
-        }
+        epi_bar_sync();  // epi_flag is reused by the next unit
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -506,7 +589,7 @@ static int num_sms() {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
+static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
@@ -515,7 +598,6 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
-  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -524,12 +606,12 @@ static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
 }
 
 template <int BN>
-static int dispatch_major(const GemmKParams& kp, bool a_mn, bool b_mn, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(kp, s);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(kp, s);
+static int dispatch_major(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(kp, grid, s);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(kp, grid, s);
   if constexpr (BN % 64 == 0) {
-    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(kp, s);
-    return launch_gemm<BN, true, true>(kp, s);
+    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(kp, grid, s);
+    return launch_gemm<BN, true, true>(kp, grid, s);
   } else {
     return set_error(TRIBE_EINVAL, "block_n=160 requires a K-major B operand");
   }
@@ -599,12 +681,34 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   if (g->rope && !al16(g->rope)) return set_error(TRIBE_EINVAL, "gemm: rope table must be 16-byte aligned");
   kp.vec_ok = vec ? 1 : 0;
 
+  // ---- schedule: whole tiles round-robin; the ragged last wave is split along K when a workspace is provided
+  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  kp.full_tiles = kp.num_tiles, kp.tail_units = 0, kp.split = 1, kp.kb_per = kp.num_kb;
+  if (g->splitk_ws && !g->kgroup && kp.num_tiles > grid && al16(g->splitk_ws)) {
+    const int full = (kp.num_tiles / grid) * grid;
+    const int rem = kp.num_tiles - full;
+    if (rem > 0 && rem <= kMaxTailTiles) {
+      int split = grid / rem;
+      if (split > kp.num_kb / 4) split = kp.num_kb / 4;  // keep >= 4 K-blocks (256 deep) per slice
+      if (split > 16) split = 16;
+      const size_t need = static_cast<size_t>(kMaxTailTiles) * sizeof(int) + static_cast<size_t>(rem) * BM * bn * sizeof(float);
+      if (split >= 2 && need <= static_cast<size_t>(g->splitk_ws_bytes)) {
+        kp.kb_per = (kp.num_kb + split - 1) / split;
+        kp.split = (kp.num_kb + kp.kb_per - 1) / kp.kb_per;
+        kp.full_tiles = full;
+        kp.tail_units = rem * kp.split;
+        kp.counters = reinterpret_cast<int*>(g->splitk_ws);
+        kp.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g->splitk_ws) + kMaxTailTiles * sizeof(int));
+      }
+    }
+  }
+
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 128: return dispatch_major<128>(kp, a_mn, b_mn, s);
-    case 160: return dispatch_major<160>(kp, a_mn, b_mn, s);
-    case 192: return dispatch_major<192>(kp, a_mn, b_mn, s);
-    default: return dispatch_major<256>(kp, a_mn, b_mn, s);
+    case 128: return dispatch_major<128>(kp, grid, a_mn, b_mn, s);
+    case 160: return dispatch_major<160>(kp, grid, a_mn, b_mn, s);
+    case 192: return dispatch_major<192>(kp, grid, a_mn, b_mn, s);
+    default: return dispatch_major<256>(kp, grid, a_mn, b_mn, s);
   }
 }
 

@@ -426,9 +426,14 @@ class Engine:
             ia, iff = 2 * l, 2 * l + 1
             small = [f"{f}.1.ff.0.0.bias", f"{f}.1.ff.2.bias", f"{a}.0.0.g", f"{a}.2.residual_scale", f"{f}.0.0.g", f"{f}.2.residual_scale"]
             gs = {n: tgt(n) for n in small}
-            for n in (f"{a}.0.0.g", f"{a}.2.residual_scale", f"{f}.0.0.g", f"{f}.2.residual_scale"):
-                if not acc[n]:
-                    gs[n].zero_()
+            atomics = (f"{a}.0.0.g", f"{a}.2.residual_scale", f"{f}.0.0.g", f"{f}.2.residual_scale")  # adjacent in the flat layout
+            if not any(acc[n] for n in atomics):
+                lo, hi = fl.offsets[atomics[0]], fl.offsets[atomics[-1]] + H
+                fl.grad[lo:hi].zero_()  # one fill per layer for every atomically accumulated small gradient
+            else:
+                for n in atomics:
+                    if not acc[n]:
+                        gs[n].zero_()
             # ================= feed-forward sub-layer (x_out = FF(norm(x_in)) + x_in * rs)
             w2, w1 = self._w16(f"{f}.1.ff.2.weight"), self._w16(f"{f}.1.ff.0.0.weight")
             # d_hpre = (dx @ W2) * gelu'(hpre)          W2 (H, F): MN-major B (N = F contiguous, K = H rows)

@@ -101,6 +101,9 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
     g.ld_res, g.res_row_mod, g.res_batched, g.ld_aux = ld_res, res_row_mod, int(res_batched), ld_aux
     g.rope_t, g.rope_dim, g.head_dim, g.rope_cols, g.rope_sign = rope_t, rope_dim, head_dim, rope_cols, rope_sign
     g.block_n = block_n
+    if SPLITK:
+        ws = _splitk_workspace(out.device)
+        g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     lib = _lib.load()
     log = GEMM_LOG
     if log is not None:
@@ -117,6 +120,19 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
 
 # bench.py sets this to a list to collect (start event, end event, algorithmic FLOPs) per GEMM launch
 GEMM_LOG = None
+
+# Split-K tail scheduling (ragged last wave of tiles split along K over idle SMs); one zeroed 20 MiB workspace per
+# device, used by the GEMMs of the current stream only (the kernel leaves it zeroed).
+SPLITK = True
+_SPLITK_WS: dict = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = _SPLITK_WS[key] = torch.zeros(20 * 1024 * 1024 + 1024, device=device, dtype=torch.uint8)
+    return ws
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> None:

@@ -98,6 +98,11 @@ typedef struct TribeGemm {
   int32_t rope_dim, head_dim, rope_cols;
   float rope_sign;
   int32_t block_n;        /* 0: auto; else one of 128, 160, 192, 256 */
+  /* optional split-K workspace (caller-owned, ZERO-initialised once, >= 640 B + tail_tiles*128*block_n*4 B; 20 MiB
+   * always suffices): lets the ragged last wave of tiles be split along K over otherwise idle SMs.  The kernel
+   * leaves it zeroed.  Must not be shared by GEMMs running concurrently on different streams. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
 } TribeGemm;
 
 int tribe_gemm_bf16(const TribeGemm* g, void* stream);

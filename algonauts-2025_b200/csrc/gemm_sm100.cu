@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -688,8 +689,13 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
     const int full = (kp.num_tiles / grid) * grid;
     const int rem = kp.num_tiles - full;
     if (rem > 0 && rem <= kMaxTailTiles) {
+      static const int min_kb = [] {
+        const char* e = getenv("TRIBE_SPLITK_MIN_KB");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 16;
+      }();
       int split = grid / rem;
-      if (split > kp.num_kb / 4) split = kp.num_kb / 4;  // keep >= 4 K-blocks (256 deep) per slice
+      if (split > kp.num_kb / min_kb) split = kp.num_kb / min_kb;  // keep >= min_kb K-blocks (1024 deep) per slice: fewer atomics
       if (split > 16) split = 16;
       const size_t need = static_cast<size_t>(kMaxTailTiles) * sizeof(int) + static_cast<size_t>(rem) * BM * bn * sizeof(float);
       if (split >= 2 && need <= static_cast<size_t>(g->splitk_ws_bytes)) {

@@ -78,8 +78,12 @@ def main():
     ms, tf = timeit(lambda: torch.matmul(a, b.t()), 2 * M * F * H)
     print(f"{'cuBLAS bf16 M4768 N12288 K3072 (context)':58s} {ms*1e3:8.1f} us {tf:8.1f} TFLOP/s {tf/peak:6.1%} of burst peak")
     for name, (fn, flops) in cases.items():
+        ops.SPLITK = True
         ms, tf = timeit(fn, flops)
-        print(f"{name:58s} {ms*1e3:8.1f} us {tf:8.1f} TFLOP/s {tf/peak:6.1%} of burst peak", flush=True)
+        ops.SPLITK = False
+        ms0, tf0 = timeit(fn, flops)
+        ops.SPLITK = True
+        print(f"{name:58s} {ms*1e3:8.1f} us {tf:8.1f} TFLOP/s {tf/peak:6.1%} of burst peak | no split-K tail: {ms0*1e3:8.1f} us {tf0:8.1f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -445,8 +445,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         mbar_arrive(&tempty_bar[acc]);
       } else {
         // K-slice of a tail tile: reduce into the fp32 workspace, last arriver finishes the tile.
+        // Phase 1: this CTA's K-slice partial goes to its own fp32 slot (plain 16-byte stores).
+        // Phase 2: once all `split` slices of the tile have landed (arrival counter; every tail unit is resident
+        // concurrently: one per CTA, grid <= #SMs), slice s reduces and finishes the 32-column chunks c = s mod split.
         const int ti = w.tile - p.full_tiles;
-        float* wrow = p.ws + (static_cast<size_t>(ti) * BM + row_in_tile) * BN;
+        const int slice = (blockIdx.x + it * gridDim.x - p.full_tiles) % p.split;
+        float* tile_ws = p.ws + static_cast<size_t>(ti) * p.split * (BM * BN);
+        float* wrow = tile_ws + static_cast<size_t>(slice) * (BM * BN) + static_cast<size_t>(row_in_tile) * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           if (t.n0 + c * 32 >= p.n) break;
@@ -455,37 +460,49 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            atomicAdd(reinterpret_cast<float4*>(wrow + c * 32 + j),
-                      make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])));
+            __stcg(reinterpret_cast<float4*>(wrow + c * 32 + j),
+                   make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])));
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
         __threadfence();
         epi_bar_sync();
+        int* arrive = p.counters + 2 * ti;
+        int* depart = arrive + 1;
         if (warp == 2 && lane == 0) {
-          const int old = atomicAdd(p.counters + ti, 1);
-          *epi_flag = (old == p.split - 1) ? 1u : 0u;
-          if (old == p.split - 1) p.counters[ti] = 0;  // ready for the next launch
+          atomicAdd(arrive, 1);
+          while (atomicAdd(arrive, 0) < p.split) __nanosleep(64);
+          __threadfence();
         }
         epi_bar_sync();
-        if (*epi_flag) {
-          __threadfence();
+        const float* rrow = tile_ws + static_cast<size_t>(row_in_tile) * BN;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            const int col0 = t.n0 + c * 32;
-            if (col0 >= p.n) break;
-            float v[32];
+        for (int c = slice; c < BN / 32; c += p.split) {
+          const int col0 = t.n0 + c * 32;
+          if (col0 >= p.n) break;
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4* wp = reinterpret_cast<float4*>(wrow + c * 32 + j);
-              const float4 s4 = __ldcg(wp);
-              __stcg(wp, make_float4(0.f, 0.f, 0.f, 0.f));  // leave the workspace zeroed for the next launch
-              v[j] = s4.x * p.alpha, v[j + 1] = s4.y * p.alpha, v[j + 2] = s4.z * p.alpha, v[j + 3] = s4.w * p.alpha;
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int s2 = 0; s2 < p.split; ++s2) {
+            const float4* src = reinterpret_cast<const float4*>(rrow + static_cast<size_t>(s2) * (BM * BN) + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 s4 = __ldcg(src + j);
+              v[4 * j] += s4.x, v[4 * j + 1] += s4.y, v[4 * j + 2] += s4.z, v[4 * j + 3] += s4.w;
             }
-            epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
+        }
+        epi_bar_sync();
+        if (warp == 2 && lane == 0) {
+          if (atomicAdd(depart, 1) == p.split - 1) {  // last slice out resets the tile's counters for the next launch
+            *arrive = 0;
+            *depart = 0;
+            __threadfence();
           }
         }
-        epi_bar_sync();  // epi_flag is reused by the next unit
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -692,19 +709,21 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
       static const int min_kb = [] {
         const char* e = getenv("TRIBE_SPLITK_MIN_KB");
         const int v = e ? atoi(e) : 0;
-        return v > 0 ? v : 16;
+        return v > 0 ? v : 8;
       }();
       int split = grid / rem;
-      if (split > kp.num_kb / min_kb) split = kp.num_kb / min_kb;  // keep >= min_kb K-blocks (1024 deep) per slice: fewer atomics
-      if (split > 16) split = 16;
-      const size_t need = static_cast<size_t>(kMaxTailTiles) * sizeof(int) + static_cast<size_t>(rem) * BM * bn * sizeof(float);
-      if (split >= 2 && need <= static_cast<size_t>(g->splitk_ws_bytes)) {
+      if (split > kp.num_kb / min_kb) split = kp.num_kb / min_kb;  // keep >= min_kb K-blocks per slice
+      if (split > bn / 32) split = bn / 32;                        // phase 2 hands out 32-column chunks
+      const size_t head = static_cast<size_t>(kMaxTailTiles) * 2 * sizeof(int);
+      const size_t per_slot = static_cast<size_t>(BM) * bn * sizeof(float);
+      while (split >= 2 && head + static_cast<size_t>(rem) * split * per_slot > static_cast<size_t>(g->splitk_ws_bytes)) --split;
+      if (split >= 2) {
         kp.kb_per = (kp.num_kb + split - 1) / split;
         kp.split = (kp.num_kb + kp.kb_per - 1) / kp.kb_per;
         kp.full_tiles = full;
         kp.tail_units = rem * kp.split;
         kp.counters = reinterpret_cast<int*>(g->splitk_ws);
-        kp.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g->splitk_ws) + kMaxTailTiles * sizeof(int));
+        kp.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g->splitk_ws) + head);
       }
     }
   }

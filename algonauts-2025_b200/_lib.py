@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(CSRC, "libtribe_b200.so")
-SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu", "contrastive.cu"]
+SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu", "contrastive.cu", "pool.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               f"-I{INCLUDE}", f"-I{CSRC}"]
 
@@ -143,6 +143,7 @@ _SIGS = {
     "tribe_nce_loss": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp],
     "tribe_nce_grad": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp],
     "tribe_cast_bf16_f32": [c_vp, c_vp, c_i64, c_vp],
+    "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["tribe_last_error", "tribe_abi_version", "tribe_launch_count"])
 

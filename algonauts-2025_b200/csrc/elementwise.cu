@@ -388,95 +388,6 @@ __device__ __forceinline__ int win_end(int i, int t_in, int t_out) {
   return static_cast<int>((static_cast<int64_t>(i + 1) * t_in + t_out - 1) / t_out);
 }
 
-// x fp32 (rows, t_in) -> y fp32 (rows, t_out).  A block stages R consecutive rows (contiguous in memory: one coalesced
-// float4 stream) in shared memory next to a per-block window table, then emits R*t_out contiguous outputs.
-// reference: nn.AdaptiveAvgPool1d(n_output_timesteps), algonauts2025/model.py:60,119-122.
-template <int R>
-__global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int t_in,
-                                                       int t_out) {
-  extern __shared__ float sm[];
-  float* data = sm;                                             // R * t_in
-  int* wstart = reinterpret_cast<int*>(sm + R * t_in);          // t_out
-  int* wlen = wstart + t_out;                                   // t_out
-  for (int i = threadIdx.x; i < t_out; i += blockDim.x) {
-    const int s0 = win_start(i, t_in, t_out), e0 = win_end(i, t_in, t_out);
-    wstart[i] = s0;
-    wlen[i] = e0 - s0;
-  }
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * R;
-  const int nr = static_cast<int>(min(static_cast<int64_t>(R), rows - r0));
-  const int n_in = nr * t_in;
-  const float* src = x + r0 * t_in;
-  if (((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    const int nv = n_in >> 2;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(data)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-    for (int i = (nv << 2) + threadIdx.x; i < n_in; i += blockDim.x) data[i] = __ldg(src + i);
-  } else {
-    for (int i = threadIdx.x; i < n_in; i += blockDim.x) data[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const int n_out = nr * t_out;
-  float* dst = y + r0 * t_out;
-  // o = r * t_out + i walks in steps of blockDim.x without divisions
-  int r = threadIdx.x / t_out, i = threadIdx.x - r * t_out;
-  const int dr = blockDim.x / t_out, di = blockDim.x - dr * t_out;
-  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-    const int s0 = wstart[i], len = wlen[i];
-    const float* row = data + r * t_in + s0;
-    float acc = 0.f;
-    for (int t = 0; t < len; ++t) acc += row[t];
-    dst[o] = acc / static_cast<float>(len);
-    r += dr, i += di;
-    if (i >= t_out) i -= t_out, ++r;
-  }
-}
-
-// dx[r, t] = sum over the (contiguous) run of windows containing t of dy[r, i] / len_i.
-template <int R>
-__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int64_t rows, int t_in,
-                                                       int t_out) {
-  extern __shared__ float sm[];
-  float* dyv = sm;                                              // R * t_out
-  float* winv = sm + R * t_out;                                 // t_out : 1 / len_i
-  int* ilo = reinterpret_cast<int*>(winv + t_out);              // t_in  : first window containing t
-  int* icnt = ilo + t_in;                                       // t_in  : number of windows containing t
-  for (int i = threadIdx.x; i < t_out; i += blockDim.x) winv[i] = 1.0f / static_cast<float>(win_end(i, t_in, t_out) - win_start(i, t_in, t_out));
-  for (int t = threadIdx.x; t < t_in; t += blockDim.x) {
-    int lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
-    int hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);  // exclusive upper bound of candidates
-    if (hi > t_out) hi = t_out;
-    while (lo < hi && !(t >= win_start(lo, t_in, t_out) && t < win_end(lo, t_in, t_out))) ++lo;
-    while (hi > lo && !(t >= win_start(hi - 1, t_in, t_out) && t < win_end(hi - 1, t_in, t_out))) --hi;
-    ilo[t] = lo;
-    icnt[t] = hi - lo;
-  }
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * R;
-  const int nr = static_cast<int>(min(static_cast<int64_t>(R), rows - r0));
-  const int n_o = nr * t_out;
-  const float* src = dy + r0 * t_out;
-  if (((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    const int nv = n_o >> 2;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<float4*>(dyv)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-    for (int i = (nv << 2) + threadIdx.x; i < n_o; i += blockDim.x) dyv[i] = __ldg(src + i);
-  } else {
-    for (int i = threadIdx.x; i < n_o; i += blockDim.x) dyv[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const int n_i = nr * t_in;
-  float* dst = dx + r0 * t_in;
-  int r = threadIdx.x / t_in, t = threadIdx.x - r * t_in;
-  const int dr = blockDim.x / t_in, dt = blockDim.x - dr * t_in;
-  for (int o = threadIdx.x; o < n_i; o += blockDim.x) {
-    const int lo = ilo[t], cnt = icnt[t];
-    const float* row = dyv + r * t_out;
-    float acc = 0.f;
-    for (int k = 0; k < cnt; ++k) acc += row[lo + k] * winv[lo + k];
-    dst[o] = acc;
-    r += dr, t += dt;
-    if (t >= t_in) t -= t_in, ++r;
-  }
-}
-
 // token-major pooling: x bf16 (B, t_in, C) -> y bf16 (B, t_out, C); 8 channels (16 B) per thread.
 __global__ void __launch_bounds__(256) token_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int t_in,
                                                              int t_out, int64_t C) {
@@ -682,38 +593,6 @@ extern "C" int tribe_axpby_f32(const float* src, float* dst, float a, int32_t ac
   if (!src || !dst || n <= 0) return set_error(TRIBE_EINVAL, "axpby: bad arguments");
   axpby_kernel<<<grid_for(n, 256, kMaxBlocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, a, accumulate, n);
   TRIBE_CHECK_LAUNCH("axpby");
-  return TRIBE_OK;
-}
-
-extern "C" int tribe_adaptive_avg_pool_fwd(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, void* stream) {
-  if (!x || !y || rows <= 0 || t_in <= 0 || t_out <= 0) return set_error(TRIBE_EINVAL, "pool_fwd: bad arguments");
-  constexpr int R = 32;
-  const size_t smem = sizeof(float) * (R * t_in + 2 * t_out);
-  if (smem > 200 * 1024) return set_error(TRIBE_EINVAL, "pool_fwd: t_in too large");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(pool_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
-  pool_fwd_kernel<R><<<static_cast<unsigned>((rows + R - 1) / R), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, y, rows, static_cast<int>(t_in), static_cast<int>(t_out));
-  TRIBE_CHECK_LAUNCH("pool_fwd");
-  return TRIBE_OK;
-}
-
-extern "C" int tribe_adaptive_avg_pool_bwd(const float* dy, float* dx, int64_t rows, int64_t t_in, int64_t t_out, void* stream) {
-  if (!dy || !dx || rows <= 0 || t_in <= 0 || t_out <= 0) return set_error(TRIBE_EINVAL, "pool_bwd: bad arguments");
-  constexpr int R = 32;
-  const size_t smem = sizeof(float) * (R * t_out + t_out + 2 * t_in);
-  if (smem > 200 * 1024) return set_error(TRIBE_EINVAL, "pool_bwd: t_out too large");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(pool_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
-  pool_bwd_kernel<R><<<static_cast<unsigned>((rows + R - 1) / R), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dy, dx, rows, static_cast<int>(t_in), static_cast<int>(t_out));
-  TRIBE_CHECK_LAUNCH("pool_bwd");
   return TRIBE_OK;
 }
 

@@ -1,0 +1,71 @@
+// Fused Adam step over a flat fp32 parameter range that ALSO emits the bf16 shadow weights the tensor cores read
+// (one pass: 16 B read + 14 B written per parameter instead of torch's multi-tensor Adam followed by a separate cast).
+// Same arithmetic as torch.optim.Adam (amsgrad=False, maximize=False), reference recipe
+// algonauts2025/grids/defaults.py:126-141 (Adam lr 1e-4, weight_decay 0, OneCycleLR stepping per batch).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tribe_b200.h"
+#include "tribe_internal.h"
+
+namespace tribe {
+
+__device__ __forceinline__ uint32_t opt_pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float beta1, float beta2, float step_size, float inv_bc2_sqrt,
+                                         float eps, float wd) {
+  if (wd != 0.f) g = fmaf(wd, p, g);
+  m = m + (g - m) * (1.0f - beta1);           // exp_avg.lerp_(grad, 1 - beta1)
+  v = beta2 * v + (1.0f - beta2) * g * g;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   __nv_bfloat16* __restrict__ p16, int64_t n, float beta1, float beta2, float step_size,
+                                                   float inv_bc2_sqrt, float eps, float wd) {
+  const int64_t nvec = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+    adam_one(pp.y, gg.y, mm.y, vv.y, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+    adam_one(pp.z, gg.z, mm.z, vv.z, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+    adam_one(pp.w, gg.w, mm.w, vv.w, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (p16) reinterpret_cast<uint2*>(p16)[i] = make_uint2(opt_pack2(pp.x, pp.y), opt_pack2(pp.z, pp.w));
+  }
+  for (int64_t i = (nvec << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_one(pp, g[i], mm, vv, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+    p[i] = pp, m[i] = mm, v[i] = vv;
+    if (p16) p16[i] = __float2bfloat16(pp);
+  }
+}
+
+}  // namespace tribe
+
+extern "C" int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int64_t step, void* stream) {
+  using namespace tribe;
+  if (!p || !g || !m || !v || n <= 0 || step <= 0) return set_error(TRIBE_EINVAL, "adam_step: bad arguments");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v);
+  if ((al & 15) || (reinterpret_cast<uintptr_t>(p_bf16) & 7)) return set_error(TRIBE_EINVAL, "adam_step: buffers must be 16-byte aligned (bf16: 8)");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, beta1, beta2, step_size, inv_bc2_sqrt, eps, weight_decay);
+  TRIBE_CHECK_LAUNCH("adam_step");
+  return TRIBE_OK;
+}

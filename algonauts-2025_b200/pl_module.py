@@ -139,4 +139,11 @@ class BrainModule(_Base):
     def configure_optimizers(self):
         optim_config = self.optim_config.copy()
         unfrozen_params = [p for p in self.parameters() if p.requires_grad]
-        return optim_config.build(unfrozen_params, total_steps=self.trainer.estimated_stepping_batches)
+        out = optim_config.build(unfrozen_params, total_steps=self.trainer.estimated_stepping_batches)
+        # A stock torch.optim.Adam (the reference recipe, defaults.py:126-141) is adopted in place by the fused
+        # Adam(+bf16 shadow) kernel; any other optimizer is left untouched.
+        from .optim import TribeAdam
+
+        opt = out["optimizer"] if isinstance(out, dict) else out
+        TribeAdam.adopt(opt, self.model)
+        return out

@@ -9,12 +9,19 @@ import typing as tp
 import torch
 
 
-def default_optimizer(params, total_steps: int, lr: float = 1e-4):
+def default_optimizer(params, total_steps: int, lr: float = 1e-4, model=None, fused_kernel: bool = True):
     """Adam(lr=1e-4, weight_decay=0) + OneCycleLR(max_lr=1e-4, pct_start=0.1), stepped per batch
-    (algonauts2025/grids/defaults.py:126-141, modeling_utils/optimizers/base.py:84-96).  Stock torch optimizer."""
+    (algonauts2025/grids/defaults.py:126-141, modeling_utils/optimizers/base.py:84-96).  With ``model`` given the
+    stock torch.optim.Adam instance is adopted by ``TribeAdam`` (same object, fused Adam + bf16 shadow kernel) — what
+    ``BrainModule.configure_optimizers`` does; otherwise torch's own fused multi-tensor Adam runs."""
     params = list(params)
-    opt = torch.optim.Adam(params, lr=lr, weight_decay=0.0, fused=params[0].is_cuda)
+    use_kernel = model is not None and fused_kernel
+    opt = torch.optim.Adam(params, lr=lr, weight_decay=0.0, fused=params[0].is_cuda and not use_kernel)
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=lr, pct_start=0.1, total_steps=max(total_steps, 2))
+    if use_kernel:
+        from .optim import TribeAdam
+
+        TribeAdam.adopt(opt, model)
     return opt, sched
 
 

@@ -161,7 +161,9 @@ def run_ours(args):
     cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3, feature_aggregation="cat", layer_aggregation="cat", contrastive_enabled=contrastive)
     model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
     module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=15)
-    opt, sched = default_optimizer(model.parameters(), total_steps=2 * (K + W) + 8)
+    # the reference recipe (Adam lr 1e-4 + OneCycleLR per step); the stock torch.optim.Adam instance is adopted by the
+    # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
+    opt, sched = default_optimizer(model.parameters(), total_steps=2 * (K + W) + 8, model=None if args.stock_adam else model)
     sync = parallel.GradAllReduce(model) if world > 1 else None
     trainer = MiniTrainer(module, opt, sched, grad_sync=sync)
     if sync is not None:
@@ -232,7 +234,7 @@ def run_ours(args):
         line = {"metric": "train windows/s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
-                           "optimizer": "Adam(fused)+OneCycleLR, fp32 master weights", "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
+                           "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel)") + " + OneCycleLR, fp32 master weights", "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
                            "last_loss": last},
                 "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
@@ -257,6 +259,7 @@ def main():
     ap.add_argument("--contrastive", type=int, default=0)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -214,6 +214,14 @@ int tribe_nce_grad(const float* logits, int64_t n, int64_t ld, float shift, cons
 /* bf16 -> fp32 cast (latents handed back to torch as fp32, model.py:178-183). */
 int tribe_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Optimizer: one fused torch.optim.Adam step (amsgrad=False, maximize=False; recipe algonauts2025/grids/defaults.py:
+ * 126-141) over a flat fp32 range, writing the bf16 shadow weights in the same pass (p_bf16 may be NULL).
+ * `step` is the 1-based step count used for the bias corrections.
+ */
+int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,8 +44,8 @@ def test_fused_adam_matches_torch_adam_with_onecycle_and_skipped_params():
         torch.testing.assert_close(p.detach(), ref[n].detach(), rtol=2e-5, atol=1e-7, msg=n)
         st, rst = opt.state[p], ropt.state[ref[n]]
         assert float(st["step"]) == float(rst["step"]), n
-        torch.testing.assert_close(st["exp_avg"], rst["exp_avg"], rtol=2e-5, atol=1e-9)
-        torch.testing.assert_close(st["exp_avg_sq"], rst["exp_avg_sq"], rtol=2e-5, atol=1e-12)
+        torch.testing.assert_close(st["exp_avg"], rst["exp_avg"], rtol=2e-5, atol=5e-6)  # |grad| up to ~5: fp32 rounding of the lerp
+        torch.testing.assert_close(st["exp_avg_sq"], rst["exp_avg_sq"], rtol=2e-5, atol=1e-5)
         # the bf16 shadow was written by the same kernel
         assert torch.equal(eng.flat.view16(n), p.detach().to(torch.bfloat16)), n
     # the engine does not re-cast after a fused step ...

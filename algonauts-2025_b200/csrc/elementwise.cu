@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restr
 //   dx_in[c] = sqrt(dim) g rnorm (d_xn[c] - x_in[c] rnorm dot) + dy_out[c] * rs[c]
 //   d_rs[c] += dy_out[c] * x_in[c]        d_g += sqrt(dim) * dot
 // Each block walks a strided set of rows and keeps its d_rs column partials in registers (dim <= 4096).
-__global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
+template <int NV>
+__global__ void __launch_bounds__(256, NV <= 3 ? 3 : 2) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
                                                            const float* __restrict__ x_in, const float* __restrict__ rnorm,
                                                            const float* __restrict__ g, const float* __restrict__ rs,
                                                            float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
@@ -157,19 +158,19 @@ __global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __res
   const int nvec = dim >> 2;
   const float sqrt_dim = sqrtf(static_cast<float>(dim));
   const float gval = g ? __ldg(g) : 0.f;
-  float4 rs_acc[4];
+  float4 rs_acc[NV];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) rs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) rs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float dg_acc = 0.f;
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const float4* xr = reinterpret_cast<const float4*>(x_in + row * dim);
     const float4* dyr = dy_out ? reinterpret_cast<const float4*>(dy_out + row * dim) : nullptr;
     const uint2* dnr = d_xn ? reinterpret_cast<const uint2*>(d_xn + row * dim) : nullptr;
     // issue every global load of this row before the block reduction (memory-level parallelism)
-    float4 xc[4], dn[4], dyv[4];
-    uint2 dnraw[4];
+    float4 xc[NV], dn[NV], dyv[NV];
+    uint2 dnraw[NV];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = threadIdx.x + i * 256;
       if (v < nvec) {
         xc[i] = __ldg(xr + v);
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __res
     float dot = 0.f;
     if (dnr) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         const int v = threadIdx.x + i * 256;
         if (v < nvec) {
           const float2 a = unpack_bf16x2(dnraw[i].x), b = unpack_bf16x2(dnraw[i].y);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __res
       dg_acc += dot;  // identical in every thread; thread 0 publishes
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = threadIdx.x + i * 256;
       if (v < nvec) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __res
   }
   if (d_rs) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = threadIdx.x + i * 256;
       if (v < nvec) {
         atomicAdd(d_rs + 4 * v, rs_acc[i].x), atomicAdd(d_rs + 4 * v + 1, rs_acc[i].y);
@@ -515,10 +516,18 @@ extern "C" int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, co
                                   void* stream) {
   if (!x_in || rows <= 0 || dim <= 0 || dim % 4 || dim > 4096) return set_error(TRIBE_EINVAL, "sublayer_bwd: bad arguments (dim % 4, dim <= 4096)");
   if (d_xn_bf16 && (!rnorm || !g)) return set_error(TRIBE_EINVAL, "sublayer_bwd: d_xn needs rnorm and g");
-  const int grid = grid_for(rows, 2, 148 * 2);
-  sublayer_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dy_out, reinterpret_cast<const __nv_bfloat16*>(d_xn_bf16), x_in, rnorm, g, rs, dx_in, reinterpret_cast<__nv_bfloat16*>(dx_in_bf16), d_rs, d_g,
-      rows, static_cast<int>(dim));
+  const int nv = static_cast<int>((dim / 4 + 255) / 256);
+  const int grid = grid_for(rows, 2, 148 * (nv <= 3 ? 3 : 2));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* dxn = reinterpret_cast<const __nv_bfloat16*>(d_xn_bf16);
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_in_bf16);
+  const int d = static_cast<int>(dim);
+  switch (nv) {
+    case 1: sublayer_bwd_kernel<1><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
+    case 2: sublayer_bwd_kernel<2><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
+    case 3: sublayer_bwd_kernel<3><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
+    default: sublayer_bwd_kernel<4><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
+  }
   TRIBE_CHECK_LAUNCH("sublayer_bwd");
   return TRIBE_OK;
 }

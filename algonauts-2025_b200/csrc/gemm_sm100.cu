@@ -67,7 +67,7 @@ struct alignas(64) GemmKParams {
   int rope_t, rope_dim, head_dim, rope_cols;
   float rope_sign;
   uint32_t k_lbo, k_sbo, mn_lbo, mn_sbo;
-  int m_blocks, n_blocks, num_tiles, num_kb;
+  int m_blocks, n_blocks, num_tiles, num_kb, raster_n_fast;
   // split-K tail
   int full_tiles, tail_units, split, kb_per;
   float* ws;
@@ -96,10 +96,18 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int bn) {
   TileCoord t;
-  int mb = tile % p.m_blocks;
-  int rest = tile / p.m_blocks;
-  int nb = rest % p.n_blocks;
-  t.z = rest / p.n_blocks;
+  int mb, nb, rest;
+  if (p.raster_n_fast) {  // consecutive tiles (one wave) share an A row-block and sweep B: B is the re-read operand
+    nb = tile % p.n_blocks;
+    rest = tile / p.n_blocks;
+    mb = rest % p.m_blocks;
+    t.z = rest / p.m_blocks;
+  } else {                // consecutive tiles share a B column-block and sweep A: A is the re-read operand
+    mb = tile % p.m_blocks;
+    rest = tile / p.m_blocks;
+    nb = rest % p.n_blocks;
+    t.z = rest / p.n_blocks;
+  }
   t.zi = t.z % p.z_inner;
   t.zo = t.z / p.z_inner;
   t.m0 = mb * BM;
@@ -688,6 +696,9 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.mn_lbo = mn_lbo ? mn_lbo : BK * 128, kp.mn_sbo = mn_sbo ? mn_sbo : 1024;
   kp.m_blocks = (g->m + BM - 1) / BM, kp.n_blocks = (g->n + bn - 1) / bn;
   kp.num_tiles = kp.m_blocks * kp.n_blocks * g->batch, kp.num_kb = (g->k + BK - 1) / BK;
+  // Tile order: every wave of ~#SM tiles streams one operand completely and re-reads the other; re-read the smaller
+  // one so that it stays L2-resident (126 MB) — e.g. FF2 (A = 117 MB activations, B = 75 MB weights) goes N-fastest.
+  kp.raster_n_fast = (static_cast<double>(g->m) > static_cast<double>(g->n)) ? 1 : 0;
   // 16-byte vector epilogue accesses need aligned bases / leading dimensions.
   const int esz = g->d_f32 ? 4 : 2;
   auto al16 = [](const void* p_) { return (reinterpret_cast<uintptr_t>(p_) & 15) == 0; };

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__
   int64_t chunk = blockIdx.x;
   if (chunk < nchunks) stage_chunk(buf[0], x + chunk * chunk_floats, rows_in_chunk(rows, chunk) * t_in);
   cp_async_commit();
-  const int dr = blockDim.x / t_out, di = blockDim.x - dr * t_out;
+  const int ix = threadIdx.x & 127, iy = threadIdx.x >> 7;
   int cur = 0;
   for (; chunk < nchunks; chunk += gridDim.x) {
     const int64_t next = chunk + gridDim.x;
@@ -64,18 +64,29 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__
     cp_async_wait<1>();
     __syncthreads();
     const int nr = rows_in_chunk(rows, chunk);
-    const int n_out = nr * t_out;
     const float* data = buf[cur];
     float* dst = y + chunk * kPoolRows * t_out;
-    int r = threadIdx.x / t_out, i = threadIdx.x - r * t_out;
-    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    // thread = (output index i, row group): the window of i is looked up once and reused for every row of the group;
+    // for a fixed row consecutive threads write consecutive outputs (coalesced) and read smem at a stride of ~T/T'.
+    for (int i = ix; i < t_out; i += 128) {
       const int s0 = wstart[i], len = wlen[i];
-      const float* row = data + r * t_in + s0;
-      float acc = 0.f;
-      for (int t = 0; t < len; ++t) acc += row[t];
-      dst[o] = acc / static_cast<float>(len);
-      r += dr, i += di;
-      if (i >= t_out) i -= t_out, ++r;
+      const float inv = 1.0f / static_cast<float>(len);
+      if (len <= 4) {
+        const int k1 = len > 1 ? 1 : 0, k2 = len > 2 ? 2 : 0, k3 = len > 3 ? 3 : 0;
+        const float m1 = len > 1 ? 1.f : 0.f, m2 = len > 2 ? 1.f : 0.f, m3 = len > 3 ? 1.f : 0.f;
+#pragma unroll 4
+        for (int r = iy; r < nr; r += 2) {
+          const float* row = data + r * t_in + s0;
+          dst[r * t_out + i] = (row[0] + m1 * row[k1] + m2 * row[k2] + m3 * row[k3]) * inv;
+        }
+      } else {
+        for (int r = iy; r < nr; r += 2) {
+          const float* row = data + r * t_in + s0;
+          float acc = 0.f;
+          for (int t = 0; t < len; ++t) acc += row[t];
+          dst[r * t_out + i] = acc * inv;
+        }
+      }
     }
     __syncthreads();
     cur ^= 1;
@@ -105,7 +116,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
   int64_t chunk = blockIdx.x;
   if (chunk < nchunks) stage_chunk(buf[0], dy + chunk * chunk_floats, rows_in_chunk(rows, chunk) * t_out);
   cp_async_commit();
-  const int dr = blockDim.x / t_in, dt = blockDim.x - dr * t_in;
+  const int ix = threadIdx.x & 127, iy = threadIdx.x >> 7;
   int cur = 0;
   for (; chunk < nchunks; chunk += gridDim.x) {
     const int64_t next = chunk + gridDim.x;
@@ -114,18 +125,26 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
     cp_async_wait<1>();
     __syncthreads();
     const int nr = rows_in_chunk(rows, chunk);
-    const int n_i = nr * t_in;
     const float* dyv = buf[cur];
     float* dst = dx + chunk * kPoolRows * t_in;
-    int r = threadIdx.x / t_in, t = threadIdx.x - r * t_in;
-    for (int o = threadIdx.x; o < n_i; o += blockDim.x) {
+    for (int t = ix; t < t_in; t += 128) {
       const int lo = ilo[t], cnt = icnt[t];
-      const float* row = dyv + r * t_out;
-      float acc = 0.f;
-      for (int k = 0; k < cnt; ++k) acc += row[lo + k] * winv[lo + k];
-      dst[o] = acc;
-      r += dr, t += dt;
-      if (t >= t_in) t -= t_in, ++r;
+      if (cnt <= 2) {
+        const float w0 = cnt > 0 ? winv[lo] : 0.f, w1 = cnt > 1 ? winv[lo + 1] : 0.f;
+        const int k0 = cnt > 0 ? lo : 0, k1 = cnt > 1 ? lo + 1 : k0;
+#pragma unroll 4
+        for (int r = iy; r < nr; r += 2) {
+          const float* row = dyv + r * t_out;
+          dst[r * t_in + t] = row[k0] * w0 + row[k1] * w1;
+        }
+      } else {
+        for (int r = iy; r < nr; r += 2) {
+          const float* row = dyv + r * t_out;
+          float acc = 0.f;
+          for (int k = 0; k < cnt; ++k) acc += row[lo + k] * winv[lo + k];
+          dst[r * t_in + t] = acc;
+        }
+      }
     }
     __syncthreads();
     cur ^= 1;

@@ -20,9 +20,10 @@ from ._lib import TribeError
 
 ALIGN = 64  # elements; keeps every parameter view 16-byte aligned in fp32 and bf16
 
-# Bumped by a global optimizer post-step hook: fused CUDA optimizers update parameters through raw pointers, so the
-# per-tensor version counters alone are not a reliable "weights changed" signal for the bf16 shadow copy.
-_OPT_STEPS = [0]
+# Fused CUDA optimizers update parameters through raw pointers, so the per-tensor version counters alone are not a
+# reliable "weights changed" signal for the bf16 shadow copy: a global optimizer post-step hook bumps a counter on every
+# FlatParams whose parameters the stepping optimizer owns.
+_FLATS = []  # weak references to live FlatParams
 _HOOK = []
 
 
@@ -31,7 +32,15 @@ def _install_optimizer_hook():
         from torch.optim.optimizer import register_optimizer_step_post_hook
 
         def _bump(optimizer, args, kwargs):
-            _OPT_STEPS[0] += 1
+            alive = []
+            for ref in _FLATS:
+                flat = ref()
+                if flat is None:
+                    continue
+                alive.append(ref)
+                if any(id(p) in flat.param_ids for group in optimizer.param_groups for p in group["params"][:1]):
+                    flat.opt_steps += 1
+            _FLATS[:] = alive
 
         _HOOK.append(register_optimizer_step_post_hook(_bump))
 
@@ -68,6 +77,11 @@ class FlatParams:
         self.grad = None
         self.bf16 = None
         self._sig = None
+        self.param_ids = {id(p) for p in self.params.values()}
+        self.opt_steps = 0
+        import weakref
+
+        _FLATS.append(weakref.ref(self))
         _install_optimizer_hook()
 
     def intact(self) -> bool:
@@ -91,7 +105,7 @@ class FlatParams:
 
     def refresh_bf16(self):
         """Re-cast the bf16 shadow when any parameter changed in place (optimizer step, load_state_dict, SWA)."""
-        sig = (sum(p._version for p in self.params.values()), _OPT_STEPS[0])
+        sig = (sum(p._version for p in self.params.values()), self.opt_steps)
         if self.bf16 is None:
             self.bf16 = torch.empty(self.total, device=self.device, dtype=torch.bfloat16)
             self._sig = None

@@ -116,5 +116,5 @@ class TribeAdam(torch.optim.Adam):
                                           ctypes.c_void_p(flat.adam_m.data_ptr() + 4 * lo), ctypes.c_void_p(flat.adam_v.data_ptr() + 4 * lo),
                                           ctypes.c_void_p(flat.bf16.data_ptr() + 2 * lo), n, lr, beta1, beta2, eps, wd, k, stream), "tribe_adam_step")
         # the shadow weights are already current for the state the post-step hook is about to announce
-        flat._sig = (sum(p._version for p in flat.params.values()), _engine._OPT_STEPS[0] + 1)
+        flat._sig = (sum(p._version for p in flat.params.values()), flat.opt_steps + 1)
         return loss

@@ -45,3 +45,39 @@ def synthetic_batch(batch_size=16, t=298, t_out=100, n_outputs=1000, n_subjects=
     data["subject_id"] = torch.randint(0, n_subjects, (batch_size, 1), generator=g)
     batch = SegmentData(data=data, segments=[None] * batch_size)
     return batch.pin_memory() if pin else batch
+
+
+class DevicePrefetcher:
+    """Iterate over pinned host batches, issuing the host->device copy of batch i+1 on a side stream while the caller
+    computes on batch i (the copy of a full TRIBE batch is 216 MB ~= 4 ms of PCIe time per step otherwise serialised
+    in front of the forward).  Yields device-resident ``SegmentData``."""
+
+    def __init__(self, batches, device=None):
+        self.batches = batches
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream(self.device)
+
+    def _load(self, batch):
+        with torch.cuda.stream(self.stream):
+            data = {k: v.to(self.device, non_blocking=True) for k, v in batch.data.items()}
+            event = torch.cuda.Event()
+            event.record(self.stream)
+        return SegmentData(data=data, segments=batch.segments), event
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            nxt = self._load(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, event = nxt
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(event)
+            for v in cur.data.values():
+                v.record_stream(main)
+            try:
+                nxt = self._load(next(it))
+            except StopIteration:
+                nxt = None
+            yield cur

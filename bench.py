@@ -146,7 +146,7 @@ def run_ours(args):
     from algonauts2025_b200 import ops, parallel
     from algonauts2025_b200.model import FmriEncoderConfig
     from algonauts2025_b200.pl_module import BrainModule
-    from algonauts2025_b200.segment import SegmentData, synthetic_batch
+    from algonauts2025_b200.segment import DevicePrefetcher, SegmentData, synthetic_batch
     from algonauts2025_b200.trainer import MiniTrainer, default_optimizer
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -211,8 +211,9 @@ def run_ours(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     last = 0.0
-    for i in range(K):
-        last = trainer.train_step(host[i % 2]).item()  # D2H read of the step's loss
+    # public-API loop a user writes: pinned host batches -> DevicePrefetcher (H2D of batch i+1 overlaps step i) -> train_step
+    for batch in DevicePrefetcher(host[i % 2] for i in range(K)):
+        last = trainer.train_step(batch).item()  # D2H read of the step's loss
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)

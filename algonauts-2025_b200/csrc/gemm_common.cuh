@@ -1,0 +1,258 @@
+// Shared device-side pieces of the tcgen05 GEMM kernels (1-CTA: gemm_sm100.cu, 2-CTA pairs: gemm2_sm100.cuh):
+// kernel parameter block, tile decoding, persistent work scheduling (whole tiles + split-K tail) and the fused epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx_sm100.cuh"
+#include "tribe_b200.h"
+
+namespace tribe {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kMaxTailTiles = 160;  // split-K counters (4 ints per tail tile) reserved at the head of the workspace
+
+struct alignas(64) GemmKParams {
+  CUtensorMap tma, tmb;
+  int m, n, k, batch, z_inner;
+  int a_inner_off, a_zin_stride, a_zdiv;
+  int b_inner_off, b_zin_stride, b_zdiv;
+  const long long* a_gather;
+  const long long* b_gather;
+  const long long* kgroup;
+  int kgroup_len;
+  void* d;
+  int d_f32, d_transposed, vec_ok;
+  long long ldd, d_zo, d_zi;
+  int epilogue;
+  float alpha;
+  const float* bias;
+  int bias_gathered;
+  long long bias_z_stride;
+  const float* res;
+  long long ld_res;
+  int res_row_mod, res_batched;
+  const float* rscale;
+  const __nv_bfloat16* aux_in;
+  __nv_bfloat16* aux_out;
+  long long ld_aux;
+  const float2* rope;
+  int rope_t, rope_dim, head_dim, rope_cols;
+  float rope_sign;
+  uint32_t k_lbo, k_sbo, mn_lbo, mn_sbo;
+  int m_blocks, n_blocks, num_tiles, num_kb, raster_n_fast;
+  // split-K tail
+  int full_tiles, tail_units, split, kb_per;
+  float* ws;
+  int* counters;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+struct TileCoord {
+  int z, zi, zo, m0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int bn, int bm = BM) {
+  TileCoord t;
+  int mb, nb, rest;
+  if (p.raster_n_fast) {  // consecutive tiles (one wave) share an A row-block and sweep B: B is the re-read operand
+    nb = tile % p.n_blocks;
+    rest = tile / p.n_blocks;
+    mb = rest % p.m_blocks;
+    t.z = rest / p.m_blocks;
+  } else {                // consecutive tiles share a B column-block and sweep A: A is the re-read operand
+    mb = tile % p.m_blocks;
+    rest = tile / p.m_blocks;
+    nb = rest % p.n_blocks;
+    t.z = rest / p.n_blocks;
+  }
+  t.zi = t.z % p.z_inner;
+  t.zo = t.z / p.z_inner;
+  t.m0 = mb * bm;
+  t.n0 = nb * bn;
+  return t;
+}
+
+__device__ __forceinline__ int batch_coord(const long long* gather, int z, int zdiv) {
+  int zz = z / zdiv;
+  return gather ? static_cast<int>(gather[zz]) : zz;
+}
+
+// One unit of work of a persistent CTA: a whole tile, or one K-slice of a tile of the ragged last wave.
+struct Work {
+  int tile, kb0, kb1, slice;
+  bool partial;
+};
+
+// worker = persistent CTA (1-CTA kernel) or CTA pair (2-CTA kernel); nworkers = how many of them the grid holds.
+__device__ __forceinline__ bool next_work(const GemmKParams& p, int it, Work& w, int worker, int nworkers) {
+  const int idx = worker + it * nworkers;
+  if (idx < p.full_tiles) {
+    w.tile = idx, w.kb0 = 0, w.kb1 = p.num_kb, w.slice = 0, w.partial = false;
+    return true;
+  }
+  const int u = idx - p.full_tiles;
+  if (u >= p.tail_units) return false;
+  w.tile = p.full_tiles + u / p.split;
+  w.slice = u % p.split;
+  w.kb0 = w.slice * p.kb_per;
+  w.kb1 = min(p.num_kb, w.kb0 + p.kb_per);
+  w.partial = true;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Fused epilogue of 32 consecutive columns of one output row (v already scaled by alpha).
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
+                                               const float* bias, int res_row, int pos) {
+  const int nvalid = min(32, p.n - col0);
+  const bool full = (nvalid == 32) && p.vec_ok;
+
+  if (bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+        v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += __ldg(bias + col0 + j);
+    }
+  }
+
+  if (p.epilogue == TRIBE_EPI_GELU) {
+    if (row_ok) {
+      __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(ap + j) = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) ap[j] = __float2bfloat16(v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.epilogue == TRIBE_EPI_GELU_BWD) {
+    if (row_ok) {
+      const __nv_bfloat16* ap = p.aux_in + static_cast<long long>(row) * p.ld_aux + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 pk = __ldg(reinterpret_cast<const uint4*>(ap + j));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[j + 2 * e] *= gelu_erf_grad(f.x);
+            v[j + 2 * e + 1] *= gelu_erf_grad(f.y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] *= gelu_erf_grad(__bfloat162float(ap[j]));
+      }
+    }
+  } else if (p.epilogue == TRIBE_EPI_RESIDUAL) {
+    if (row_ok) {
+      const float* rp = p.res + (p.res_batched ? zoff : 0) + static_cast<long long>(res_row) * p.ld_res + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.rscale) s4 = __ldg(reinterpret_cast<const float4*>(p.rscale + col0 + j));
+          v[j] += r4.x * s4.x, v[j + 1] += r4.y * s4.y, v[j + 2] += r4.z * s4.z, v[j + 3] += r4.w * s4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __ldg(rp + j) * (p.rscale ? __ldg(p.rscale + col0 + j) : 1.0f);
+      }
+    }
+  } else if (p.epilogue == TRIBE_EPI_ROPE) {
+    const int cih = col0 % p.head_dim;  // chunk-uniform: head_dim, rope_dim are multiples of 32
+    if (col0 < p.rope_cols && cih < p.rope_dim) {
+      const float2* tab = p.rope + static_cast<long long>(pos) * (p.rope_dim >> 1) + (cih >> 1);
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(tab + j));  // (cos, sin) of two pairs
+        const float s0 = cs.y * p.rope_sign, s1 = cs.w * p.rope_sign;
+        const float x0 = v[2 * j], x1 = v[2 * j + 1], y0 = v[2 * j + 2], y1 = v[2 * j + 3];
+        v[2 * j] = x0 * cs.x - x1 * s0;
+        v[2 * j + 1] = x1 * cs.x + x0 * s0;
+        v[2 * j + 2] = y0 * cs.z - y1 * s1;
+        v[2 * j + 3] = y1 * cs.z + y0 * s1;
+      }
+    }
+  }
+
+  if (!row_ok) return;
+  if (p.d_transposed) {
+    if (p.d_f32) {
+      float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = v[j];
+    } else {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = __float2bfloat16(v[j]);
+    }
+  } else if (p.d_f32) {
+    float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(dp + j) = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+}  // namespace tribe

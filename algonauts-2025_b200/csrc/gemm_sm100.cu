@@ -31,250 +31,10 @@
 #include "tribe_b200.h"
 #include "tribe_internal.h"
 
+#include "gemm_common.cuh"
+#include "gemm2_sm100.cuh"
+
 namespace tribe {
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
-constexpr int kTmemCols = 512;
-constexpr int kMaxTailTiles = 160;  // split-K counters reserved at the head of the workspace
-
-struct alignas(64) GemmKParams {
-  CUtensorMap tma, tmb;
-  int m, n, k, batch, z_inner;
-  int a_inner_off, a_zin_stride, a_zdiv;
-  int b_inner_off, b_zin_stride, b_zdiv;
-  const long long* a_gather;
-  const long long* b_gather;
-  const long long* kgroup;
-  int kgroup_len;
-  void* d;
-  int d_f32, d_transposed, vec_ok;
-  long long ldd, d_zo, d_zi;
-  int epilogue;
-  float alpha;
-  const float* bias;
-  int bias_gathered;
-  long long bias_z_stride;
-  const float* res;
-  long long ld_res;
-  int res_row_mod, res_batched;
-  const float* rscale;
-  const __nv_bfloat16* aux_in;
-  __nv_bfloat16* aux_out;
-  long long ld_aux;
-  const float2* rope;
-  int rope_t, rope_dim, head_dim, rope_cols;
-  float rope_sign;
-  uint32_t k_lbo, k_sbo, mn_lbo, mn_sbo;
-  int m_blocks, n_blocks, num_tiles, num_kb, raster_n_fast;
-  // split-K tail
-  int full_tiles, tail_units, split, kb_per;
-  float* ws;
-  int* counters;
-};
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KiB alignment
-};
-
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
-
-struct TileCoord {
-  int z, zi, zo, m0, n0;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int bn) {
-  TileCoord t;
-  int mb, nb, rest;
-  if (p.raster_n_fast) {  // consecutive tiles (one wave) share an A row-block and sweep B: B is the re-read operand
-    nb = tile % p.n_blocks;
-    rest = tile / p.n_blocks;
-    mb = rest % p.m_blocks;
-    t.z = rest / p.m_blocks;
-  } else {                // consecutive tiles share a B column-block and sweep A: A is the re-read operand
-    mb = tile % p.m_blocks;
-    rest = tile / p.m_blocks;
-    nb = rest % p.n_blocks;
-    t.z = rest / p.n_blocks;
-  }
-  t.zi = t.z % p.z_inner;
-  t.zo = t.z / p.z_inner;
-  t.m0 = mb * BM;
-  t.n0 = nb * bn;
-  return t;
-}
-
-__device__ __forceinline__ int batch_coord(const long long* gather, int z, int zdiv) {
-  int zz = z / zdiv;
-  return gather ? static_cast<int>(gather[zz]) : zz;
-}
-
-// One unit of work of a persistent CTA: a whole tile, or one K-slice of a tile of the ragged last wave.
-struct Work {
-  int tile, kb0, kb1;
-  bool partial;
-};
-
-__device__ __forceinline__ bool next_work(const GemmKParams& p, int it, Work& w) {
-  const int idx = blockIdx.x + it * gridDim.x;
-  if (idx < p.full_tiles) {
-    w.tile = idx, w.kb0 = 0, w.kb1 = p.num_kb, w.partial = false;
-    return true;
-  }
-  const int u = idx - p.full_tiles;
-  if (u >= p.tail_units) return false;
-  w.tile = p.full_tiles + u / p.split;
-  const int slice = u % p.split;
-  w.kb0 = slice * p.kb_per;
-  w.kb1 = min(p.num_kb, w.kb0 + p.kb_per);
-  w.partial = true;
-  return true;
-}
-
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// Fused epilogue of 32 consecutive columns of one output row (v already scaled by alpha).
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
-                                               const float* bias, int res_row, int pos) {
-  const int nvalid = min(32, p.n - col0);
-  const bool full = (nvalid == 32) && p.vec_ok;
-
-  if (bias) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-        v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) v[j] += __ldg(bias + col0 + j);
-    }
-  }
-
-  if (p.epilogue == TRIBE_EPI_GELU) {
-    if (row_ok) {
-      __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          *reinterpret_cast<uint4*>(ap + j) = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) ap[j] = __float2bfloat16(v[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.epilogue == TRIBE_EPI_GELU_BWD) {
-    if (row_ok) {
-      const __nv_bfloat16* ap = p.aux_in + static_cast<long long>(row) * p.ld_aux + col0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 pk = __ldg(reinterpret_cast<const uint4*>(ap + j));
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(h[e]);
-            v[j + 2 * e] *= gelu_erf_grad(f.x);
-            v[j + 2 * e + 1] *= gelu_erf_grad(f.y);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) v[j] *= gelu_erf_grad(__bfloat162float(ap[j]));
-      }
-    }
-  } else if (p.epilogue == TRIBE_EPI_RESIDUAL) {
-    if (row_ok) {
-      const float* rp = p.res + (p.res_batched ? zoff : 0) + static_cast<long long>(res_row) * p.ld_res + col0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
-          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.rscale) s4 = __ldg(reinterpret_cast<const float4*>(p.rscale + col0 + j));
-          v[j] += r4.x * s4.x, v[j + 1] += r4.y * s4.y, v[j + 2] += r4.z * s4.z, v[j + 3] += r4.w * s4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) v[j] += __ldg(rp + j) * (p.rscale ? __ldg(p.rscale + col0 + j) : 1.0f);
-      }
-    }
-  } else if (p.epilogue == TRIBE_EPI_ROPE) {
-    const int cih = col0 % p.head_dim;  // chunk-uniform: head_dim, rope_dim are multiples of 32
-    if (col0 < p.rope_cols && cih < p.rope_dim) {
-      const float2* tab = p.rope + static_cast<long long>(pos) * (p.rope_dim >> 1) + (cih >> 1);
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float4 cs = __ldg(reinterpret_cast<const float4*>(tab + j));  // (cos, sin) of two pairs
-        const float s0 = cs.y * p.rope_sign, s1 = cs.w * p.rope_sign;
-        const float x0 = v[2 * j], x1 = v[2 * j + 1], y0 = v[2 * j + 2], y1 = v[2 * j + 3];
-        v[2 * j] = x0 * cs.x - x1 * s0;
-        v[2 * j + 1] = x1 * cs.x + x0 * s0;
-        v[2 * j + 2] = y0 * cs.z - y1 * s1;
-        v[2 * j + 3] = y1 * cs.z + y0 * s1;
-      }
-    }
-  }
-
-  if (!row_ok) return;
-  if (p.d_transposed) {
-    if (p.d_f32) {
-      float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = v[j];
-    } else {
-      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dp[static_cast<long long>(j) * p.ldd] = __float2bfloat16(v[j]);
-    }
-  } else if (p.d_f32) {
-    float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dp[j] = v[j];
-    }
-  } else {
-    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.d) + zoff + static_cast<long long>(row) * p.ldd + col0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(dp + j) = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
-    }
-  }
-}
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
@@ -325,7 +85,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       Work w;
-      for (int it = 0; next_work(p, it, w); ++it) {
+      for (int it = 0; next_work(p, it, w, blockIdx.x, gridDim.x); ++it) {
         const TileCoord t = decode_tile(p, w.tile, BN);
         const int a_in = p.a_inner_off + t.zi * p.a_zin_stride;
         const int b_in = p.b_inner_off + t.zi * p.b_zin_stride;
@@ -379,7 +139,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       int acc = 0;
       uint32_t acc_phase = 0;
       Work w;
-      for (int it = 0; next_work(p, it, w); ++it) {
+      for (int it = 0; next_work(p, it, w, blockIdx.x, gridDim.x); ++it) {
         const TileCoord t = decode_tile(p, w.tile, BN);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -419,7 +179,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     int acc = 0;
     uint32_t acc_phase = 0;
     Work w;
-    for (int it = 0; next_work(p, it, w); ++it) {
+    for (int it = 0; next_work(p, it, w, blockIdx.x, gridDim.x); ++it) {
       const TileCoord t = decode_tile(p, w.tile, BN);
       bool has_k = true;
       if (p.kgroup) {
@@ -458,7 +218,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         // Phase 2: once all `split` slices of the tile have landed (arrival counter; every tail unit is resident
         // concurrently: one per CTA, grid <= #SMs), slice s reduces and finishes the 32-column chunks c = s mod split.
         const int ti = w.tile - p.full_tiles;
-        const int slice = (blockIdx.x + it * gridDim.x - p.full_tiles) % p.split;
+        const int slice = w.slice;
         float* tile_ws = p.ws + static_cast<size_t>(ti) * p.split * (BM * BN);
         float* wrow = tile_ws + static_cast<size_t>(slice) * (BM * BN) + static_cast<size_t>(row_in_tile) * BN;
 #pragma unroll 1
@@ -476,7 +236,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
         mbar_arrive(&tempty_bar[acc]);
         __threadfence();
         epi_bar_sync();
-        int* arrive = p.counters + 2 * ti;
+        int* arrive = p.counters + 4 * ti;
         int* depart = arrive + 1;
         if (warp == 2 && lane == 0) {
           atomicAdd(arrive, 1);
@@ -632,6 +392,31 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
   return TRIBE_OK;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm2)");
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);  // __cluster_dims__(2,1,1): grid is a multiple of 2
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "gemm2 launch");
+  return TRIBE_OK;
+}
+
+template <int BN>
+static int dispatch_major2(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm2<BN, false, false>(kp, grid, s);
+  if (a_mn && !b_mn) return launch_gemm2<BN, true, false>(kp, grid, s);
+  if (!a_mn && b_mn) return launch_gemm2<BN, false, true>(kp, grid, s);
+  return launch_gemm2<BN, true, true>(kp, grid, s);
+}
+
 template <int BN>
 static int dispatch_major(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
   if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(kp, grid, s);
@@ -672,9 +457,15 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
   const bool a_mn = g->a.mn_major != 0, b_mn = g->b.mn_major != 0;
+  // CTA pairs (cta_group::2, 256 x BN tiles) for the big GEMMs; single CTAs for short-M / grouped problems.
+  static const int allow_2cta = [] {
+    const char* e = getenv("TRIBE_GEMM_2CTA");
+    return e ? atoi(e) : 1;
+  }();
+  const bool use2 = allow_2cta && bn == 256 && !g->kgroup && g->m >= 1024 && (num_sms() % 2 == 0);
   int rc = encode_operand(g->a, a_mn ? BK : BM, &kp.tma);
   if (rc) return rc;
-  rc = encode_operand(g->b, b_mn ? BK : bn, &kp.tmb);
+  rc = encode_operand(g->b, b_mn ? BK : (use2 ? bn / 2 : bn), &kp.tmb);
   if (rc) return rc;
   kp.m = g->m, kp.n = g->n, kp.k = g->k, kp.batch = g->batch, kp.z_inner = g->z_inner > 0 ? g->z_inner : 1;
   kp.a_inner_off = g->a.inner_off, kp.a_zin_stride = g->a.zin_stride, kp.a_zdiv = g->a.zdiv > 0 ? g->a.zdiv : 1;
@@ -694,7 +485,8 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.rope_cols = g->rope_cols, kp.rope_sign = g->rope_sign;
   kp.k_lbo = k_lbo ? k_lbo : 16, kp.k_sbo = k_sbo ? k_sbo : 1024;
   kp.mn_lbo = mn_lbo ? mn_lbo : BK * 128, kp.mn_sbo = mn_sbo ? mn_sbo : 1024;
-  kp.m_blocks = (g->m + BM - 1) / BM, kp.n_blocks = (g->n + bn - 1) / bn;
+  const int bm = use2 ? BM2 : BM;
+  kp.m_blocks = (g->m + bm - 1) / bm, kp.n_blocks = (g->n + bn - 1) / bn;
   kp.num_tiles = kp.m_blocks * kp.n_blocks * g->batch, kp.num_kb = (g->k + BK - 1) / BK;
   // Tile order: every wave of ~#SM tiles streams one operand completely and re-reads the other; re-read the smaller
   // one so that it stays L2-resident (126 MB) — e.g. FF2 (A = 117 MB activations, B = 75 MB weights) goes N-fastest.
@@ -712,7 +504,8 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.vec_ok = vec ? 1 : 0;
 
   // ---- schedule: whole tiles round-robin; the ragged last wave is split along K when a workspace is provided
-  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  const int workers_max = use2 ? num_sms() / 2 : num_sms();  // persistent CTAs, or CTA pairs
+  const int grid = kp.num_tiles < workers_max ? kp.num_tiles : workers_max;
   kp.full_tiles = kp.num_tiles, kp.tail_units = 0, kp.split = 1, kp.kb_per = kp.num_kb;
   // (measured on B200: the tail split pays off for deep contractions — +15..18 % at K >= 9216 — and is neutral to
   //  slightly negative at K = 3072, where a tile is only ~27 us long; hence the K >= 6144 gate.)
@@ -728,8 +521,8 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
       int split = grid / rem;
       if (split > kp.num_kb / min_kb) split = kp.num_kb / min_kb;  // keep >= min_kb K-blocks per slice
       if (split > bn / 32) split = bn / 32;                        // phase 2 hands out 32-column chunks
-      const size_t head = static_cast<size_t>(kMaxTailTiles) * 2 * sizeof(int);
-      const size_t per_slot = static_cast<size_t>(BM) * bn * sizeof(float);
+      const size_t head = static_cast<size_t>(kMaxTailTiles) * 4 * sizeof(int);
+      const size_t per_slot = static_cast<size_t>(bm) * bn * sizeof(float);
       while (split >= 2 && head + static_cast<size_t>(rem) * split * per_slot > static_cast<size_t>(g->splitk_ws_bytes)) --split;
       if (split >= 2) {
         kp.kb_per = (kp.num_kb + split - 1) / split;
@@ -743,6 +536,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   }
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use2) return dispatch_major2<256>(kp, 2 * grid, a_mn, b_mn, s);
   switch (bn) {
     case 128: return dispatch_major<128>(kp, grid, a_mn, b_mn, s);
     case 160: return dispatch_major<160>(kp, grid, a_mn, b_mn, s);

@@ -98,7 +98,7 @@ typedef struct TribeGemm {
   int32_t rope_dim, head_dim, rope_cols;
   float rope_sign;
   int32_t block_n;        /* 0: auto; else one of 128, 160, 192, 256 */
-  /* optional split-K workspace (caller-owned, its first 1280 bytes ZERO-initialised once; 20 MiB is plenty): lets the
+  /* optional split-K workspace (caller-owned, its first 2560 bytes ZERO-initialised once; 20 MiB is plenty): lets the
    * ragged last wave of tiles be split along K over otherwise idle SMs (per-slice fp32 partial slots + arrival
    * counters, which the kernel resets).  Must not be shared by GEMMs running concurrently on different streams. */
   void* splitk_ws;

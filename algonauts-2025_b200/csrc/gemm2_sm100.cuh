@@ -8,13 +8,16 @@
 //   full[s]   lives in the LEADER; both CTAs' TMA loads complete_tx on it, the leader arms expect_tx for 2 stages' bytes
 //   empty[s]  one per CTA; the leader's tcgen05.commit multicasts the arrive to both
 //   tfull[a]  one per CTA (multicast commit) -> each CTA's epilogue drains its own TMEM half
-//   tempty[a] lives in the leader, count 256: the epilogue threads of BOTH CTAs arrive on it (remote arrive)
+//   tempty[a] lives in the leader, count 512: the epilogue threads of BOTH CTAs arrive on it (remote arrive)
 #pragma once
 #include "gemm_common.cuh"
 
 namespace tribe {
 
 constexpr int BM2 = 256;  // rows per CTA pair
+constexpr int kGemm2Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+constexpr int kEpi2Threads = 256;
+__device__ __forceinline__ void epi2_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -71,7 +74,7 @@ struct Gemm2Cfg {
 };
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gemm2_bf16_kernel(const __grid_constant__ GemmKParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) gemm2_bf16_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = Gemm2Cfg<BN>;
   static_assert(BN == 128 || BN == 256, "2-CTA tiles: BN/2 must be a multiple of 64");
   extern __shared__ uint8_t smem_raw[];
@@ -100,7 +103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 256);
+        mbar_init(&tempty_bar[s], 2 * kEpi2Threads);
       }
       fence_mbar_init();
     }
@@ -198,7 +201,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 TMEM lanes)
-    const int q = warp & 3;
+    const int q = warp & 3;               // TMEM lane quarter
+    const int chalf = (warp - 2) >> 2;    // which half of the 32-column chunks this warp takes
     const int row_in_half = q * 32 + lane;
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t leader_tempty1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
@@ -221,7 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
 
       if (!w.partial) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = chalf; c < BN / 32; c += 2) {
           const int col0 = t.n0 + c * 32;
           if (col0 >= p.n) break;
           uint32_t raw[32];
@@ -240,7 +244,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
         float* tile_ws = p.ws + (static_cast<size_t>(ti) * 2 + rank) * p.split * (128 * BN);
         float* wrow = tile_ws + static_cast<size_t>(w.slice) * (128 * BN) + static_cast<size_t>(row_in_half) * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = chalf; c < BN / 32; c += 2) {
           if (t.n0 + c * 32 >= p.n) break;
           uint32_t raw[32];
           tmem_ld_32x32(t_addr + c * 32, raw);
@@ -253,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
         tc_fence_before();
         mbar_arrive_remote(leader_tempty);
         __threadfence();
-        epi_bar_sync();
+        epi2_bar_sync();
         int* arrive = p.counters + 4 * ti + 2 * static_cast<int>(rank);
         int* depart = arrive + 1;
         if (warp == 2 && lane == 0) {
@@ -261,10 +265,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
           while (atomicAdd(arrive, 0) < p.split) __nanosleep(64);
           __threadfence();
         }
-        epi_bar_sync();
+        epi2_bar_sync();
         const float* rrow = tile_ws + static_cast<size_t>(row_in_half) * BN;
 #pragma unroll 1
-        for (int c = w.slice; c < BN / 32; c += p.split) {
+        for (int c = w.slice + chalf * p.split; c < BN / 32; c += 2 * p.split) {
           const int col0 = t.n0 + c * 32;
           if (col0 >= p.n) break;
           float v[32];
@@ -282,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gem
           for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
           epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
         }
-        epi_bar_sync();
+        epi2_bar_sync();
         if (warp == 2 && lane == 0) {
           if (atomicAdd(depart, 1) == p.split - 1) {
             *arrive = 0;

@@ -402,7 +402,7 @@ static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm2)");
     attr_set = true;
   }
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);  // __cluster_dims__(2,1,1): grid is a multiple of 2
+  kern<<<grid, kGemm2Threads, Cfg::SMEM_BYTES, stream>>>(kp);  // __cluster_dims__(2,1,1): grid is a multiple of 2
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "gemm2 launch");
@@ -509,7 +509,12 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.full_tiles = kp.num_tiles, kp.tail_units = 0, kp.split = 1, kp.kb_per = kp.num_kb;
   // (measured on B200: the tail split pays off for deep contractions — +15..18 % at K >= 9216 — and is neutral to
   //  slightly negative at K = 3072, where a tile is only ~27 us long; hence the K >= 6144 gate.)
-  if (g->splitk_ws && !g->kgroup && kp.num_tiles > grid && kp.num_kb >= 96 && al16(g->splitk_ws)) {
+  static const int split_gate_kb = [] {
+    const char* e = getenv("TRIBE_SPLITK_GATE_KB");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 96;
+  }();
+  if (g->splitk_ws && !g->kgroup && kp.num_tiles > grid && kp.num_kb >= (use2 ? split_gate_kb / 2 : split_gate_kb) && al16(g->splitk_ws)) {
     const int full = (kp.num_tiles / grid) * grid;
     const int rem = kp.num_tiles - full;
     if (rem > 0 && rem <= kMaxTailTiles) {

@@ -265,17 +265,40 @@ class FmriEncoder(nn.Module):
             dropped = list(np.random.choice(dropped, len(dropped) - 1, replace=False))
         return dropped
 
+    # common.py:53-55 asserts ``subjects.max() < N`` on the host (a device sync in the reference as well).  With
+    # ``defer_subject_check = True`` (set by trainer.MiniTrainer) the range check still runs on the device every call
+    # but its flag is read back asynchronously and raised at the next call / ``flush_subject_check()``, so the training
+    # loop has no host-device synchronisation point.
+    defer_subject_check = False
+
+    def flush_subject_check(self) -> None:
+        pending = self.__dict__.get("_pending_subject_check")
+        if pending is not None:
+            event, host_flag = pending
+            event.synchronize()
+            self.__dict__["_pending_subject_check"] = None
+            assert int(host_flag.item()) == 0, "Subject index higher than number of subjects used to initialize the weights."
+
     def _subjects(self, batch):
         subject_id = batch.data.get("subject_id", None)
         if subject_id is None:
             return None
         self._engine._check_flat()
-        subj = subject_id.to(self._engine.device, torch.int64).flatten().contiguous()
+        subj = subject_id.to(self._engine.device, torch.int64, non_blocking=True).flatten().contiguous()
         n = self.predictor.weights.shape[0]
-        # common.py:53-55 asserts on the host (a device sync in the reference as well)
         flag = torch.zeros(1, device=subj.device, dtype=torch.int32)
         ops.check_subjects(subj, n, flag)
-        assert int(flag.item()) == 0, "Subject index higher than number of subjects used to initialize the weights."
+        if self.defer_subject_check:
+            self.flush_subject_check()
+            ring = self.__dict__.setdefault("_flag_ring", [torch.empty(1, dtype=torch.int32).pin_memory() for _ in range(2)])
+            ring.append(ring.pop(0))  # the previous call's buffer was consumed by flush_subject_check() above
+            host_flag = ring[0]
+            host_flag.copy_(flag, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            self.__dict__["_pending_subject_check"] = (event, host_flag)
+        else:
+            assert int(flag.item()) == 0, "Subject index higher than number of subjects used to initialize the weights."
         return subj
 
     def _anchor(self):

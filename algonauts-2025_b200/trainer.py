@@ -29,6 +29,9 @@ class MiniTrainer:
     def __init__(self, module, optimizer, scheduler=None, grad_sync=None):
         self.module, self.optimizer, self.scheduler, self.grad_sync = module, optimizer, scheduler, grad_sync
         self.global_step = 0
+        model = getattr(module, "model", None)
+        if model is not None and hasattr(model, "defer_subject_check"):
+            model.defer_subject_check = True  # no host sync inside the step; raised one call later (see model.py)
 
     def train_step(self, batch) -> torch.Tensor:
         self.module.train()
@@ -53,6 +56,8 @@ class MiniTrainer:
                 metric.reset()
         for i, batch in enumerate(batches):
             self.module.validation_step(batch, i)
+        if hasattr(getattr(self.module, "model", None), "flush_subject_check"):
+            self.module.model.flush_subject_check()
         self.module.on_validation_epoch_end()
         out = dict(getattr(self.module, "logged", {}))
         for name, metric in self.module.metrics.items():

@@ -148,6 +148,17 @@ def test_subject_range_assert_and_no_cpu_fallback():
         model(bad)
     with pytest.raises(algonauts2025_b200.TribeError):
         model.pooler(torch.zeros(2, 3, 10))
+    # deferred mode (training loops: no host sync inside the step): same check, raised at the next call / flush
+    model.defer_subject_check = True
+    with torch.no_grad():
+        model(bad)
+        with pytest.raises(AssertionError):
+            model.flush_subject_check()
+        model(bad)
+        with pytest.raises(AssertionError):
+            model(batch)
+        model(batch)
+        model.flush_subject_check()
 
 
 def test_transformer_forward_and_state_dict_roundtrip():

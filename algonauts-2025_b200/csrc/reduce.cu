@@ -206,6 +206,102 @@ __global__ void __launch_bounds__(256) pearson_strided_kernel(const float* __res
   }
 }
 
+// Fast (B, D, T) path: t contiguous and parcels adjacent (stride_t == 1, stride_p == t_len), i.e. the prediction tensor
+// exactly as FmriEncoder.forward returns it, or a parcel slice [:, lo:hi] of it (stride_b stays the full D*T).  A block
+// owns PB consecutive parcels (PB * t_len / VEC <= 256 items) and a chunk of windows b; thread i keeps the SAME
+// (parcel, t) position for every b, so all loads of a block at one b are one contiguous 16 B-per-lane run and the only
+// cross-thread reduction is one shared-memory fold per block.  kBdtUnroll windows of independent loads are in flight.
+constexpr int kBdtUnroll = 4;
+
+template <int VEC>
+__global__ void __launch_bounds__(256) pearson_bdt_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_b,
+                                                          int64_t n_parcels, int t_len, int64_t stride_b, int pb, int64_t b_per_block,
+                                                          const long long* __restrict__ group, double* __restrict__ stats) {
+  __shared__ double sh[64 * 5];  // pb <= 64 parcels x 5 sums
+  const int tv = t_len / VEC;
+  const int item = threadIdx.x;
+  const int pl = item / tv;  // parcel within the block
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * pb + pl;
+  const bool active = pl < pb && p < n_parcels;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.y) * b_per_block;
+  const int64_t b1 = min(n_b, b0 + b_per_block);
+  if (b0 >= b1) return;
+  const int64_t off = static_cast<int64_t>(blockIdx.x) * pb * t_len + static_cast<int64_t>(item) * VEC;
+  double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+  long long cur = group ? group[b0] : 0;
+  int64_t cnt = 0;
+
+  auto flush = [&](long long gsel, int64_t count) {  // block-uniform call sites only
+    for (int i = threadIdx.x; i < pb * 5; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    if (active) {
+      atomicAdd(&sh[pl * 5 + 0], sx), atomicAdd(&sh[pl * 5 + 1], sy), atomicAdd(&sh[pl * 5 + 2], sxx);
+      atomicAdd(&sh[pl * 5 + 3], syy), atomicAdd(&sh[pl * 5 + 4], sxy);
+    }
+    __syncthreads();
+    double* st = stats + gsel * 6 * n_parcels;
+    for (int i = threadIdx.x; i < pb * 6; i += blockDim.x) {
+      const int q = i / 6, k = i - q * 6;
+      const int64_t pp = static_cast<int64_t>(blockIdx.x) * pb + q;
+      if (pp < n_parcels) atomicAdd(st + k * n_parcels + pp, k == 0 ? static_cast<double>(count * t_len) : sh[q * 5 + k - 1]);
+    }
+    __syncthreads();
+    sx = sy = sxx = syy = sxy = 0.0;
+  };
+
+  int64_t b = b0;
+  while (b < b1) {
+    int nk = static_cast<int>(min(static_cast<int64_t>(kBdtUnroll), b1 - b));
+    if (group) {
+      const long long gid = group[b];
+      if (gid != cur) {
+        flush(cur, cnt);
+        cur = gid, cnt = 0;
+      }
+      int run = 1;
+      while (run < nk && group[b + run] == gid) ++run;
+      nk = run;
+    }
+    if (active) {
+      float fx = 0, fy = 0, fxx = 0, fyy = 0, fxy = 0;
+      if (VEC == 4) {
+        float4 xs[kBdtUnroll], ys[kBdtUnroll];
+#pragma unroll
+        for (int k = 0; k < kBdtUnroll; ++k) {
+          if (k < nk) {
+            xs[k] = __ldcs(reinterpret_cast<const float4*>(pred + (b + k) * stride_b + off));
+            ys[k] = __ldcs(reinterpret_cast<const float4*>(target + (b + k) * stride_b + off));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kBdtUnroll; ++k) {
+          if (k < nk) {
+            const float x[4] = {xs[k].x, xs[k].y, xs[k].z, xs[k].w}, y[4] = {ys[k].x, ys[k].y, ys[k].z, ys[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              fx += x[j], fy += y[j];
+              fxx = fmaf(x[j], x[j], fxx), fyy = fmaf(y[j], y[j], fyy), fxy = fmaf(x[j], y[j], fxy);
+            }
+          }
+        }
+      } else {
+        float xs[kBdtUnroll], ys[kBdtUnroll];
+#pragma unroll
+        for (int k = 0; k < kBdtUnroll; ++k) {
+          if (k < nk) xs[k] = __ldcs(pred + (b + k) * stride_b + off), ys[k] = __ldcs(target + (b + k) * stride_b + off);
+        }
+#pragma unroll
+        for (int k = 0; k < kBdtUnroll; ++k) {
+          if (k < nk) fx += xs[k], fy += ys[k], fxx = fmaf(xs[k], xs[k], fxx), fyy = fmaf(ys[k], ys[k], fyy), fxy = fmaf(xs[k], ys[k], fxy);
+        }
+      }
+      sx += fx, sy += fy, sxx += fxx, syy += fyy, sxy += fxy;
+    }
+    b += nk, cnt += nk;
+  }
+  flush(cur, cnt);
+}
+
 __global__ void __launch_bounds__(256) pearson_finalize_kernel(const double* __restrict__ stats, int64_t n_parcels, float* __restrict__ r_out,
                                                                float* __restrict__ mean_out) {
   __shared__ double red[8];
@@ -264,6 +360,27 @@ extern "C" int tribe_pearson_stats(const float* pred, const float* target, int64
     dim3 grid(static_cast<unsigned>(pblocks), static_cast<unsigned>((n_rows + rpb - 1) / rpb));
     pearson_rowmajor_kernel<<<grid, 256, 0, s>>>(pred, target, n_rows, n_parcels, rpb, g, stats);
     TRIBE_CHECK_LAUNCH("pearson_rowmajor");
+  } else if (stride_t == 1 && stride_p == t_len && t_len <= 1024 &&
+             (((t_len & 3) == 0 && (stride_b & 3) == 0 && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target)) & 15) == 0) ||
+              t_len <= 256)) {
+    const int64_t n_b = n_rows / t_len;
+    const bool vec = (t_len & 3) == 0 && (stride_b & 3) == 0 && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+    const int tv = static_cast<int>(vec ? t_len / 4 : t_len);
+    int pb = 256 / tv;
+    if (pb > 64) pb = 64;
+    const int64_t pblocks = (n_parcels + pb - 1) / pb;
+    int64_t chunks = (148 * 8 + pblocks - 1) / pblocks;
+    const int64_t max_chunks = (n_b + kBdtUnroll - 1) / kBdtUnroll;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > 65535) chunks = 65535;
+    int64_t bpb = (n_b + chunks - 1) / chunks;
+    bpb = (bpb + kBdtUnroll - 1) / kBdtUnroll * kBdtUnroll;
+    dim3 grid(static_cast<unsigned>(pblocks), static_cast<unsigned>((n_b + bpb - 1) / bpb));
+    if (vec)
+      pearson_bdt_kernel<4><<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, static_cast<int>(t_len), stride_b, pb, bpb, g, stats);
+    else
+      pearson_bdt_kernel<1><<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, static_cast<int>(t_len), stride_b, pb, bpb, g, stats);
+    TRIBE_CHECK_LAUNCH("pearson_bdt");
   } else {
     const int64_t n_b = n_rows / t_len;
     if (n_b > 65535) return set_error(TRIBE_EINVAL, "pearson_stats: more than 65535 strided blocks per call");

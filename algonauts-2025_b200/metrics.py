@@ -144,9 +144,44 @@ def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice
         if y_true.ndim == 4:
             y_true = y_true.squeeze(-1)
         if parcel_slice is not None:
-            y_pred, y_true = y_pred[:, parcel_slice].contiguous(), y_true[:, parcel_slice].contiguous()
+            y_pred, y_true = y_pred[:, parcel_slice], y_true.contiguous()[:, parcel_slice]  # read in place by the kernel
         if stats is None:
             stats = torch.zeros(1, 6, y_pred.shape[1], device=y_pred.device, dtype=torch.float64)
-        ops.pearson_stats(y_pred.float().contiguous(), y_true.contiguous(), stats, layout="bdt")
+        ops.pearson_stats(y_pred.float(), y_true, stats, layout="bdt")
+    r, _ = ops.pearson_finalize(stats[0])
+    return r.cpu().numpy().astype(np.float32)
+
+
+@torch.no_grad()
+def pearson_from_host(preds: torch.Tensor, trues: torch.Tensor, chunk_windows: int = 128, device=None) -> np.ndarray:
+    """Per-parcel Pearson r of HOST-resident prediction / target arrays (what main.py:470-473 holds after its predict
+    loop): (N_windows, O, T) — or (N_rows, O) row-major — float32, ideally pinned.  Chunks are copied to two alternating
+    device slots on a copy stream while the statistics kernel consumes the previous chunk; only r (O floats) returns."""
+    if preds.shape != trues.shape or preds.dtype != torch.float32 or trues.dtype != torch.float32:
+        raise TribeError("pearson_from_host: preds/trues must be float32 tensors of the same shape")
+    if not torch.cuda.is_available():
+        raise TribeError("pearson_from_host needs a CUDA device (no CPU fallback)")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    layout = "bdt" if preds.dim() == 3 else "no"
+    n, o = preds.shape[0], preds.shape[1]
+    if layout == "no":
+        chunk_windows *= 100
+    stats = torch.zeros(1, 6, o, device=dev, dtype=torch.float64)
+    main, copy = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+    slots = [(torch.empty((min(chunk_windows, n),) + tuple(preds.shape[1:]), device=dev), torch.empty((min(chunk_windows, n),) + tuple(preds.shape[1:]), device=dev))
+             for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]   # slot consumed by the statistics kernel
+    ready = [torch.cuda.Event() for _ in range(2)]  # slot filled by the copy stream
+    for i, lo in enumerate(range(0, n, chunk_windows)):
+        hi, s = min(n, lo + chunk_windows), i % 2
+        with torch.cuda.stream(copy):
+            if i >= 2:
+                copy.wait_event(free[s])
+            slots[s][0][: hi - lo].copy_(preds[lo:hi], non_blocking=True)
+            slots[s][1][: hi - lo].copy_(trues[lo:hi], non_blocking=True)
+            ready[s].record(copy)
+        main.wait_event(ready[s])
+        ops.pearson_stats(slots[s][0][: hi - lo], slots[s][1][: hi - lo], stats, layout=layout)
+        free[s].record(main)
     r, _ = ops.pearson_finalize(stats[0])
     return r.cpu().numpy().astype(np.float32)

@@ -26,6 +26,36 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+# Launch tape: when TAPE is a list every C-ABI call is appended as (function, ctypes args, name) while it executes, so a
+# static kernel sequence (fixed buffers, see engine.Workspace) can be replayed next step with ~2 us of host time per
+# launch instead of re-deriving every argument in Python.
+TAPE = None
+
+
+def _run(name, *args):
+    fn = getattr(_lib.load(), name)
+    if TAPE is not None:
+        TAPE.append((fn, args, name))
+    rc = fn(*args)
+    if rc:
+        check(rc, name)
+
+
+def replay(tape) -> None:
+    for fn, args, name in tape:
+        if fn is None:
+            args()  # python callback recorded between launches (e.g. gradient-bucket all-reduce trigger)
+            continue
+        rc = fn(*args)
+        if rc:
+            check(rc, name)
+
+
+def zero_(t: torch.Tensor) -> None:
+    """Tape-able memset of a contiguous tensor."""
+    _run("tribe_zero", _ptr(t), t.numel() * t.element_size(), _stream())
+
+
 def _need(t, dtype, name):
     if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
         raise TribeError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
@@ -104,15 +134,14 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
     if SPLITK:
         ws = _splitk_workspace(out.device)
         g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel()
-    lib = _lib.load()
     log = GEMM_LOG
     if log is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     if probe is None:
-        check(lib.tribe_gemm_bf16(ctypes.byref(g), _stream()), "tribe_gemm_bf16")
+        _run("tribe_gemm_bf16", ctypes.byref(g), _stream())
     else:
-        check(lib.tribe_gemm_bf16_probe(ctypes.byref(g), _stream(), *probe), "tribe_gemm_bf16_probe")
+        _run("tribe_gemm_bf16_probe", ctypes.byref(g), _stream(), *probe)
     if log is not None:
         e1.record()
         log.append((e0, e1, 2.0 * m * n * k * (kgroup.numel() if kgroup is not None else batch)))
@@ -147,47 +176,47 @@ def ingest_features(x: torch.Tensor, out: torch.Tensor, col_off: int, layer_mean
     x = x.contiguous()
     B, L, D, T = x.shape
     _need(out, torch.bfloat16, "ingest out")
-    check(_lib.load().tribe_ingest_features(_ptr(x), _DT[x.dtype], B, L, D, T, int(layer_mean), _ptr(out), out.stride(0), col_off,
-                                            _stream()), "tribe_ingest_features")
+    _run("tribe_ingest_features", _ptr(x), _DT[x.dtype], B, L, D, T, int(layer_mean), _ptr(out), out.stride(0), col_off,
+                                            _stream())
 
 
 def scalenorm_fwd(x, g, y, rnorm) -> None:
     _need(x, torch.float32, "scalenorm x"), _need(y, torch.bfloat16, "scalenorm y")
     rows, dim = x.shape
-    check(_lib.load().tribe_scalenorm_fwd(_ptr(x), _ptr(g), _ptr(y), _ptr(rnorm), rows, dim, _stream()), "tribe_scalenorm_fwd")
+    _run("tribe_scalenorm_fwd", _ptr(x), _ptr(g), _ptr(y), _ptr(rnorm), rows, dim, _stream())
 
 
 def sublayer_bwd(dy_out, d_xn, x_in, rnorm, g, rs, dx_in, dx_in_bf16, d_rs, d_g) -> None:
     rows, dim = x_in.shape
-    check(_lib.load().tribe_sublayer_bwd(_ptr(dy_out), _ptr(d_xn), _ptr(x_in), _ptr(rnorm), _ptr(g), _ptr(rs), _ptr(dx_in),
-                                         _ptr(dx_in_bf16), _ptr(d_rs), _ptr(d_g), rows, dim, _stream()), "tribe_sublayer_bwd")
+    _run("tribe_sublayer_bwd", _ptr(dy_out), _ptr(d_xn), _ptr(x_in), _ptr(rnorm), _ptr(g), _ptr(rs), _ptr(dx_in),
+                                         _ptr(dx_in_bf16), _ptr(d_rs), _ptr(d_g), rows, dim, _stream())
 
 
 def softmax_fwd(s, p, n_valid) -> None:
     _need(s, torch.float32, "softmax s"), _need(p, torch.bfloat16, "softmax p")
     ld = s.shape[-1]
-    check(_lib.load().tribe_softmax_fwd(_ptr(s), _ptr(p), s.numel() // ld, n_valid, ld, _stream()), "tribe_softmax_fwd")
+    _run("tribe_softmax_fwd", _ptr(s), _ptr(p), s.numel() // ld, n_valid, ld, _stream())
 
 
 def softmax_bwd(p, dp, ds, scale, n_valid) -> None:
     ld = p.shape[-1]
-    check(_lib.load().tribe_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), scale, p.numel() // ld, n_valid, ld, _stream()), "tribe_softmax_bwd")
+    _run("tribe_softmax_bwd", _ptr(p), _ptr(dp), _ptr(ds), scale, p.numel() // ld, n_valid, ld, _stream())
 
 
 def colsum(x, out, y=None, accumulate=False) -> None:
     """out[c] (+)= sum_r x[r, c] (* y[r, c])."""
     rows, cols = x.shape
-    check(_lib.load().tribe_colsum(_ptr(x), _DT[x.dtype], _ptr(y), _DT[y.dtype] if y is not None else 0, _ptr(out), rows, cols,
-                                   x.stride(0), int(accumulate), _stream()), "tribe_colsum")
+    _run("tribe_colsum", _ptr(x), _DT[x.dtype], _ptr(y), _DT[y.dtype] if y is not None else 0, _ptr(out), rows, cols,
+                                   x.stride(0), int(accumulate), _stream())
 
 
 def cast_f32_bf16(src, dst) -> None:
     _need(src, torch.float32, "cast src"), _need(dst, torch.bfloat16, "cast dst")
-    check(_lib.load().tribe_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "tribe_cast_f32_bf16")
+    _run("tribe_cast_f32_bf16", _ptr(src), _ptr(dst), src.numel(), _stream())
 
 
 def axpby(src, dst, a=1.0, accumulate=False) -> None:
-    check(_lib.load().tribe_axpby_f32(_ptr(src), _ptr(dst), a, int(accumulate), src.numel(), _stream()), "tribe_axpby_f32")
+    _run("tribe_axpby_f32", _ptr(src), _ptr(dst), a, int(accumulate), src.numel(), _stream())
 
 
 def adaptive_avg_pool_fwd(x, t_out) -> torch.Tensor:
@@ -195,8 +224,7 @@ def adaptive_avg_pool_fwd(x, t_out) -> torch.Tensor:
     x = x.contiguous()
     _need(x, torch.float32, "pool x")
     y = torch.empty(*x.shape[:-1], t_out, device=x.device, dtype=torch.float32)
-    check(_lib.load().tribe_adaptive_avg_pool_fwd(_ptr(x), _ptr(y), x.numel() // x.shape[-1], x.shape[-1], t_out, _stream()),
-          "tribe_adaptive_avg_pool_fwd")
+    _run("tribe_adaptive_avg_pool_fwd", _ptr(x), _ptr(y), x.numel() // x.shape[-1], x.shape[-1], t_out, _stream())
     return y
 
 
@@ -204,41 +232,37 @@ def adaptive_avg_pool_bwd(dy, t_in) -> torch.Tensor:
     dy = dy.contiguous()
     _need(dy, torch.float32, "pool dy")
     dx = torch.empty(*dy.shape[:-1], t_in, device=dy.device, dtype=torch.float32)
-    check(_lib.load().tribe_adaptive_avg_pool_bwd(_ptr(dy), _ptr(dx), dy.numel() // dy.shape[-1], t_in, dy.shape[-1], _stream()),
-          "tribe_adaptive_avg_pool_bwd")
+    _run("tribe_adaptive_avg_pool_bwd", _ptr(dy), _ptr(dx), dy.numel() // dy.shape[-1], t_in, dy.shape[-1], _stream())
     return dx
 
 
 def token_pool_fwd(x, y, B, t_in, t_out, C) -> None:
-    check(_lib.load().tribe_token_pool_fwd(_ptr(x), _ptr(y), B, t_in, t_out, C, _stream()), "tribe_token_pool_fwd")
+    _run("tribe_token_pool_fwd", _ptr(x), _ptr(y), B, t_in, t_out, C, _stream())
 
 
 def token_pool_bwd(dy, dx, B, t_in, t_out, C) -> None:
-    check(_lib.load().tribe_token_pool_bwd(_ptr(dy), _DT[dy.dtype], _ptr(dx), _DT[dx.dtype], B, t_in, t_out, C, _stream()),
-          "tribe_token_pool_bwd")
+    _run("tribe_token_pool_bwd", _ptr(dy), _DT[dy.dtype], _ptr(dx), _DT[dx.dtype], B, t_in, t_out, C, _stream())
 
 
 def add_rows_periodic(x, pos, out, rows, cols, row_mod, *, ld_x=0, ld_pos, ld_out, x_off=0, pos_off=0, out_off=0) -> None:
     """out[r, c] = (x[r, c] if x is not None else 0) + pos[r % row_mod, c]; offsets are in elements."""
     xp = ctypes.c_void_p(x.data_ptr() + 4 * x_off) if x is not None else None
-    check(_lib.load().tribe_add_rows_periodic(xp, ld_x, ctypes.c_void_p(pos.data_ptr() + 4 * pos_off), ld_pos,
-                                              ctypes.c_void_p(out.data_ptr() + 4 * out_off), ld_out, rows, cols, row_mod, _stream()),
-          "tribe_add_rows_periodic")
+    _run("tribe_add_rows_periodic", xp, ld_x, ctypes.c_void_p(pos.data_ptr() + 4 * pos_off), ld_pos,
+                                              ctypes.c_void_p(out.data_ptr() + 4 * out_off), ld_out, rows, cols, row_mod, _stream())
 
 
 def transpose_cast_bot(x, y) -> None:
     B, O, T = x.shape
     _need(x, torch.float32, "transpose x")
-    check(_lib.load().tribe_transpose_cast_bot(_ptr(x), _ptr(y), B, O, T, _stream()), "tribe_transpose_cast_bot")
+    _run("tribe_transpose_cast_bot", _ptr(x), _ptr(y), B, O, T, _stream())
 
 
 def subject_bias_grad(dy, subjects, d_bias, B, T, O, n_subjects) -> None:
-    check(_lib.load().tribe_subject_bias_grad(_ptr(dy), _ptr(subjects), _ptr(d_bias), B, T, O, n_subjects, _stream()),
-          "tribe_subject_bias_grad")
+    _run("tribe_subject_bias_grad", _ptr(dy), _ptr(subjects), _ptr(d_bias), B, T, O, n_subjects, _stream())
 
 
 def check_subjects(subjects, n_subjects, flag) -> None:
-    check(_lib.load().tribe_check_subjects(_ptr(subjects), subjects.numel(), n_subjects, _ptr(flag), _stream()), "tribe_check_subjects")
+    _run("tribe_check_subjects", _ptr(subjects), subjects.numel(), n_subjects, _ptr(flag), _stream())
 
 
 def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):
@@ -247,8 +271,8 @@ def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):
     loss = torch.empty(1, device=pred.device, dtype=torch.float32)
     grad = torch.empty_like(pred) if want_grad else None
     partial = torch.empty(1024, device=pred.device, dtype=torch.float64)
-    check(_lib.load().tribe_mse_fwd_bwd(_ptr(pred), _ptr(target), _ptr(loss), _ptr(grad), grad_scale, pred.numel(), _ptr(partial),
-                                        _stream()), "tribe_mse_fwd_bwd")
+    _run("tribe_mse_fwd_bwd", _ptr(pred), _ptr(target), _ptr(loss), _ptr(grad), grad_scale, pred.numel(), _ptr(partial),
+                                        _stream())
     return loss, grad
 
 
@@ -257,41 +281,47 @@ def pearson_stats(pred, target, stats, *, layout: str, group=None, n_groups: int
 
     layout "no": pred/target are row-major (N, O).  layout "bdt": they are (B, D, T) and rows are the flattened
     ``(b t)`` of ``rearrange(x, "b d t -> (b t) d")`` (pl_module.py:54-55, main.py:472-473) without materialising it."""
-    _need(pred, torch.float32, "pearson pred"), _need(target, torch.float32, "pearson target")
     if stats.dtype != torch.float64:
         raise TribeError("pearson stats must be fp64")
     if layout == "no":
+        _need(pred, torch.float32, "pearson pred"), _need(target, torch.float32, "pearson target")
         n, o = pred.shape
         args = (n, o, 1, o, 1, 1)
     elif layout == "bdt":
+        # a parcel slice x[:, lo:hi] of a contiguous (B, D, T) tensor is read in place (stride_b stays D_full * T)
         b, d, t = pred.shape
-        args = (b * t, d, t, d * t, t, 1)
+        for x, name in ((pred, "pearson pred"), (target, "pearson target")):
+            if x.dtype != torch.float32 or not x.is_cuda or x.shape != pred.shape:
+                raise TribeError(f"{name}: expected CUDA float32 of shape {tuple(pred.shape)}, got {x.dtype} {x.device} {tuple(x.shape)}")
+        if not (pred.stride(2) == 1 and pred.stride(1) == t and pred.stride() == target.stride()) and b * d * t > 0:
+            pred, target = pred.contiguous(), target.contiguous()
+        args = (b * t, d, t, pred.stride(0) if b > 1 else d * t, t, 1)
     else:
         raise TribeError(f"unknown layout {layout}")
-    check(_lib.load().tribe_pearson_stats(_ptr(pred), _ptr(target), *args, _ptr(group), n_groups if group is not None else 0,
-                                          _ptr(stats), _stream()), "tribe_pearson_stats")
+    _run("tribe_pearson_stats", _ptr(pred), _ptr(target), *args, _ptr(group), n_groups if group is not None else 0,
+                                          _ptr(stats), _stream())
 
 
 def pearson_finalize(stats_one_group, want_mean=False):
     o = stats_one_group.shape[-1]
     r = torch.empty(o, device=stats_one_group.device, dtype=torch.float32)
     mean = torch.empty(1, device=r.device, dtype=torch.float32) if want_mean else None
-    check(_lib.load().tribe_pearson_finalize(_ptr(stats_one_group), o, _ptr(r), _ptr(mean), _stream()), "tribe_pearson_finalize")
+    _run("tribe_pearson_finalize", _ptr(stats_one_group), o, _ptr(r), _ptr(mean), _stream())
     return r, mean
 
 
 def cast_bf16_f32(src, dst) -> None:
-    check(_lib.load().tribe_cast_bf16_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), "tribe_cast_bf16_f32")
+    _run("tribe_cast_bf16_f32", _ptr(src), _ptr(dst), src.numel(), _stream())
 
 
 def nce_expsums(logits, n, shift, row_sum, col_sum) -> None:
-    check(_lib.load().tribe_nce_expsums(_ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _stream()), "tribe_nce_expsums")
+    _run("tribe_nce_expsums", _ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _stream())
 
 
 def nce_loss(logits, n, shift, row_sum, col_sum, loss) -> None:
-    check(_lib.load().tribe_nce_loss(_ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(loss), _stream()), "tribe_nce_loss")
+    _run("tribe_nce_loss", _ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(loss), _stream())
 
 
 def nce_grad(logits, n, shift, row_sum, col_sum, upstream, scale, g) -> None:
-    check(_lib.load().tribe_nce_grad(_ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(upstream), scale, _ptr(g),
-                                     g.stride(0), _stream()), "tribe_nce_grad")
+    _run("tribe_nce_grad", _ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(upstream), scale, _ptr(g),
+                                     g.stride(0), _stream())

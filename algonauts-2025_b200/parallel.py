@@ -73,10 +73,12 @@ def parcel_bounds(n_parcels: int, world_size: int) -> list[tuple[int, int]]:
 
 
 def exchange_parcel_shards(local: torch.Tensor, group=None) -> tuple[torch.Tensor, tuple[int, int]]:
-    """local: (n_local_rows, O) rows owned by this rank -> (n_total_rows, O_shard): every rank's rows for THIS rank's
-    parcel shard, ordered by source rank.  One all-gather of row counts + one all-to-all."""
+    """local: (n_local_rows, O) rows — or (n_local_windows, O, T) predictions as the model returns them — owned by this
+    rank -> (n_total, O_shard[, T]): every rank's rows/windows for THIS rank's parcel shard, ordered by source rank.
+    One all-gather of counts + one all-to-all."""
     rank, ws = world()
-    n_local, O = local.shape
+    n_local, O = local.shape[0], local.shape[1]
+    tail = tuple(local.shape[2:])
     bounds = parcel_bounds(O, ws)
     lo, hi = bounds[rank]
     if ws == 1:
@@ -85,7 +87,7 @@ def exchange_parcel_shards(local: torch.Tensor, group=None) -> tuple[torch.Tenso
     dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=local.device), group=group)
     counts = [int(c.item()) for c in counts]
     send = [local[:, a:b].contiguous() for a, b in bounds]
-    recv = [torch.empty(counts[src], hi - lo, dtype=local.dtype, device=local.device) for src in range(ws)]
+    recv = [torch.empty(counts[src], hi - lo, *tail, dtype=local.dtype, device=local.device) for src in range(ws)]
     if dist.get_backend(group) == "nccl":
         dist.all_to_all(recv, send, group=group)
     else:  # gloo (CPU tests) has no all-to-all: the same blocks move as point-to-point sends
@@ -111,14 +113,15 @@ def gather_parcels(r_shard: torch.Tensor, n_parcels: int, group=None) -> torch.T
 
 
 def sharded_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=None) -> torch.Tensor:
-    """Per-parcel Pearson r over ALL ranks' rows, parcels sharded across ranks.  (n_local, O) fp32 CUDA -> (O,) fp32."""
+    """Per-parcel Pearson r over ALL ranks' rows, parcels sharded across ranks.  Inputs are this rank's (n_local, O)
+    row-major matrices or (n_windows_local, O, T) prediction tensors, fp32 CUDA -> (O,) fp32 on every rank."""
     from . import ops
 
     O = preds_local.shape[1]
     p_shard, _ = exchange_parcel_shards(preds_local, group)
     t_shard, _ = exchange_parcel_shards(trues_local, group)
     stats = torch.zeros(1, 6, p_shard.shape[1], device=p_shard.device, dtype=torch.float64)
-    ops.pearson_stats(p_shard.contiguous(), t_shard.contiguous(), stats, layout="no")
+    ops.pearson_stats(p_shard.contiguous(), t_shard.contiguous(), stats, layout="no" if p_shard.dim() == 2 else "bdt")
     r, _ = ops.pearson_finalize(stats[0])
     return gather_parcels(r, O, group)
 
@@ -128,7 +131,7 @@ def allreduced_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, gro
     from . import ops
 
     stats = torch.zeros(1, 6, preds_local.shape[1], device=preds_local.device, dtype=torch.float64)
-    ops.pearson_stats(preds_local.contiguous(), trues_local.contiguous(), stats, layout="no")
+    ops.pearson_stats(preds_local.contiguous(), trues_local.contiguous(), stats, layout="no" if preds_local.dim() == 2 else "bdt")
     _, ws = world()
     if ws > 1:
         dist.all_reduce(stats, group=group)

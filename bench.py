@@ -136,7 +136,100 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "windows_per_step": 1, "contrastive": bool(args.contrastive)},
             "cpu_baseline": {"value": r["windows_per_s"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["windows_per_s"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    pe = cpu_pearson_baseline()
+    line["pearson_eval"] = {"metric": "Pearson eval parcel-TRs/s", "value": pe["value"], "unit": pe["unit"], "cpu_baseline": pe}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ Pearson eval leg
+EVAL_WINDOWS, EVAL_PARCELS, EVAL_TRS = 2560, 1000, 100  # Movie10-shaped held-out set, 256 M parcel-TRs
+
+
+def cpu_pearson_baseline(n_windows: int = 256):
+    """The reference's literal evaluation loop (main.py:470-476): host rearrange + 1000 x scipy.stats.pearsonr."""
+    import numpy as np
+    from oracle import tribe_oracle as O
+
+    rng = np.random.default_rng(7)
+    trues = rng.standard_normal((n_windows, EVAL_PARCELS, EVAL_TRS), dtype=np.float32)
+    preds = (0.2 * trues + rng.standard_normal(trues.shape, dtype=np.float32)).astype(np.float32)
+    t0 = time.perf_counter()
+    r = O.multidim_pearson_scipy(preds, trues)
+    dt = time.perf_counter() - t0
+    assert r.shape == (EVAL_PARCELS,)
+    n = n_windows * EVAL_PARCELS * EVAL_TRS
+    return {"value": n / dt, "unit": "parcel-TRs/s", "cores": 1, "kind": "port",
+            "sample": f"{n_windows} windows x {EVAL_PARCELS} parcels x {EVAL_TRS} TRs through the main.py:470-476 scipy.stats.pearsonr loop"}
+
+
+def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with_cpu: bool):
+    """Per-parcel Pearson r over (windows, parcels, TRs) prediction/target tensors, parcels sharded 1000/G per rank
+    (no data-path collective: shards are independent; r is gathered once at the end, outside the kernel timing)."""
+    import torch.distributed as dist
+
+    from algonauts2025_b200 import metrics, ops, parallel
+
+    lo, hi = parallel.parcel_bounds(EVAL_PARCELS, world)[rank]
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    trues = torch.randn(EVAL_WINDOWS, hi - lo, EVAL_TRS, device="cuda", generator=g)
+    preds = 0.2 * trues + torch.randn(EVAL_WINDOWS, hi - lo, EVAL_TRS, device="cuda", generator=g)
+    stats = torch.zeros(1, 6, hi - lo, device="cuda", dtype=torch.float64)
+
+    def one():
+        stats.zero_()
+        ops.pearson_stats(preds, trues, stats, layout="bdt")
+        return ops.pearson_finalize(stats[0])[0]
+
+    for _ in range(max(warmup, 3)):
+        r = one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b, c in ev:  # operands (2 x 1.02 GB / G) exceed L2, every pass streams from HBM
+        a.record()
+        stats.zero_()
+        b.record()
+        ops.pearson_stats(preds, trues, stats, layout="bdt")
+        c.record()
+        r = ops.pearson_finalize(stats[0])[0]
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    torch.cuda.synchronize()
+    total_ms = ev[0][0].elapsed_time(end)
+    kern_ms = sum(b.elapsed_time(c) for _, b, c in ev) / steps
+    # end to end from HOST arrays (what main.py:470-473 holds after the predict loop): chunked H2D + statistics + r back
+    n_e2e = 640 // world
+    hp = preds[:n_e2e].cpu().pin_memory()
+    ht = trues[:n_e2e].cpu().pin_memory()
+    metrics.pearson_from_host(hp, ht)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r_host = metrics.pearson_from_host(hp, ht)
+    e2e_s = time.perf_counter() - t0
+    assert r_host.shape == (hi - lo,)
+    t = torch.tensor([total_ms, kern_ms, e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms, e2e_s = (float(x) for x in t.cpu())
+    r_all = parallel.gather_parcels(r, EVAL_PARCELS)
+    if rank != 0:
+        return None
+    n_total = EVAL_WINDOWS * EVAL_PARCELS * EVAL_TRS
+    shard_bytes = 8.0 * EVAL_WINDOWS * (hi - lo) * EVAL_TRS
+    gbs = shard_bytes / (kern_ms / 1e3) / 1e9
+    out = {"metric": "Pearson eval parcel-TRs/s", "value": n_total * steps / (total_ms / 1e3), "unit": "parcel-TRs/s", "n_gpus": world,
+           "scaling": "strong", "ms_per_pass": total_ms / steps, "mean_r": float(r_all.mean()),
+           "config": {"workload": f"per-parcel Pearson r, {EVAL_WINDOWS} windows x {EVAL_PARCELS} parcels x {EVAL_TRS} TRs fp32 (b,d,t) layout, parcels sharded {EVAL_PARCELS}/{world} per GPU",
+                      "l2": "operands larger than L2"},
+           "e2e": {"value": n_e2e * EVAL_PARCELS * EVAL_TRS / e2e_s,
+                   "unit": "parcel-TRs/s", "h2d_bytes_per_step": 8 * n_e2e * (hi - lo) * EVAL_TRS, "d2h_bytes_per_step": 4 * (hi - lo),
+                   "sample": f"{n_e2e} windows per rank from pinned host arrays via metrics.pearson_from_host"},
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None,
+                        "kernel": "pearson_bdt_kernel<4>", "peak_source": peaks["src"] + " copy bandwidth", "bytes_per_parcel_tr": 8}}
+    if with_cpu:
+        out["cpu_baseline"] = cpu_pearson_baseline()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
@@ -254,6 +347,12 @@ def run_ours(args):
                 "clocks": clk}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+    del trainer, opt, sched, module, model, dev
+    torch.cuda.empty_cache()
+    pe = pearson_eval_leg(rank, world, max(K, 5), W, measured_peaks(), world == 1 and not args.no_cpu_baseline) if not args.no_pearson else None
+    if rank == 0:
+        if pe is not None:
+            line["pearson_eval"] = pe
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -268,6 +367,7 @@ def main():
     ap.add_argument("--contrastive", type=int, default=0)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
     ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -404,6 +404,36 @@ def test_pearson_bdt_layout_matches_scipy_loop():
         assert float(np.abs(rs.cpu().numpy() - ref_s).max()) < 1e-5
 
 
+@pytest.mark.parametrize("Bsz,D,T", [(1, 7, 100), (9, 1000, 100), (5, 37, 298), (6, 50, 33), (3, 11, 3), (2, 5, 1500)])
+def test_pearson_bdt_shapes_slices_and_groups(Bsz, D, T):
+    """(B, D, T) statistics kernel: vector (T % 4 == 0) and scalar item mapping, long-T fallback, parcel slices read in
+    place (parcel-sharded evaluation), per-window group ids with repeated / alternating runs."""
+    torch.manual_seed(15)
+    true = torch.randn(Bsz, D, T)
+    pred = 0.3 * true + torch.randn(Bsz, D, T) - 0.25
+    ref = O.pearson_columns_f64(O.flatten_bdt(pred).numpy(), O.flatten_bdt(true).numpy())
+    pd, td = pred.to(DEV), true.to(DEV)
+    stats = torch.zeros(1, 6, D, device=DEV, dtype=torch.float64)
+    ops.pearson_stats(pd, td, stats, layout="bdt")
+    assert float(stats[0, 0].min()) == float(stats[0, 0].max()) == Bsz * T
+    if Bsz * T > 2:
+        r, _ = ops.pearson_finalize(stats[0])
+        assert float(np.abs(r.cpu().numpy() - ref).max()) < 1e-5
+    lo, hi = D // 3, D - D // 4
+    st2 = torch.zeros(1, 6, hi - lo, device=DEV, dtype=torch.float64)
+    ops.pearson_stats(pd[:, lo:hi], td[:, lo:hi], st2, layout="bdt")  # non-contiguous views, no copy
+    torch.testing.assert_close(st2[0], stats[0][:, lo:hi], rtol=1e-6, atol=1e-4)  # block/atomic order differs
+    groups = torch.tensor([(i // 2) % 3 for i in range(Bsz)])
+    gst = torch.zeros(3, 6, D, device=DEV, dtype=torch.float64)
+    ops.pearson_stats(pd, td, gst, layout="bdt", group=groups.to(DEV), n_groups=3)
+    # group runs change how many windows share an fp32 partial sum before the fp64 fold: equal to fp32 rounding only
+    torch.testing.assert_close(gst.sum(0), stats[0], rtol=1e-6, atol=1e-4)
+    for s in groups.unique().tolist():
+        sel = groups == s
+        want = (pred[sel].double() * true[sel].double()).sum((0, 2))
+        torch.testing.assert_close(gst[s, 5].cpu(), want, rtol=1e-6, atol=1e-4)
+
+
 def test_pearson_ragged_and_odd_parcel_counts():
     torch.manual_seed(14)
     for n, o in ((1, 5), (7, 1003), (1000, 37), (4099, 1000)):

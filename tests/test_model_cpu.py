@@ -117,6 +117,11 @@ GLOO_WORKER = textwrap.dedent("""
     r_shard = torch.from_numpy(O.pearson_columns_f64(shard.numpy(), tshard.numpy())).float()
     r = parallel.gather_parcels(r_shard, 13)
     np.testing.assert_allclose(r.numpy(), O.pearson_columns_f64(preds.numpy(), trues.numpy()), atol=1e-6)
+    # the same exchange on (windows, parcels, TRs) prediction tensors (the layout FmriEncoder.forward returns)
+    p3 = torch.randn(7, 13, 5, generator=g)
+    wins = slice(0, 3) if rank == 0 else slice(3, 7)
+    shard3, (lo3, hi3) = parallel.exchange_parcel_shards(p3[wins].contiguous())
+    assert torch.equal(shard3, p3[:, lo3:hi3])
     # ensemble: one member per rank
     member_pred = preds * (rank + 1)
     member_r = torch.linspace(0.0, 0.3, 13) * (rank + 1)

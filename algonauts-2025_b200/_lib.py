@@ -135,7 +135,7 @@ _SIGS = {
     "tribe_add_rows_periodic": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
     "tribe_transpose_cast_bot": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
     "tribe_subject_bias_grad": [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
-    "tribe_check_subjects": [c_vp, c_i64, c_i64, c_vp, c_vp],
+    "tribe_check_subjects": [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "tribe_mse_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp],
     "tribe_pearson_stats": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp],
     "tribe_pearson_finalize": [c_vp, c_i64, c_vp, c_vp, c_vp],
@@ -144,6 +144,8 @@ _SIGS = {
     "tribe_nce_grad": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp],
     "tribe_cast_bf16_f32": [c_vp, c_vp, c_i64, c_vp],
     "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
+    "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "tribe_adam_hyper": [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["tribe_last_error", "tribe_abi_version", "tribe_launch_count"])
 
@@ -175,5 +177,9 @@ def check(rc: int, what: str) -> None:
         raise TribeError(f"{what} failed (code {rc}): {msg}")
 
 
+REPLAYED_LAUNCHES = 0  # kernels launched by CUDA-graph replays (graphed.py): they bypass the C entry points' counter
+
+
 def launch_count() -> int:
-    return int(load().tribe_launch_count())
+    """Kernels of this library launched so far by this process: direct launches + launches inside replayed graphs."""
+    return int(load().tribe_launch_count()) + REPLAYED_LAUNCHES

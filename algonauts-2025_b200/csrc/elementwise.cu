@@ -474,9 +474,13 @@ __global__ void __launch_bounds__(256) subject_bias_grad_kernel(const __nv_bfloa
   atomicAdd(d_bias + s * O + o, acc);
 }
 
-__global__ void check_subjects_kernel(const long long* __restrict__ subjects, int64_t n, int64_t n_subjects, int* __restrict__ flag) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    if (subjects[i] >= n_subjects || subjects[i] < 0) atomicExch(flag, 1);
+__global__ void check_subjects_kernel(const long long* __restrict__ subjects, int64_t n, int64_t n_subjects, int* __restrict__ flag,
+                                      long long* __restrict__ clamped) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const long long s = subjects[i];
+    if (s >= n_subjects || s < 0) atomicExch(flag, 1);
+    if (clamped) clamped[i] = s < 0 ? 0 : (s >= n_subjects ? n_subjects - 1 : s);
+  }
 }
 
 }  // namespace tribe
@@ -657,10 +661,10 @@ extern "C" int tribe_subject_bias_grad(const void* dy_bf16, const int64_t* subje
   return TRIBE_OK;
 }
 
-extern "C" int tribe_check_subjects(const int64_t* subjects, int64_t n, int64_t n_subjects, int32_t* flag_out, void* stream) {
-  if (!subjects || !flag_out || n <= 0) return set_error(TRIBE_EINVAL, "check_subjects: bad arguments");
-  check_subjects_kernel<<<grid_for(n, 256, 64), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(subjects), n,
-                                                                                                   n_subjects, flag_out);
+extern "C" int tribe_check_subjects(const int64_t* subjects, int64_t n, int64_t n_subjects, int32_t* flag_out, int64_t* clamped_out, void* stream) {
+  if (!subjects || !flag_out || n <= 0 || n_subjects <= 0) return set_error(TRIBE_EINVAL, "check_subjects: bad arguments");
+  check_subjects_kernel<<<grid_for(n, 256, 64), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(subjects), n, n_subjects, flag_out, reinterpret_cast<long long*>(clamped_out));
   TRIBE_CHECK_LAUNCH("check_subjects");
   return TRIBE_OK;
 }

@@ -25,24 +25,29 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = p - step_size * (m / denom);
 }
 
+// hyper == nullptr: scalars come from the launch arguments; otherwise from 6 floats in device memory
+// {beta1, beta2, step_size, inv_bc2_sqrt, eps, weight_decay}, so a captured CUDA graph replays with fresh values.
+// All traffic is streaming (evict-first): nothing here is re-read before ~28 GB have passed through L2, and the
+// kernel may run beside the backward GEMMs whose operand tiles should stay L2-resident.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    __nv_bfloat16* __restrict__ p16, int64_t n, float beta1, float beta2, float step_size,
-                                                   float inv_bc2_sqrt, float eps, float wd) {
+                                                   float inv_bc2_sqrt, float eps, float wd, const float* __restrict__ hyper) {
+  if (hyper) beta1 = hyper[0], beta2 = hyper[1], step_size = hyper[2], inv_bc2_sqrt = hyper[3], eps = hyper[4], wd = hyper[5];
   const int64_t nvec = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 pp = __ldcs(reinterpret_cast<const float4*>(p) + i);
+    const float4 gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = __ldcs(reinterpret_cast<const float4*>(m) + i);
+    float4 vv = __ldcs(reinterpret_cast<const float4*>(v) + i);
     adam_one(pp.x, gg.x, mm.x, vv.x, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
     adam_one(pp.y, gg.y, mm.y, vv.y, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
     adam_one(pp.z, gg.z, mm.z, vv.z, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
     adam_one(pp.w, gg.w, mm.w, vv.w, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
-    reinterpret_cast<float4*>(p)[i] = pp;
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    if (p16) reinterpret_cast<uint2*>(p16)[i] = make_uint2(opt_pack2(pp.x, pp.y), opt_pack2(pp.z, pp.w));
+    __stcs(reinterpret_cast<float4*>(p) + i, pp);
+    __stcs(reinterpret_cast<float4*>(m) + i, mm);
+    __stcs(reinterpret_cast<float4*>(v) + i, vv);
+    if (p16) __stcs(reinterpret_cast<uint2*>(p16) + i, make_uint2(opt_pack2(pp.x, pp.y), opt_pack2(pp.z, pp.w)));
   }
   for (int64_t i = (nvec << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     float pp = p[i], mm = m[i], vv = v[i];
@@ -50,6 +55,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     p[i] = pp, m[i] = mm, v[i] = vv;
     if (p16) p16[i] = __float2bfloat16(pp);
   }
+}
+
+__global__ void set_floats_kernel(float* __restrict__ dst, int n, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
+  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+  if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
 }
 
 }  // namespace tribe
@@ -65,7 +75,29 @@ extern "C" int tribe_adam_step(float* p, const float* g, float* m, float* v, voi
   const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, beta1, beta2, step_size, inv_bc2_sqrt, eps, weight_decay);
+      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, beta1, beta2, step_size, inv_bc2_sqrt, eps, weight_decay, nullptr);
   TRIBE_CHECK_LAUNCH("adam_step");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, void* stream) {
+  using namespace tribe;
+  if (!p || !g || !m || !v || !hyper || n <= 0) return set_error(TRIBE_EINVAL, "adam_step_dev: bad arguments");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v);
+  if ((al & 15) || (reinterpret_cast<uintptr_t>(p_bf16) & 7)) return set_error(TRIBE_EINVAL, "adam_step_dev: buffers must be 16-byte aligned (bf16: 8)");
+  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, hyper);
+  TRIBE_CHECK_LAUNCH("adam_step_dev");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_adam_hyper(float* hyper_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+  using namespace tribe;
+  if (!hyper_dev || step <= 0) return set_error(TRIBE_EINVAL, "adam_hyper: bad arguments");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  set_floats_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hyper_dev, 6, beta1, beta2, static_cast<float>(static_cast<double>(lr) / bc1),
+                                                                        static_cast<float>(1.0 / sqrt(bc2)), eps, weight_decay, 0.f, 0.f);
+  TRIBE_CHECK_LAUNCH("adam_hyper");
   return TRIBE_OK;
 }

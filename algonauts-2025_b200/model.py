@@ -257,6 +257,9 @@ class FmriEncoder(nn.Module):
     def _draw_dropout(self) -> list[str]:
         """model.py:134-141 verbatim in behaviour: one CPU ``torch.rand(1)`` per modality *evaluated before*
         ``and self.training`` (so eval also advances the generator); NumPy global RNG if everything was selected."""
+        preset = self.__dict__.get("_preset_dropped")
+        if preset:  # drawn ahead of a CUDA-graph capture / replay by graphed.GraphedTrainStep (same draws, same order)
+            return list(preset.pop(0))
         dropped = []
         for modality in self.feature_dims.keys():
             if torch.rand(1).item() < self.config.modality_dropout and self.training:
@@ -265,40 +268,54 @@ class FmriEncoder(nn.Module):
             dropped = list(np.random.choice(dropped, len(dropped) - 1, replace=False))
         return dropped
 
-    # common.py:53-55 asserts ``subjects.max() < N`` on the host (a device sync in the reference as well).  With
-    # ``defer_subject_check = True`` (set by trainer.MiniTrainer) the range check still runs on the device every call
-    # but its flag is read back asynchronously and raised at the next call / ``flush_subject_check()``, so the training
-    # loop has no host-device synchronisation point.
+    # common.py:53-55 asserts ``subjects.max() < N`` on the host (a device sync in the reference as well).  The range
+    # check always runs on the device into a sticky per-model flag.  With ``defer_subject_check = True`` (set by
+    # trainer.MiniTrainer) the flag is copied to pinned host memory asynchronously and examined at the NEXT call /
+    # ``flush_subject_check()``, so the training loop has no host-device synchronisation point and the whole step can
+    # be captured in a CUDA graph (the copy is a memcpy node).
     defer_subject_check = False
+    _MSG = "Subject index higher than number of subjects used to initialize the weights."
 
     def flush_subject_check(self) -> None:
-        pending = self.__dict__.get("_pending_subject_check")
-        if pending is not None:
-            event, host_flag = pending
-            event.synchronize()
-            self.__dict__["_pending_subject_check"] = None
-            assert int(host_flag.item()) == 0, "Subject index higher than number of subjects used to initialize the weights."
+        flags = self.__dict__.get("_subject_flags")
+        if flags is not None:
+            torch.cuda.current_stream(flags[0].device).synchronize()
+            bad = int(flags[0].item())
+            flags[0].zero_()
+            flags[1].zero_()
+            self.__dict__["_subject_event"] = None
+            assert bad == 0, self._MSG
 
     def _subjects(self, batch):
         subject_id = batch.data.get("subject_id", None)
         if subject_id is None:
             return None
         self._engine._check_flat()
-        subj = subject_id.to(self._engine.device, torch.int64, non_blocking=True).flatten().contiguous()
+        dev = self._engine.device
+        subj = subject_id.to(dev, torch.int64, non_blocking=True).flatten().contiguous()
         n = self.predictor.weights.shape[0]
-        flag = torch.zeros(1, device=subj.device, dtype=torch.int32)
-        ops.check_subjects(subj, n, flag)
+        flags = self.__dict__.get("_subject_flags")
+        if flags is None or flags[0].device != dev:
+            flags = self.__dict__["_subject_flags"] = (torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, dtype=torch.int32).pin_memory())
+        dev_flag, host_flag = flags
         if self.defer_subject_check:
-            self.flush_subject_check()
-            ring = self.__dict__.setdefault("_flag_ring", [torch.empty(1, dtype=torch.int32).pin_memory() for _ in range(2)])
-            ring.append(ring.pop(0))  # the previous call's buffer was consumed by flush_subject_check() above
-            host_flag = ring[0]
-            host_flag.copy_(flag, non_blocking=True)
-            event = torch.cuda.Event()
-            event.record()
-            self.__dict__["_pending_subject_check"] = (event, host_flag)
+            pending = self.__dict__.get("_subject_event")
+            if pending is not None:
+                pending.synchronize()  # the PREVIOUS call's flag copy: the host runs at most one step ahead
+            if int(host_flag.item()) != 0:
+                self.flush_subject_check()
+            safe = torch.empty_like(subj)  # ids clamped into range: the enqueued step stays in bounds until the flag is read
+            ops.check_subjects(subj, n, dev_flag, safe)
+            subj = safe
+            host_flag.copy_(dev_flag, non_blocking=True)
+            self.__dict__["_subject_event"] = None
+            if not torch.cuda.is_current_stream_capturing():  # graph replays poll host_flag themselves (graphed.py)
+                event = torch.cuda.Event()
+                event.record()
+                self.__dict__["_subject_event"] = event
         else:
-            assert int(flag.item()) == 0, "Subject index higher than number of subjects used to initialize the weights."
+            ops.check_subjects(subj, n, dev_flag)
+            self.flush_subject_check()
         return subj
 
     def _anchor(self):

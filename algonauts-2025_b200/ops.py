@@ -26,34 +26,10 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-# Launch tape: when TAPE is a list every C-ABI call is appended as (function, ctypes args, name) while it executes, so a
-# static kernel sequence (fixed buffers, see engine.Workspace) can be replayed next step with ~2 us of host time per
-# launch instead of re-deriving every argument in Python.
-TAPE = None
-
-
 def _run(name, *args):
-    fn = getattr(_lib.load(), name)
-    if TAPE is not None:
-        TAPE.append((fn, args, name))
-    rc = fn(*args)
+    rc = getattr(_lib.load(), name)(*args)
     if rc:
         check(rc, name)
-
-
-def replay(tape) -> None:
-    for fn, args, name in tape:
-        if fn is None:
-            args()  # python callback recorded between launches (e.g. gradient-bucket all-reduce trigger)
-            continue
-        rc = fn(*args)
-        if rc:
-            check(rc, name)
-
-
-def zero_(t: torch.Tensor) -> None:
-    """Tape-able memset of a contiguous tensor."""
-    _run("tribe_zero", _ptr(t), t.numel() * t.element_size(), _stream())
 
 
 def _need(t, dtype, name):
@@ -261,8 +237,8 @@ def subject_bias_grad(dy, subjects, d_bias, B, T, O, n_subjects) -> None:
     _run("tribe_subject_bias_grad", _ptr(dy), _ptr(subjects), _ptr(d_bias), B, T, O, n_subjects, _stream())
 
 
-def check_subjects(subjects, n_subjects, flag) -> None:
-    _run("tribe_check_subjects", _ptr(subjects), subjects.numel(), n_subjects, _ptr(flag), _stream())
+def check_subjects(subjects, n_subjects, flag, clamped=None) -> None:
+    _run("tribe_check_subjects", _ptr(subjects), subjects.numel(), n_subjects, _ptr(flag), _ptr(clamped), _stream())
 
 
 def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):

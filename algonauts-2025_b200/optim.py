@@ -61,6 +61,128 @@ class TribeAdam(torch.optim.Adam):
                 return False
         return True
 
+    # ------------------------------------------------------------------------------------------------ state / runs
+    def _ensure_state(self, flat, p, off):
+        st = self.state[p]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["exp_avg"] = flat.adam_m[off: off + p.numel()].view(p.shape)
+            st["exp_avg_sq"] = flat.adam_v[off: off + p.numel()].view(p.shape)
+            st["exp_avg"].zero_(), st["exp_avg_sq"].zero_()
+        elif st["exp_avg"].data_ptr() != flat.adam_m.data_ptr() + 4 * off:  # state loaded from a checkpoint
+            flat.adam_m[off: off + p.numel()].view(p.shape).copy_(st["exp_avg"])
+            flat.adam_v[off: off + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+            st["exp_avg"] = flat.adam_m[off: off + p.numel()].view(p.shape)
+            st["exp_avg_sq"] = flat.adam_v[off: off + p.numel()].view(p.shape)
+        return st
+
+    def _buffers(self, flat):
+        if flat.bf16 is None:
+            flat.refresh_bf16()
+        if getattr(flat, "adam_m", None) is None:
+            flat.adam_m, flat.adam_v = torch.zeros_like(flat.flat), torch.zeros_like(flat.flat)
+            flat.adam_hyper = torch.zeros(len(flat.params) + 1, 8, device=flat.device, dtype=torch.float32)
+            flat.adam_slot = {}
+
+    def init_all_state(self) -> bool:
+        """Create the (zero) state of every parameter now.  torch creates it lazily at a parameter's first gradient;
+        step = 0 with zero moments is the same state, and a captured graph must not contain the zero-fills."""
+        flat = self._flat()
+        if not self._fusable(flat):
+            return False
+        self._buffers(flat)
+        name_of = {id(p): n for n, p in flat.params.items()}
+        for group in self.param_groups:
+            for p in group["params"]:
+                self._ensure_state(flat, p, flat.offsets[name_of[id(p)]])
+        return True
+
+    @staticmethod
+    def _run_class(name: str) -> str:
+        # parameters that can be absent from a step on their own (dropped modality: grad stays None, model.py:158-159)
+        # never share a launch with others, so the runs of a captured graph keep a common step count forever
+        parts = name.split(".")
+        return ".".join(parts[:2]) if parts[0] in ("projectors", "contrastive_heads") else "core"
+
+    def _plan_runs(self, flat, split: bool, only=None):
+        """Contiguous [lo, hi) ranges of the flat buffer to update: adjacent parameters with a gradient, the same
+        param group and the same step count (and, with ``split``, the same run class) share one launch.  ``only``:
+        optional (lo, hi) window of the flat buffer (one gradient bucket)."""
+        name_of = {id(p): n for n, p in flat.params.items()}
+        todo = []
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                name = name_of[id(p)]
+                off = flat.offsets[name]
+                if only is not None and not (only[0] <= off < only[1]):
+                    continue
+                st = self._ensure_state(flat, p, off)
+                if p.grad.data_ptr() != flat.grad.data_ptr() + 4 * off:  # foreign gradient tensor: bring it into the flat buffer
+                    flat.gview(name).copy_(p.grad)
+                todo.append((off, off + _engine._round_up(p.numel(), _engine.ALIGN), int(st["step"].item()), gi,
+                             self._run_class(name) if split else "", p))
+        todo.sort(key=lambda t: t[0])
+        runs = []
+        for lo, hi, k, gi, cls_, p in todo:
+            if runs and runs[-1]["hi"] == lo and runs[-1]["k"] == k and runs[-1]["group"] == gi and runs[-1]["cls"] == cls_:
+                runs[-1]["hi"] = hi
+                runs[-1]["params"].append(p)
+            else:
+                runs.append({"lo": lo, "hi": hi, "k": k, "group": gi, "cls": cls_, "params": [p]})
+        return runs
+
+    def _launch(self, flat, run, k, stream, device_hyper: bool):
+        lib = _lib.load()
+        group = self.param_groups[run["group"]]
+        lr = float(group["lr"])
+        beta1, beta2 = (float(b) for b in group["betas"])
+        eps, wd = float(group["eps"]), float(group["weight_decay"])
+        lo, n = run["lo"], run["hi"] - run["lo"]
+        ptrs = (ctypes.c_void_p(flat.flat.data_ptr() + 4 * lo), ctypes.c_void_p(flat.grad.data_ptr() + 4 * lo),
+                ctypes.c_void_p(flat.adam_m.data_ptr() + 4 * lo), ctypes.c_void_p(flat.adam_v.data_ptr() + 4 * lo),
+                ctypes.c_void_p(flat.bf16.data_ptr() + 2 * lo))
+        if device_hyper:
+            slot = flat.adam_slot.setdefault(lo, len(flat.adam_slot))
+            check(lib.tribe_adam_step_dev(*ptrs, n, ctypes.c_void_p(flat.adam_hyper[slot].data_ptr()), stream), "tribe_adam_step_dev")
+        else:
+            check(lib.tribe_adam_step(*ptrs, n, lr, beta1, beta2, eps, wd, k, stream), "tribe_adam_step")
+
+    # ------------------------------------------------------------------------------------------------ CUDA-graph protocol
+    def graph_begin(self) -> None:
+        """Called (by graphed.GraphedTrainStep) right before a train step is captured: ``step()`` then records its
+        launches with device-resident hyper-parameters and leaves the host-side step counters untouched (a capture
+        executes nothing)."""
+        self._graph_runs = []
+
+    def graph_end(self) -> list:
+        runs, self._graph_runs = self._graph_runs, None
+        return runs
+
+    def prepare_replay(self, runs) -> None:
+        """Host bookkeeping of one optimizer step whose kernels are about to be replayed: advance the step counters and
+        refresh each run's device hyper-parameter block with the scheduler's current lr / betas."""
+        flat = self._flat()
+        lib = _lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for run in runs:
+            steps = {int(self.state[p]["step"].item()) for p in run["params"]}
+            if len(steps) != 1:
+                raise _lib.TribeError("captured Adam run lost its common step count; re-capture the train step")
+            k = steps.pop() + 1
+            for p in run["params"]:
+                self.state[p]["step"] += 1
+            group = self.param_groups[run["group"]]
+            beta1, beta2 = (float(b) for b in group["betas"])
+            slot = flat.adam_slot[run["lo"]]
+            check(lib.tribe_adam_hyper(ctypes.c_void_p(flat.adam_hyper[slot].data_ptr()), float(group["lr"]), beta1, beta2, float(group["eps"]),
+                                       float(group["weight_decay"]), k, stream), "tribe_adam_hyper")
+        self._opt_called = True  # what LR schedulers look at to warn about scheduler.step() before optimizer.step()
+        flat.opt_steps += 1
+        flat._sig = (sum(p._version for p in flat.params.values()), flat.opt_steps)
+
+    # ------------------------------------------------------------------------------------------------ step
     @torch.no_grad()
     def step(self, closure=None):
         flat = self._flat()
@@ -70,51 +192,23 @@ class TribeAdam(torch.optim.Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        if flat.bf16 is None:
-            flat.refresh_bf16()
-        if getattr(flat, "adam_m", None) is None:
-            flat.adam_m, flat.adam_v = torch.zeros_like(flat.flat), torch.zeros_like(flat.flat)
-        name_of = {id(p): n for n, p in flat.params.items()}
-        lib = _lib.load()
+        self._buffers(flat)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for group in self.param_groups:
-            lr = float(group["lr"])
-            beta1, beta2 = (float(b) for b in group["betas"])
-            eps, wd = float(group["eps"]), float(group["weight_decay"])
-            todo = []
-            for p in group["params"]:
-                if p.grad is None:
-                    continue
-                name = name_of[id(p)]
-                off = flat.offsets[name]
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    st["exp_avg"] = flat.adam_m[off: off + p.numel()].view(p.shape)
-                    st["exp_avg_sq"] = flat.adam_v[off: off + p.numel()].view(p.shape)
-                    st["exp_avg"].zero_(), st["exp_avg_sq"].zero_()
-                elif st["exp_avg"].data_ptr() != flat.adam_m.data_ptr() + 4 * off:  # state loaded from a checkpoint
-                    flat.adam_m[off: off + p.numel()].view(p.shape).copy_(st["exp_avg"])
-                    flat.adam_v[off: off + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
-                    st["exp_avg"] = flat.adam_m[off: off + p.numel()].view(p.shape)
-                    st["exp_avg_sq"] = flat.adam_v[off: off + p.numel()].view(p.shape)
-                if p.grad.data_ptr() != flat.grad.data_ptr() + 4 * off:  # foreign gradient tensor: bring it into the flat buffer
-                    flat.gview(name).copy_(p.grad)
-                st["step"] += 1
-                todo.append((off, off + _engine._round_up(p.numel(), _engine.ALIGN), int(st["step"].item())))
-            # merge adjacent parameters with the same step count into one launch
-            todo.sort()
-            runs = []
-            for lo, hi, k in todo:
-                if runs and runs[-1][1] == lo and runs[-1][2] == k:
-                    runs[-1][1] = hi
-                else:
-                    runs.append([lo, hi, k])
-            for lo, hi, k in runs:
-                n = hi - lo
-                check(lib.tribe_adam_step(ctypes.c_void_p(flat.flat.data_ptr() + 4 * lo), ctypes.c_void_p(flat.grad.data_ptr() + 4 * lo),
-                                          ctypes.c_void_p(flat.adam_m.data_ptr() + 4 * lo), ctypes.c_void_p(flat.adam_v.data_ptr() + 4 * lo),
-                                          ctypes.c_void_p(flat.bf16.data_ptr() + 2 * lo), n, lr, beta1, beta2, eps, wd, k, stream), "tribe_adam_step")
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing and getattr(self, "_graph_runs", None) is None:
+            raise _lib.TribeError("TribeAdam.step() inside a CUDA graph capture needs graph_begin() (see graphed.GraphedTrainStep)")
+        done = getattr(self, "_early", None)  # buckets already stepped inside the backward (overlap mode)
+        for run in self._plan_runs(flat, split=capturing):
+            if done and any(lo <= run["lo"] < hi for lo, hi in done):
+                continue
+            if capturing:
+                self._launch(flat, run, 0, stream, device_hyper=True)
+                self._graph_runs.append(run)
+            else:
+                for p in run["params"]:
+                    self.state[p]["step"] += 1
+                self._launch(flat, run, run["k"] + 1, stream, device_hyper=False)
+        self._early = None
         # the shadow weights are already current for the state the post-step hook is about to announce
         flat._sig = (sum(p._version for p in flat.params.values()), flat.opt_steps + 1)
         return loss

@@ -75,6 +75,23 @@ class DevicePrefetcher:
             ready.record(self.stream)
         return SegmentData(data={k: slot[k] for k in batch.data}, segments=batch.segments), ready
 
+    def feed(self, batches) -> "DevicePrefetcher":
+        """Iterate over another stream of host batches through the SAME two device slots (stable device addresses are
+        what lets ``graphed.GraphedTrainStep`` replay captured steps)."""
+        self.batches = batches
+        return self
+
+    def resident(self, batches) -> list:
+        """Load up to two host batches into the slots and return them as device-resident ``SegmentData``."""
+        out = []
+        for j, batch in enumerate(list(batches)[:2]):
+            cur, ready = self._load(batch, j)
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            out.append(cur)
+        torch.cuda.synchronize(self.device)
+        self.free = [None, None]
+        return out
+
     def __iter__(self):
         it = iter(self.batches)
         try:

@@ -26,15 +26,25 @@ def default_optimizer(params, total_steps: int, lr: float = 1e-4, model=None, fu
 
 
 class MiniTrainer:
-    def __init__(self, module, optimizer, scheduler=None, grad_sync=None):
+    """``use_graphs=True``: steady-state steps are replayed as whole-step CUDA graphs (``graphed.GraphedTrainStep``);
+    results are identical to the eager path (same kernels, same RNG draws), only the host enqueue cost disappears.
+    ``graph_collectives``: also capture the NCCL gradient all-reduces of ``grad_sync`` (data-parallel runs)."""
+
+    def __init__(self, module, optimizer, scheduler=None, grad_sync=None, use_graphs: bool = False, graph_collectives: bool = True):
         self.module, self.optimizer, self.scheduler, self.grad_sync = module, optimizer, scheduler, grad_sync
         self.global_step = 0
+        self.graph_collectives = graph_collectives
+        self._graphed = None
         model = getattr(module, "model", None)
         if model is not None and hasattr(model, "defer_subject_check"):
             model.defer_subject_check = True  # no host sync inside the step; raised one call later (see model.py)
+        if use_graphs:
+            from .graphed import GraphedTrainStep
 
-    def train_step(self, batch) -> torch.Tensor:
-        self.module.train()
+            self._graphed = GraphedTrainStep(self)
+
+    def run_step_body(self, batch) -> torch.Tensor:
+        """Device work of one automatic-optimisation step (everything a CUDA graph may capture)."""
         self.optimizer.zero_grad(set_to_none=True)
         if self.grad_sync is not None:
             self.grad_sync.begin_step()
@@ -43,10 +53,20 @@ class MiniTrainer:
         if self.grad_sync is not None:
             self.grad_sync.finish_step()
         self.optimizer.step()
+        return loss.detach()
+
+    def eager_step(self, batch) -> torch.Tensor:
+        self.module.train()
+        loss = self.run_step_body(batch)
         if self.scheduler is not None:
             self.scheduler.step()
         self.global_step += 1
-        return loss.detach()
+        return loss
+
+    def train_step(self, batch) -> torch.Tensor:
+        if self._graphed is not None:
+            return self._graphed.step(batch)
+        return self.eager_step(batch)
 
     @torch.no_grad()
     def validate(self, batches: tp.Iterable) -> dict:

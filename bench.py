@@ -259,15 +259,18 @@ def run_ours(args):
     # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
     opt, sched = default_optimizer(model.parameters(), total_steps=2 * (K + W) + 8, model=None if args.stock_adam else model)
     sync = parallel.GradAllReduce(model) if world > 1 else None
-    trainer = MiniTrainer(module, opt, sched, grad_sync=sync)
+    use_graphs = not args.eager and not args.stock_adam
+    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=not args.no_graph_comm)
     if sync is not None:
         passes, heads = (2, 1) if contrastive else (1, 0)
         orig_begin = sync.begin_step
         sync.begin_step = lambda: orig_begin(passes, heads)
 
-    # two distinct host batches (pinned) alternate; 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
+    # two distinct host batches (pinned) alternate through the two persistent device slots of a DevicePrefetcher;
+    # 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
     host = [synthetic_batch(batch_size=B, seed=1234 + 17 * rank + i, pin=True) for i in range(2)]
-    dev = [SegmentData(data={k: v.cuda(non_blocking=True) for k, v in b.data.items()}, segments=b.segments) for b in host]
+    prefetch = DevicePrefetcher(())
+    dev = prefetch.resident(host)
     h2d = sum(v.numel() * v.element_size() for v in host[0].data.values())
 
     def barrier():
@@ -277,12 +280,18 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for i in range(W):
-        trainer.train_step(dev[i % 2])
+        trainer.eager_step(dev[i % 2])
     barrier()
+    n_graphs = 0
+    if use_graphs:
+        # steady state of a long run: every modality-dropout variant of the step has been captured (captures execute
+        # nothing; weights, optimizer state and RNG streams are untouched)
+        n_graphs = trainer._graphed.warm(dev)
+        for i in range(2):
+            trainer.train_step(dev[i % 2])
+        barrier()
 
     # ---- timed region 1: device-resident inputs
-    gemm_log = []
-    ops.GEMM_LOG = gemm_log
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = algonauts2025_b200.launch_count()
@@ -295,12 +304,9 @@ def run_ours(args):
     cpu_enqueue_ms = 1e3 * (time.perf_counter() - t_cpu) / K  # host time to enqueue one step (no sync inside the loop)
     e1.record()
     barrier()
-    ops.GEMM_LOG = None
     clk = clocks.stop()
     launches = algonauts2025_b200.launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_log)
-    gemm_flops = sum(f for _, _, f in gemm_log)
 
     # ---- timed region 2: end to end through the public API from pinned host memory
     barrier()
@@ -311,18 +317,33 @@ def run_ours(args):
     # every step's loss is read back to pinned host memory inside the timed region (asynchronously, like a logger that
     # consumes it later; a blocking .item() per step would only measure Python launch latency after each sync)
     loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
-    for i, batch in enumerate(DevicePrefetcher(host[j % 2] for j in range(K))):
+    for i, batch in enumerate(prefetch.feed(host[j % 2] for j in range(K))):
         loss_host[i].copy_(trainer.train_step(batch), non_blocking=True)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+
+    # ---- roofline pass: the same K steps launched eagerly with a CUDA-event pair around every tcgen05 GEMM launch
+    # (events cannot be read back from inside a replayed graph; the kernels and their order are identical)
+    gemm_log = []
+    ops.GEMM_LOG = gemm_log
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(K):
+        trainer.eager_step(dev[i % 2])
+    g1.record()
+    barrier()
+    ops.GEMM_LOG = None
+    ms_eager = g0.elapsed_time(g1)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_log)
+    gemm_flops = sum(f for _, _, f in gemm_log)
     last = float(loss_host[-1])
     assert all(math.isfinite(float(x)) for x in loss_host), "non-finite loss in the end-to-end loop"
 
-    t = torch.tensor([ms, ms_e2e, gemm_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, gemm_ms, ms_eager], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, gemm_ms = (float(x) for x in t.cpu())
+    ms, ms_e2e, gemm_ms, ms_eager = (float(x) for x in t.cpu())
     if rank == 0:
         peaks = measured_peaks()
         value = world * B * K / (ms / 1e3)
@@ -337,12 +358,14 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
                            "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel)") + " + OneCycleLR, fp32 master weights", "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
-                           "last_loss": last, "host_enqueue_ms_per_step": cpu_enqueue_ms},
+                           "last_loss": last, "host_enqueue_ms_per_step": cpu_enqueue_ms,
+                           "cuda_graphs": {"enabled": use_graphs, "variants_captured": n_graphs, "replays": trainer._graphed.replays if use_graphs else 0}},
                 "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                              "traffic": None, "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of the timed steps)",
-                             "peak_source": peaks["src"] + " sustained bf16", "gemm_share_of_step": gemm_ms / ms if ms else None,
+                             "peak_source": peaks["src"] + " sustained bf16", "gemm_share_of_step": gemm_ms / ms_eager if ms_eager else None,
+                             "measured_in": "eager pass of the same K steps, CUDA-event pair per GEMM launch", "eager_ms_per_step": ms_eager / K,
                              "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peaks["tflops"]},
                 "clocks": clk}
         if cpu is not None:
@@ -368,6 +391,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
+    ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying whole-step CUDA graphs")
+    ap.add_argument("--no-graph-comm", action="store_true", help="N > 1: keep steps with NCCL all-reduces eager")
     ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -172,8 +172,10 @@ int tribe_subject_bias_grad(const void* dy_bf16, const int64_t* subjects, float*
                             int64_t n_subjects, void* stream);
 
 /* max(subjects) >= n_subjects check of SubjectLayers.forward (common.py:53-55) without a host sync on the hot path:
- * writes 1 into *flag_out (device int32) when violated. */
-int tribe_check_subjects(const int64_t* subjects, int64_t n, int64_t n_subjects, int32_t* flag_out, void* stream);
+ * writes 1 into *flag_out (device int32) when violated (never clears it: the flag is sticky).  clamped_out (optional,
+ * int64[n]) receives the ids clamped into [0, n_subjects): when the host examines the flag one step late (training
+ * loops, CUDA-graph replays) the gathers of the already enqueued step stay inside the weight tensors. */
+int tribe_check_subjects(const int64_t* subjects, int64_t n, int64_t n_subjects, int32_t* flag_out, int64_t* clamped_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Loss / evaluation reductions
@@ -221,6 +223,12 @@ int tribe_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* strea
  */
 int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int64_t step, void* stream);
+/* The same step with its scalars read from DEVICE memory — hyper[6] = {beta1, beta2, lr / (1 - beta1^step),
+ * 1 / sqrt(1 - beta2^step), eps, weight_decay} — so that a captured CUDA graph of the whole train step replays with the
+ * scheduler's current lr / momentum (OneCycleLR cycles both per batch).  tribe_adam_hyper fills such a block from the
+ * host-side values (one 1-block launch; the bias corrections are computed in fp64 on the host like torch does). */
+int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, void* stream);
+int tribe_adam_hyper(float* hyper_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ def modality_latents(model, batch, modality: str) -> torch.Tensor:
     data = batch.data[modality]
     needs_grad = torch.is_grad_enabled() and model.contrastive_heads[modality].weight.requires_grad
     if needs_grad:
-        return _HeadFn.apply(model.contrastive_heads[modality].weight, model, data, modality)
+        return _HeadFn.apply(model._anchor(), model, data, modality)  # fresh leaf, see FmriEncoder._anchor
 
     class _Ctx:  # no-grad path reuses the forward body
         pass

@@ -72,6 +72,7 @@ class GraphedTrainStep:
                 assert not leftover, "train step consumed fewer dropout draws than were drawn ahead"
         if entry == "seen":
             entry = self.cache[key] = self._capture(batch, masks)
+        model.last_dropped = list(masks[-1])  # what the eager path leaves behind after its last aggregate_features call
         return self._replay(entry)
 
     def warm(self, batches) -> int:

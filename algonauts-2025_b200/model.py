@@ -319,7 +319,10 @@ class FmriEncoder(nn.Module):
         return subj
 
     def _anchor(self):
-        return self.time_pos_embed
+        # What makes the output of ``_Fn`` require grad.  A FRESH leaf per call (not a parameter): autograd caches a
+        # leaf's AccumulateGrad node together with the stream it was created on for as long as any old graph is alive,
+        # and running that node during a CUDA-graph capture would tie the capture to uncaptured work on that stream.
+        return torch.empty(0, device=self._engine.device, requires_grad=True)
 
     def _run(self, batch, *, mode, pool=True, x_in=None):
         eng = self._engine

@@ -26,10 +26,18 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_DEBUG_CAPTURE = bool(int(__import__("os").environ.get("TRIBE_DEBUG_CAPTURE", "0")))
+
+
 def _run(name, *args):
     rc = getattr(_lib.load(), name)(*args)
     if rc:
         check(rc, name)
+    if _DEBUG_CAPTURE:  # bisecting a broken CUDA-graph capture: the stream status turns into an error right after the culprit
+        try:
+            torch.cuda.is_current_stream_capturing()
+        except Exception as e:  # noqa: BLE001
+            raise TribeError(f"capture invalid after {name}: {e}") from e
 
 
 def _need(t, dtype, name):
@@ -112,7 +120,10 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
         g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     log = GEMM_LOG
     if log is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # inside a CUDA-graph capture the pair becomes event-record NODES (external events): every replay re-records
+        # them, so per-launch durations can be read after a replay of the whole step
+        ext = torch.cuda.is_current_stream_capturing()
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
     if probe is None:
         _run("tribe_gemm_bf16", ctypes.byref(g), _stream())

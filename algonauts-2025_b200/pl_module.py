@@ -29,10 +29,12 @@ except Exception:  # noqa: BLE001
             self.trainer = types.SimpleNamespace(estimated_stepping_batches=1000)
 
         def log(self, name, value, **kwargs):
-            self.logged[name] = value
+            # like Lightning's logger connector: keep the value, not its autograd graph (and the workspaces it pins)
+            self.logged[name] = value.detach() if torch.is_tensor(value) else value
 
         def log_dict(self, d, **kwargs):
-            self.logged.update(d)
+            for name, value in d.items():
+                self.log(name, value)
 
         def on_validation_epoch_end(self) -> None:
             return None

@@ -143,8 +143,8 @@ _SIGS = {
     "tribe_nce_loss": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp],
     "tribe_nce_grad": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp],
     "tribe_cast_bf16_f32": [c_vp, c_vp, c_i64, c_vp],
-    "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
-    "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_i32, c_vp],
+    "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
     "tribe_adam_hyper": [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["tribe_last_error", "tribe_abi_version", "tribe_launch_count"])

@@ -393,6 +393,16 @@ class Engine:
             touched.append(name)
             return g
 
+        def publish():
+            # hand the finished gradients to autograd's view of the parameters (p.grad = view of the flat buffer);
+            # done bucket by bucket so that an overlapped all-reduce / optimizer step can consume a finished layer
+            # while the backward of earlier layers is still running
+            while touched:
+                n = touched.pop()
+                p = fl.params[n]
+                if p.grad is None:
+                    p.grad = fl.gview(n)
+
         dx_cur, dx_nxt = ws.dx[0], ws.dx[1]
         dxb_cur, dxb_nxt = ws.dxb[0], ws.dxb[1]
         gfin = tgt("encoder.final_norm.g")
@@ -502,6 +512,7 @@ class Engine:
                              dx_nxt, dxb_nxt, gs[f"{a}.2.residual_scale"], gs[f"{a}.0.0.g"])
             dx_cur, dx_nxt, dxb_cur, dxb_nxt = dx_nxt, dx_cur, dxb_nxt, dxb_cur
             if self.comm is not None:
+                publish()
                 self.comm.bucket_ready(l + 1)
 
         # ---- encoder input: positional embedding, projectors
@@ -529,10 +540,7 @@ class Engine:
                 a_op = ops.Operand(dxb_cur, inner=H, rows=M, row_stride=H, mn_major=True, inner_off=col)
                 self._wgrad(a_op, ops.mnmajor(ws.feat[mod]), wn, width, K, M, acc[wn])
                 ops.colsum(dx_cur[:, col: col + width], gb, accumulate=acc[bn])
-        for n in touched:
-            p = fl.params[n]
-            if p.grad is None:
-                p.grad = fl.gview(n)
+        publish()
         if self.comm is not None:
             self.comm.bucket_ready(0)
         dx_ret = dx_cur.view(B, T, H).clone() if want_dx_in else None

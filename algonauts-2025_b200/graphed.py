@@ -41,7 +41,10 @@ class GraphedTrainStep:
         if model is None or not hasattr(model, "_draw_dropout") or not isinstance(tr.optimizer, TribeAdam):
             return False
         if tr.grad_sync is not None and not tr.graph_collectives:
-            return False
+            from .parallel import world
+
+            if world()[1] > 1:  # NCCL all-reduces inside the step: captured only when asked to
+                return False
         return all(torch.is_tensor(v) and v.is_cuda for v in batch.data.values())
 
     @staticmethod

@@ -104,7 +104,7 @@ class TribeAdam(torch.optim.Adam):
         parts = name.split(".")
         return ".".join(parts[:2]) if parts[0] in ("projectors", "contrastive_heads") else "core"
 
-    def _plan_runs(self, flat, split: bool, only=None):
+    def _plan_runs(self, flat, split: bool, only=None, exclude=()):
         """Contiguous [lo, hi) ranges of the flat buffer to update: adjacent parameters with a gradient, the same
         param group and the same step count (and, with ``split``, the same run class) share one launch.  ``only``:
         optional (lo, hi) window of the flat buffer (one gradient bucket)."""
@@ -117,6 +117,8 @@ class TribeAdam(torch.optim.Adam):
                 name = name_of[id(p)]
                 off = flat.offsets[name]
                 if only is not None and not (only[0] <= off < only[1]):
+                    continue
+                if any(lo <= off < hi for lo, hi in exclude):
                     continue
                 st = self._ensure_state(flat, p, off)
                 if p.grad.data_ptr() != flat.grad.data_ptr() + 4 * off:  # foreign gradient tensor: bring it into the flat buffer
@@ -133,7 +135,7 @@ class TribeAdam(torch.optim.Adam):
                 runs.append({"lo": lo, "hi": hi, "k": k, "group": gi, "cls": cls_, "params": [p]})
         return runs
 
-    def _launch(self, flat, run, k, stream, device_hyper: bool):
+    def _launch(self, flat, run, k, stream, device_hyper: bool, max_blocks: int = 0):
         lib = _lib.load()
         group = self.param_groups[run["group"]]
         lr = float(group["lr"])
@@ -145,9 +147,9 @@ class TribeAdam(torch.optim.Adam):
                 ctypes.c_void_p(flat.bf16.data_ptr() + 2 * lo))
         if device_hyper:
             slot = flat.adam_slot.setdefault(lo, len(flat.adam_slot))
-            check(lib.tribe_adam_step_dev(*ptrs, n, ctypes.c_void_p(flat.adam_hyper[slot].data_ptr()), stream), "tribe_adam_step_dev")
+            check(lib.tribe_adam_step_dev(*ptrs, n, ctypes.c_void_p(flat.adam_hyper[slot].data_ptr()), max_blocks, stream), "tribe_adam_step_dev")
         else:
-            check(lib.tribe_adam_step(*ptrs, n, lr, beta1, beta2, eps, wd, k, stream), "tribe_adam_step")
+            check(lib.tribe_adam_step(*ptrs, n, lr, beta1, beta2, eps, wd, k, max_blocks, stream), "tribe_adam_step")
 
     # ------------------------------------------------------------------------------------------------ CUDA-graph protocol
     def graph_begin(self) -> None:
@@ -183,6 +185,32 @@ class TribeAdam(torch.optim.Adam):
         flat._sig = (sum(p._version for p in flat.params.values()), flat.opt_steps)
 
     # ------------------------------------------------------------------------------------------------ step
+    def _apply_runs(self, flat, runs, capturing, stream, max_blocks):
+        for run in runs:
+            if capturing:
+                self._launch(flat, run, 0, stream, device_hyper=True, max_blocks=max_blocks)
+                self._graph_runs.append(run)
+            else:
+                for p in run["params"]:
+                    self.state[p]["step"] += 1
+                self._launch(flat, run, run["k"] + 1, stream, device_hyper=False, max_blocks=max_blocks)
+
+    @torch.no_grad()
+    def step_bucket(self, lo_hi, max_blocks: int = 0) -> None:
+        """The optimizer step of the parameters inside one gradient bucket [lo, hi) of the flat buffer, on the CURRENT
+        stream (parallel.StepOverlap calls this behind the backward pass); the following ``step()`` skips them.
+        ``max_blocks`` bounds the grid so the kernel shares the SMs with the backward GEMMs instead of displacing them."""
+        flat = self._flat()
+        if not self._fusable(flat):
+            return  # step() will do everything
+        self._buffers(flat)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing and getattr(self, "_graph_runs", None) is None:
+            raise _lib.TribeError("TribeAdam.step_bucket() inside a CUDA graph capture needs graph_begin()")
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._apply_runs(flat, self._plan_runs(flat, split=capturing, only=lo_hi), capturing, stream, max_blocks)
+        self._early = (getattr(self, "_early", None) or []) + [tuple(lo_hi)]
+
     @torch.no_grad()
     def step(self, closure=None):
         flat = self._flat()
@@ -197,17 +225,8 @@ class TribeAdam(torch.optim.Adam):
         capturing = torch.cuda.is_current_stream_capturing()
         if capturing and getattr(self, "_graph_runs", None) is None:
             raise _lib.TribeError("TribeAdam.step() inside a CUDA graph capture needs graph_begin() (see graphed.GraphedTrainStep)")
-        done = getattr(self, "_early", None)  # buckets already stepped inside the backward (overlap mode)
-        for run in self._plan_runs(flat, split=capturing):
-            if done and any(lo <= run["lo"] < hi for lo, hi in done):
-                continue
-            if capturing:
-                self._launch(flat, run, 0, stream, device_hyper=True)
-                self._graph_runs.append(run)
-            else:
-                for p in run["params"]:
-                    self.state[p]["step"] += 1
-                self._launch(flat, run, run["k"] + 1, stream, device_hyper=False)
+        early = getattr(self, "_early", None) or ()  # buckets already stepped behind the backward (StepOverlap)
+        self._apply_runs(flat, self._plan_runs(flat, split=capturing, exclude=early), capturing, stream, 0)
         self._early = None
         # the shadow weights are already current for the state the post-step hook is about to announce
         flat._sig = (sum(p._version for p in flat.params.values()), flat.opt_steps + 1)

@@ -28,14 +28,25 @@ def default_optimizer(params, total_steps: int, lr: float = 1e-4, model=None, fu
 class MiniTrainer:
     """``use_graphs=True``: steady-state steps are replayed as whole-step CUDA graphs (``graphed.GraphedTrainStep``);
     results are identical to the eager path (same kernels, same RNG draws), only the host enqueue cost disappears.
-    ``graph_collectives``: also capture the NCCL gradient all-reduces of ``grad_sync`` (data-parallel runs)."""
+    ``graph_collectives``: also capture the NCCL gradient all-reduces of ``grad_sync`` (data-parallel runs).
+    ``overlap_optimizer``: run the optimizer layer by layer behind the backward pass (``parallel.StepOverlap``)."""
 
-    def __init__(self, module, optimizer, scheduler=None, grad_sync=None, use_graphs: bool = False, graph_collectives: bool = True):
+    def __init__(self, module, optimizer, scheduler=None, grad_sync=None, use_graphs: bool = False, graph_collectives: bool = True,
+                 overlap_optimizer: bool = False):
         self.module, self.optimizer, self.scheduler, self.grad_sync = module, optimizer, scheduler, grad_sync
         self.global_step = 0
         self.graph_collectives = graph_collectives
         self._graphed = None
         model = getattr(module, "model", None)
+        if overlap_optimizer and model is not None and hasattr(optimizer, "step_bucket"):
+            # each encoder layer's Adam step runs on a side stream as soon as that layer's gradients are final
+            # (after their all-reduce in data-parallel runs), hidden behind the backward of the earlier layers
+            from .parallel import StepOverlap
+
+            if self.grad_sync is None:
+                self.grad_sync = StepOverlap(model, optimizer=optimizer)
+            else:
+                self.grad_sync.optimizer = optimizer
         if model is not None and hasattr(model, "defer_subject_check"):
             model.defer_subject_check = True  # no host sync inside the step; raised one call later (see model.py)
         if use_graphs:

@@ -260,11 +260,11 @@ def run_ours(args):
     opt, sched = default_optimizer(model.parameters(), total_steps=4 * (K + W) + 16, model=None if args.stock_adam else model)
     sync = parallel.GradAllReduce(model) if world > 1 else None
     use_graphs = not args.eager and not args.stock_adam
-    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=not args.no_graph_comm)
-    if sync is not None:
-        passes, heads = (2, 1) if contrastive else (1, 0)
-        orig_begin = sync.begin_step
-        sync.begin_step = lambda: orig_begin(passes, heads)
+    # measured on B200 (profiles/r01_adam_overlap_ab.txt): the step is power-capped, so moving Adam's 28 GB of HBM
+    # traffic beside the GEMMs lowers their clocks by as much as it saves — off by default
+    overlap = args.overlap and not args.stock_adam
+    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=not args.no_graph_comm,
+                          overlap_optimizer=overlap)
 
     # two distinct host batches (pinned) alternate through the two persistent device slots of a DevicePrefetcher;
     # 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
@@ -376,7 +376,8 @@ def run_ours(args):
         line = {"metric": "train windows/s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
-                           "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel)") + " + OneCycleLR, fp32 master weights", "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
+                           "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel)") + " + OneCycleLR, fp32 master weights",
+                           "optimizer_overlap": overlap, "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
                            "last_loss": last, "host_enqueue_ms_per_step": cpu_enqueue_ms,
                            "cuda_graphs": {"enabled": use_graphs, "variants_captured": n_graphs, "replays": trainer._graphed.replays if use_graphs else 0}},
                 "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -413,6 +414,7 @@ def main():
     ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying whole-step CUDA graphs")
     ap.add_argument("--no-graph-comm", action="store_true", help="N > 1: keep steps with NCCL all-reduces eager")
+    ap.add_argument("--overlap", action="store_true", help="run each layer's Adam step behind the backward (parallel.StepOverlap) instead of after it")
     ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")
     args = ap.parse_args()
     if args.impl == "reference":

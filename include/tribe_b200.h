@@ -219,15 +219,17 @@ int tribe_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* strea
 /* ------------------------------------------------------------------------------------------------------------------
  * Optimizer: one fused torch.optim.Adam step (amsgrad=False, maximize=False; recipe algonauts2025/grids/defaults.py:
  * 126-141) over a flat fp32 range, writing the bf16 shadow weights in the same pass (p_bf16 may be NULL).
- * `step` is the 1-based step count used for the bias corrections.
+ * `step` is the 1-based step count used for the bias corrections.  max_blocks > 0 bounds the grid (a step that runs
+ * beside the backward GEMMs on a side stream should leave SM slots to them); 0 = fill the device.
  */
 int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int64_t step, void* stream);
+                    float weight_decay, int64_t step, int32_t max_blocks, void* stream);
 /* The same step with its scalars read from DEVICE memory — hyper[6] = {beta1, beta2, lr / (1 - beta1^step),
  * 1 / sqrt(1 - beta2^step), eps, weight_decay} — so that a captured CUDA graph of the whole train step replays with the
  * scheduler's current lr / momentum (OneCycleLR cycles both per batch).  tribe_adam_hyper fills such a block from the
  * host-side values (one 1-block launch; the bias corrections are computed in fp64 on the host like torch does). */
-int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, void* stream);
+int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, int32_t max_blocks,
+                        void* stream);
 int tribe_adam_hyper(float* hyper_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
 #ifdef __cplusplus

@@ -17,14 +17,14 @@ SMALL_DIMS = {"text": (2, 96), "audio": (2, 40), "video": (1, 72)}
 SMALL = dict(hidden=384, depth=2, heads=6)
 
 
-def _run(use_graphs: bool, contrastive: bool, steps: int, p_drop: float = 0.4, slots: int = 2):
+def _run(use_graphs: bool, contrastive: bool, steps: int, p_drop: float = 0.4, slots: int = 2, overlap: bool = False):
     torch.manual_seed(21)
     np.random.seed(21)
     cfg = FmriEncoderConfig(n_subjects=3, modality_dropout=p_drop, contrastive_enabled=contrastive)
     model = FmriEncoder(SMALL_DIMS, 200, 25, cfg, **SMALL)
     module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=1)
     opt, sched = default_optimizer(model.parameters(), total_steps=steps + 4, lr=3e-3, model=model)
-    trainer = MiniTrainer(module, opt, sched, use_graphs=use_graphs)
+    trainer = MiniTrainer(module, opt, sched, use_graphs=use_graphs, overlap_optimizer=overlap)
     spec = tuple((k, v[0], v[1]) for k, v in SMALL_DIMS.items())
     host = [synthetic_batch(batch_size=3, t=74, t_out=25, n_outputs=200, n_subjects=3, seed=70 + i, dims=spec) for i in range(2)]
     dev = [SegmentData(data={k: v.cuda() for k, v in b.data.items()}, segments=b.segments) for b in host]  # two fixed device slots
@@ -68,6 +68,28 @@ def test_graphed_steps_equal_eager_steps(contrastive):
     for k, v in eager["state"].items():
         n_k = float((eager2["state"][k].float() - v.float()).abs().max())
         d_k = float((graphed["state"][k].float() - v.float()).abs().max())
+        assert d_k <= max(4.0 * n_k, 5e-4 + 5e-3 * float(v.float().abs().max())), (k, d_k, n_k)
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+@pytest.mark.parametrize("contrastive", [False, True])
+def test_optimizer_overlapped_with_backward_equals_plain_step(use_graphs, contrastive):
+    """parallel.StepOverlap: each layer's Adam launch moves behind the backward (side stream); same arithmetic, same
+    step counts, same skipped projectors — also when the whole step is a replayed graph (forked capture streams)."""
+    steps, kw = (20, {}) if not contrastive else (30, dict(p_drop=0.25, slots=1))
+    plain = _run(False, contrastive, steps, **kw)
+    plain2 = _run(False, contrastive, steps, **kw)
+    over = _run(use_graphs, contrastive, steps, overlap=True, **kw)
+    assert over["trainer"].grad_sync is not None and over["trainer"].grad_sync.opt_stream is not None
+    assert plain["masks"] == over["masks"] and plain["none_grads"] == over["none_grads"] and plain["lr"] == over["lr"]
+    for n, k in plain["steps_of"].items():
+        assert over["steps_of"][n] == k, n
+    noise = float((plain2["losses"] - plain["losses"]).abs().max())
+    diff = float((over["losses"] - plain["losses"]).abs().max())
+    assert diff <= max(4.0 * noise, 2e-4 * float(plain["losses"].abs().max())), (diff, noise)
+    for k, v in plain["state"].items():
+        n_k = float((plain2["state"][k].float() - v.float()).abs().max())
+        d_k = float((over["state"][k].float() - v.float()).abs().max())
         assert d_k <= max(4.0 * n_k, 5e-4 + 5e-3 * float(v.float().abs().max())), (k, d_k, n_k)
 
 

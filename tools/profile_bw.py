@@ -32,6 +32,6 @@ for _ in range(2):
     ops.pearson_stats(pred, true, stats, layout="no")
     ops.ingest_features(feats, fout, 0, False)
     lib.tribe_adam_step(ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(gr.data_ptr()), ctypes.c_void_p(m.data_ptr()), ctypes.c_void_p(v.data_ptr()),
-                        ctypes.c_void_p(p16.data_ptr()), n, 1e-4, 0.9, 0.999, 1e-8, 0.0, 3, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                        ctypes.c_void_p(p16.data_ptr()), n, 1e-4, 0.9, 0.999, 1e-8, 0.0, 3, 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 print("ok")

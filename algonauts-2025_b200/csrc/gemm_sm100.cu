@@ -371,6 +371,12 @@ static int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    // TRIBE_GEMM_SMS=<k>: persistent workers use at most k SMs (leave the rest to concurrently running collectives,
+    // whose CTAs would otherwise delay the one-CTA-per-SM grid by a whole kernel)
+    if (const char* e = getenv("TRIBE_GEMM_SMS")) {
+      const int v = atoi(e);
+      if (v >= 2 && v < n) n = v & ~1;
+    }
   }
   return n;
 }

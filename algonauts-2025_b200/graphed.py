@@ -117,7 +117,8 @@ class GraphedTrainStep:
         launches0 = int(lib.tribe_launch_count())
         opt.graph_begin()
         try:
-            with torch.cuda.graph(graph):
+            # thread_local: helper threads (NCCL watchdog, pin-memory, samplers) may keep calling the CUDA runtime
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 loss = tr.run_step_body(batch)
         finally:
             runs = opt.graph_end()

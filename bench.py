@@ -59,9 +59,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float | None = None, t1: float | None = None):
+        """Median SM clock and throttle reasons of the samples that arrived inside [t0, t1] (perf_counter; the timed
+        region), or of every sample taken under load when the window caught none."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -69,8 +71,12 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+        inside = [ln for t, ln in self.lines if t0 is None or (t0 <= t <= (t1 if t1 is not None else t))]
+        window = "timed region"
+        if not inside:
+            inside, window = [ln for _, ln in self.lines], "whole loaded run (timed region shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -82,7 +88,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def algorithmic_flops_per_window(contrastive: bool) -> float:
@@ -259,11 +265,12 @@ def run_ours(args):
     # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
     opt, sched = default_optimizer(model.parameters(), total_steps=4 * (K + W) + 16, model=None if args.stock_adam else model)
     sync = parallel.GradAllReduce(model) if world > 1 else None
-    use_graphs = not args.eager and not args.stock_adam
+    # whole-step CUDA graphs; with N > 1 the step contains NCCL all-reduces, which are only captured on request
+    use_graphs = not args.eager and not args.stock_adam and (world == 1 or args.graph_comm)
     # measured on B200 (profiles/r01_adam_overlap_ab.txt): the step is power-capped, so moving Adam's 28 GB of HBM
     # traffic beside the GEMMs lowers their clocks by as much as it saves — off by default
     overlap = args.overlap and not args.stock_adam
-    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=not args.no_graph_comm,
+    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=args.graph_comm,
                           overlap_optimizer=overlap)
 
     # two distinct host batches (pinned) alternate through the two persistent device slots of a DevicePrefetcher;
@@ -279,6 +286,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.start()  # nvidia-smi needs a few hundred ms to deliver its first sample: start ahead of the timed region
     for i in range(W):
         trainer.eager_step(dev[i % 2])
     barrier()
@@ -292,8 +301,6 @@ def run_ours(args):
         barrier()
 
     # ---- timed region 1: device-resident inputs
-    clocks = ClockSampler(local)
-    clocks.start()
     launches0 = algonauts2025_b200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -304,7 +311,7 @@ def run_ours(args):
     cpu_enqueue_ms = 1e3 * (time.perf_counter() - t_cpu) / K  # host time to enqueue one step (no sync inside the loop)
     e1.record()
     barrier()
-    clk = clocks.stop()
+    t_end = time.perf_counter()
     launches = algonauts2025_b200.launch_count() - launches0
     ms = e0.elapsed_time(e1)
 
@@ -322,6 +329,7 @@ def run_ours(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop(t_cpu, t_end)
 
     # ---- roofline pass: K more steps with a CUDA-event pair around every tcgen05 GEMM launch.  With graphs the pairs
     # are captured as event-record nodes of an instrumented copy of the (no-modality-dropped) step graph and read back
@@ -399,6 +407,13 @@ def run_ours(args):
             line["pearson_eval"] = pe
         print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()
+        if use_graphs:
+            # CUDA graphs that captured NCCL collectives keep the communicator busy: destroy_process_group() blocks on
+            # them (seen on 2 x B200).  The result is printed and every rank has passed the barrier — leave directly.
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -413,10 +428,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying whole-step CUDA graphs")
-    ap.add_argument("--no-graph-comm", action="store_true", help="N > 1: keep steps with NCCL all-reduces eager")
+    ap.add_argument("--graph-comm", action="store_true", help="N > 1: capture the steps including their NCCL all-reduces (default: eager steps)")
+    ap.add_argument("--watchdog", type=int, default=1500, help="dump all thread stacks and exit if the run takes longer than this many seconds (0 = off)")
     ap.add_argument("--overlap", action="store_true", help="run each layer's Adam step behind the backward (parallel.StepOverlap) instead of after it")
     ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

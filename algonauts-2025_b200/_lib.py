@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(CSRC, "libtribe_b200.so")
-SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu", "contrastive.cu", "pool.cu", "optim.cu"]
+SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu", "contrastive.cu", "pool.cu", "optim.cu", "losses.cu", "aux.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               f"-I{INCLUDE}", f"-I{CSRC}"]
 
@@ -146,6 +146,15 @@ _SIGS = {
     "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_i32, c_vp],
     "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
     "tribe_adam_hyper": [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
+    "tribe_point_loss_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp, c_vp],
+    "tribe_pearson_loss_finalize": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp],
+    "tribe_pearson_loss_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "tribe_gather_windows": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "tribe_ensemble_weights": [c_vp, c_i64, c_i64, c_f32, c_i32, c_vp, c_vp],
+    "tribe_ensemble_average": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp],
+    "tribe_mean_lastdim": [c_vp, c_vp, c_i64, c_i64, c_vp],
+    "tribe_retrieval_ranks": [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
+    "tribe_swa_update": [c_vp, c_vp, c_i64, c_i64, c_vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["tribe_last_error", "tribe_abi_version", "tribe_launch_count"])
 

@@ -185,3 +185,93 @@ def pearson_from_host(preds: torch.Tensor, trues: torch.Tensor, chunk_windows: i
         free[s].record(main)
     r, _ = ops.pearson_finalize(stats[0])
     return r.cpu().numpy().astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ retrieval (§8f row 2)
+class Rank(nn.Module):
+    """Mirror of ``modeling_utils.metrics.metrics.Rank`` (metrics.py:66-168) for the unlabeled use of the TRIBE path
+    (``x_labels`` / ``y_labels`` None: the true candidate of query b is row b): rank of the true target among the
+    cosine-normalised scores, ties averaged.  State ``ranks`` is concatenated over updates (and over ranks on compute)."""
+
+    is_differentiable = False
+    higher_is_better = False
+
+    def __init__(self, reduction: str = "median", relative: bool = False) -> None:
+        super().__init__()
+        self.reduction = reduction
+        self.relative = relative
+        self._ranks: list[torch.Tensor] = []
+
+    @property
+    def ranks(self) -> torch.Tensor:
+        if not self._ranks:
+            return torch.zeros(0)
+        return torch.cat(self._ranks)
+
+    @torch.no_grad()
+    def update(self, x: torch.Tensor, y: torch.Tensor, x_labels=None, y_labels=None) -> None:
+        if x_labels is not None or y_labels is not None:
+            raise NotImplementedError("labeled retrieval is not on the TRIBE path (pl_module.py:100-101 passes no labels)")
+        if not x.is_cuda:
+            raise TribeError("retrieval metric needs CUDA tensors (no CPU fallback)")
+        assert x.shape[0] == y.shape[0]
+        r, _ = ops.retrieval_ranks(x.detach().float().contiguous(), y.detach().to(x.device).float().contiguous())
+        if self.relative:
+            r = r / y.shape[0]
+        self._ranks.append(r)
+
+    @torch.no_grad()
+    def update_bdt(self, preds: torch.Tensor, target: torch.Tensor) -> None:
+        """``update(preds.mean(-1), target.mean(-1))`` of pl_module.py:100-101 with the time average in our kernel."""
+        if not preds.is_cuda:
+            raise TribeError("retrieval metric needs CUDA tensors (no CPU fallback)")
+        self.update(ops.mean_lastdim(preds.detach().float().contiguous()), ops.mean_lastdim(target.detach().to(preds.device).float().contiguous()))
+
+    def _gathered(self) -> torch.Tensor:
+        r = self.ranks
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:  # dist_reduce_fx="cat"
+            ws = dist.get_world_size()
+            dev = r.device if r.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            n = torch.tensor([r.numel()], device=dev)
+            sizes = [torch.zeros_like(n) for _ in range(ws)]
+            dist.all_gather(sizes, n)
+            width = int(max(s.item() for s in sizes))
+            mine = torch.zeros(width, device=dev)
+            mine[: r.numel()] = r.to(dev)
+            parts = [torch.empty_like(mine) for _ in range(ws)]
+            dist.all_gather(parts, mine)
+            r = torch.cat([p[: int(s.item())] for p, s in zip(parts, sizes)])
+        return r
+
+    def compute(self) -> torch.Tensor:
+        r = self._gathered()
+        if self.reduction == "mean":
+            return torch.mean(r)
+        if self.reduction == "median":
+            return torch.median(r)
+        if self.reduction == "std":
+            return torch.std(r)
+        raise ValueError(f'Unknown aggregation {self.reduction} for computing metric. Available aggregations are: "mean", "median" or "std".')
+
+    def reset(self) -> None:
+        self._ranks = []
+
+    def forward(self, x, y):
+        self.update(x, y)
+        return self.compute()
+
+
+class TopkAcc(Rank):
+    """``modeling_utils.metrics.metrics.TopkAcc`` (metrics.py:194-218): share of queries whose true target is ranked in the
+    top k — the ``val/retrieval_top1`` metric of algonauts2025/grids/defaults.py:119-123 (topk=1)."""
+
+    higher_is_better = True
+
+    def __init__(self, topk: int = 5) -> None:
+        super().__init__(relative=False)
+        self.topk = topk
+
+    def compute(self) -> torch.Tensor:
+        return (self._gathered() < self.topk).float().mean()

@@ -312,3 +312,87 @@ def nce_loss(logits, n, shift, row_sum, col_sum, loss) -> None:
 def nce_grad(logits, n, shift, row_sum, col_sum, upstream, scale, g) -> None:
     _run("tribe_nce_grad", _ptr(logits), n, logits.stride(0), shift, _ptr(row_sum), _ptr(col_sum), _ptr(upstream), scale, _ptr(g),
                                      g.stride(0), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- alternative losses
+LOSS_SMOOTH_L1, LOSS_HUBER, LOSS_L1 = 1, 2, 3
+
+
+def point_loss_fwd_bwd(pred, target, kind: int, param: float, want_grad=True, grad_scale=1.0):
+    """SmoothL1 / Huber / L1 with reduction="mean": loss[1] fp32 (+ gradient wrt pred in the same pass)."""
+    _need(pred, torch.float32, "loss pred"), _need(target, torch.float32, "loss target")
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if want_grad else None
+    partial = torch.empty(1024, device=pred.device, dtype=torch.float64)
+    _run("tribe_point_loss_fwd_bwd", _ptr(pred), _ptr(target), _ptr(loss), _ptr(grad), kind, float(param), grad_scale, pred.numel(),
+         _ptr(partial), _stream())
+    return loss, grad
+
+
+def pearson_loss_fwd(pred, target, *, layout: str, reduction_mean: bool = True, want_coef: bool = True):
+    """PearsonLoss(dim=1) forward on (N, O) ("no") or (B, O, T) ("bdt") tensors -> (loss[1], coef (4, O) or None)."""
+    o = pred.shape[1]
+    stats = torch.zeros(1, 6, o, device=pred.device, dtype=torch.float64)
+    pearson_stats(pred, target, stats, layout=layout)
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    coef = torch.empty(4, o, device=pred.device, dtype=torch.float32) if want_coef else None
+    _run("tribe_pearson_loss_finalize", _ptr(stats), o, int(reduction_mean), _ptr(coef), _ptr(loss), _stream())
+    return loss, coef
+
+
+def pearson_loss_bwd(pred, target, coef, upstream, *, layout: str, reduction_mean: bool = True):
+    _need(pred, torch.float32, "pearson loss pred"), _need(target, torch.float32, "pearson loss target")
+    grad = torch.empty_like(pred)
+    t_len = 1 if layout == "no" else pred.shape[2]
+    _run("tribe_pearson_loss_bwd", _ptr(pred), _ptr(target), _ptr(coef), _ptr(upstream), int(reduction_mean), _ptr(grad), pred.numel(),
+         pred.shape[1], t_len, _stream())
+    return grad
+
+
+# ---------------------------------------------------------------------------------------------- around the path (§8f)
+def gather_windows(src_ptrs, src_dtype, t_total, dst_start, src_start, length, out) -> None:
+    """out fp32 (B, rows, T): window b <- rows x [src_start[b], +length[b]) of its timeline array, zero padded."""
+    _need(out, torch.float32, "gather_windows out")
+    n, rows, t = out.shape
+    _run("tribe_gather_windows", _ptr(src_ptrs), _DT[src_dtype], _ptr(t_total), _ptr(dst_start), _ptr(src_start), _ptr(length), _ptr(out),
+         n, rows, t, _stream())
+
+
+def ensemble_weights(r, temperature: float, axis: int = 1):
+    """r (M, O) -> softmax(r / temperature) over parcels (axis=1, the reference's behaviour) or members (axis=0)."""
+    _need(r, torch.float32, "ensemble r")
+    w = torch.empty_like(r)
+    _run("tribe_ensemble_weights", _ptr(r), r.shape[0], r.shape[1], float(temperature), int(axis), _ptr(w), _stream())
+    return w
+
+
+def ensemble_average(preds, w=None):
+    """preds (M, N, O) fp32 stacked member predictions, w (M, O) or None (plain mean) -> (N, O)."""
+    _need(preds, torch.float32, "ensemble preds")
+    m, n, o = preds.shape
+    out = torch.empty(n, o, device=preds.device, dtype=torch.float32)
+    _run("tribe_ensemble_average", _ptr(preds), _ptr(w), m, n, o, _ptr(out), _stream())
+    return out
+
+
+def mean_lastdim(x):
+    _need(x, torch.float32, "mean_lastdim x")
+    y = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
+    _run("tribe_mean_lastdim", _ptr(x), _ptr(y), y.numel(), x.shape[-1], _stream())
+    return y
+
+
+def retrieval_ranks(x, y, want_scores=False):
+    _need(x, torch.float32, "retrieval x"), _need(y, torch.float32, "retrieval y")
+    n, c = x.shape
+    if y.shape != x.shape:
+        raise TribeError("retrieval_ranks: x and y must have the same (n, c) shape")
+    ranks = torch.empty(n, device=x.device, dtype=torch.float32)
+    scores = torch.empty(n, n, device=x.device, dtype=torch.float32) if want_scores else None
+    _run("tribe_retrieval_ranks", _ptr(x), _ptr(y), n, c, _ptr(ranks), _ptr(scores), _stream())
+    return ranks, scores
+
+
+def swa_update(avg, params, n_averaged: int) -> None:
+    _need(avg, torch.float32, "swa avg"), _need(params, torch.float32, "swa params")
+    _run("tribe_swa_update", _ptr(avg), _ptr(params), avg.numel(), int(n_averaged), _stream())

@@ -181,24 +181,33 @@ def allreduced_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, gro
 
 
 # ------------------------------------------------------------------------------------------------ ensembles
-def ensemble_weights(member_r: torch.Tensor, temperature: float = 0.3) -> torch.Tensor:
-    """member_r (N, O) -> per-parcel softmax(r / tau) over members (average_submissions.py:107-125)."""
-    return torch.softmax(member_r / temperature, dim=0)
+def ensemble_weights(member_r: torch.Tensor, temperature: float = 0.3, softmax_over: str = "voxels") -> torch.Tensor:
+    """member_r (N, O) -> (N, O) weights.  ``"voxels"``: ``softmax(r / tau, dim=1)`` — the reference's arithmetic
+    (average_submissions.py:108-109 normalises every member's weights over the voxel axis); ``"members"``: softmax over the
+    members per parcel (a convex combination per parcel)."""
+    return torch.softmax(member_r / temperature, dim=1 if softmax_over == "voxels" else 0)
 
 
-def ensemble_average(pred_member: torch.Tensor, r_member: torch.Tensor, temperature: float = 0.3, group=None) -> torch.Tensor:
+def ensemble_average(pred_member: torch.Tensor, r_member: torch.Tensor, temperature: float = 0.3, group=None,
+                     softmax_over: str = "voxels") -> torch.Tensor:
     """One member per rank: pred_member (..., O, T) or (N_rows, O) predictions of THIS rank's model on the shared
-    evaluation set, r_member (O,) its per-parcel validation Pearson.  Returns the softmax-weighted ensemble
-    prediction (identical on every rank): all-gather of r (O floats per rank) + one all-reduce of the predictions."""
+    evaluation set, r_member (O,) its per-parcel validation Pearson.  Returns the weighted ensemble prediction (identical
+    on every rank): [all-gather of r (O floats per rank) when the weights are normalised over members] + one all-reduce
+    of the weighted predictions."""
     rank, ws = world()
-    if ws == 1:
-        return pred_member
-    rs = [torch.empty_like(r_member) for _ in range(ws)]
-    dist.all_gather(rs, r_member.contiguous(), group=group)
-    w = ensemble_weights(torch.stack(rs), temperature)[rank]  # (O,)
+    if softmax_over == "voxels":
+        w = ensemble_weights(r_member[None, :], temperature, "voxels")[0]  # depends on this member's r only
+    else:
+        rs = [torch.empty_like(r_member) for _ in range(ws)]
+        if ws > 1:
+            dist.all_gather(rs, r_member.contiguous(), group=group)
+        else:
+            rs = [r_member]
+        w = ensemble_weights(torch.stack(rs), temperature, "members")[rank]  # (O,)
     parcel_dim = 1
     shape = [1] * pred_member.dim()
     shape[parcel_dim] = -1
     out = pred_member * w.view(shape)
-    dist.all_reduce(out, group=group)
+    if ws > 1:
+        dist.all_reduce(out, group=group)
     return out

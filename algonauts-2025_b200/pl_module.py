@@ -68,10 +68,10 @@ class BrainModule(_Base):
         if step_name == "val":
             y_true = y_true[:, :, 0:]
             y_pred = y_pred[:, :, 0:]
-        if L.is_plain_mse(self.loss):
-            loss = L.mse_loss(y_pred, y_true)  # fused kernel; the mean is invariant to the (b t) d rearrange
-            y_pred_flat = y_true_flat = None
-        else:
+        # the grid's losses run fused on the (B, D, T) tensors (their value is invariant to the (b t) d rearrange, or
+        # — PearsonLoss — the kernel indexes parcels in place); anything else gets the flattened matrices
+        loss = L.fused_loss(self.loss, y_pred, y_true)
+        if loss is None:
             y_pred_flat, y_true_flat = _flatten_bdt(y_pred), _flatten_bdt(y_true)
             loss = self.loss(y_pred_flat, y_true_flat)
 
@@ -100,7 +100,10 @@ class BrainModule(_Base):
                         metric.update(_flatten_bdt(yp), _flatten_bdt(yt), groups=groups)
                 else:
                     if "retrieval" in metric_name:
-                        metric.update(yp.mean(dim=-1), yt.mean(dim=-1))
+                        if hasattr(metric, "update_bdt"):
+                            metric.update_bdt(yp, yt)  # the time average is fused into the metric's kernels
+                        else:
+                            metric.update(yp.mean(dim=-1), yt.mean(dim=-1))
                     elif hasattr(metric, "update_bdt"):
                         metric.update_bdt(yp, yt)
                     else:

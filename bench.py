@@ -168,6 +168,48 @@ def cpu_pearson_baseline(n_windows: int = 256):
             "sample": f"{n_windows} windows x {EVAL_PARCELS} parcels x {EVAL_TRS} TRs through the main.py:470-476 scipy.stats.pearsonr loop"}
 
 
+def eval_predict_leg(model, rank: int, world: int, steps: int, batch: int = 64):
+    """BASELINE.json config 5, first half: eval-mode batched predict (windows sharded across ranks, no collective) feeding
+    the per-parcel Pearson statistics — ``metrics.compute_multidim_pearson`` (main.py:459-477) from pinned host batches."""
+    import torch.distributed as dist
+
+    from algonauts2025_b200 import metrics
+    from algonauts2025_b200.segment import DevicePrefetcher, synthetic_batch
+
+    host = [synthetic_batch(batch_size=batch, seed=4321 + 31 * rank + i, pin=True) for i in range(2)]
+    prefetch = DevicePrefetcher(())
+    dev = prefetch.resident(host)
+    model.eval()
+    with torch.no_grad():
+        for i in range(2):
+            model(dev[i % 2])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            y = model(dev[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t0 = time.perf_counter()
+        r = metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(steps)))
+        e2e_s = time.perf_counter() - t0
+    assert r.shape == (1000,) and y.shape == (batch, 1000, 100)
+    t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = (float(x) for x in t.cpu())
+    model.train()
+    h2d = sum(v.numel() * v.element_size() for v in host[0].data.values())
+    flops = algorithmic_flops_per_window(False) / 3.0
+    return {"metric": "eval predict windows/s", "value": world * batch * steps / (ms / 1e3), "unit": "windows/s", "ms_per_batch": ms / steps,
+            "batch_per_gpu": batch, "tflops": flops * batch * steps * world / (ms / 1e3) / 1e12 / world,
+            "e2e": {"value": world * batch * steps / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4000,
+                    "api": "metrics.compute_multidim_pearson(model, DevicePrefetcher(pinned host batches)) -> r[1000] on host"}}
+
+
 def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with_cpu: bool):
     """Per-parcel Pearson r over (windows, parcels, TRs) prediction/target tensors, parcels sharded 1000/G per rank
     (no data-path collective: shards are independent; r is gathered once at the end, outside the kernel timing)."""
@@ -399,7 +441,12 @@ def run_ours(args):
                 "clocks": clk}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    del trainer, opt, sched, module, model, dev
+    del trainer, opt, sched, module, dev
+    torch.cuda.empty_cache()
+    ev = eval_predict_leg(model, rank, world, max(K // 2, 4)) if not args.no_pearson else None
+    if rank == 0 and ev is not None:
+        line["eval_predict"] = ev
+    del model
     torch.cuda.empty_cache()
     pe = pearson_eval_leg(rank, world, max(K, 5), W, measured_peaks(), world == 1 and not args.no_cpu_baseline) if not args.no_pearson else None
     if rank == 0:

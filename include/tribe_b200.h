@@ -24,6 +24,17 @@ extern "C" {
 #define TRIBE_EDRIVER (-2)  /* CUDA driver entry point (cuTensorMapEncodeTiled) unavailable */
 #define TRIBE_ETMAP (-3)    /* tensor-map encoding failed */
 
+/* element types of `*_dtype` arguments */
+#define TRIBE_DT_F32 0
+#define TRIBE_DT_F64 1
+#define TRIBE_DT_BF16 2
+#define TRIBE_DT_F16 3
+
+/* point-wise training losses of tribe_point_loss_fwd_bwd (MSE has its own entry point) */
+#define TRIBE_LOSS_SMOOTH_L1 1 /* torch.nn.SmoothL1Loss(beta = param)  */
+#define TRIBE_LOSS_HUBER 2     /* torch.nn.HuberLoss(delta = param)    */
+#define TRIBE_LOSS_L1 3        /* torch.nn.L1Loss                      */
+
 const char* tribe_last_error(void);
 int tribe_abi_version(void);
 /* Number of kernels launched through this library since load (bench.py's `gpu_launches`). */
@@ -231,6 +242,53 @@ int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, 
 int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, int32_t max_blocks,
                         void* stream);
 int tribe_adam_hyper(float* hyper_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Alternative training losses (grid: algonauts2025/grids/run_ensemble.py:29; built by modeling_utils/losses/base.py:
+ * 43-59 from torch.nn, PearsonLoss from modeling_utils/losses/losses.py:11-42).  Same contract as tribe_mse_fwd_bwd:
+ * reduction="mean", loss_out[0] fp32, grad (optional) = grad_scale * dloss/dpred, partial >= 1024 doubles.
+ */
+int tribe_point_loss_fwd_bwd(const float* pred, const float* target, float* loss_out, float* grad, int32_t kind, float param,
+                             float grad_scale, int64_t n, double* partial, void* stream);
+/* PearsonLoss(dim=1) = reduce_p (1 - pcc_p), pcc_p = cov / (std_x std_y + 1e-8) over all rows of parcel p.
+ * Forward: tribe_pearson_stats into a ZEROED stats block, then this finalize, which writes loss_out[0] and (optional)
+ * coef fp32 [4][n_parcels] = mean_x, mean_y, 1/D, cov*std_y/(D^2 std_x) for the backward pass.
+ * Backward: grad[i] = -(upstream[0] * (reduction_mean ? 1/n_parcels : 1)) * (coef2[p] (y_i - coef1[p]) - coef3[p] (x_i - coef0[p]))
+ * with p = (i / t_len) % n_parcels over contiguous (N, O) (t_len = 1) or (B, O, T) (t_len = T) tensors; upstream is a
+ * device scalar (autograd's grad_output) or NULL for 1. */
+int tribe_pearson_loss_finalize(const double* stats, int64_t n_parcels, int32_t reduction_mean, float* coef, float* loss_out, void* stream);
+int tribe_pearson_loss_bwd(const float* pred, const float* target, const float* coef, const float* upstream, int32_t reduction_mean,
+                           float* grad, int64_t n, int64_t n_parcels, int64_t t_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The steps either side of the path.
+ */
+/* Window assembly (data_utils/base.py:167-198 TimedArray._overlap_slice / __iadd__, data_utils/segments.py:144-180):
+ * out fp32 (n_windows, rows, t_out); window b copies length[b] samples starting at src_start[b] of every row of its
+ * timeline array src_ptrs[b] (row-major (rows, t_total[b]), f32 or f64, device pointers in a device array) to columns
+ * [dst_start[b], dst_start[b] + length[b]) and zero-fills the rest.  The index triples are computed on the host with
+ * the reference's own rounding rules (windows.py) and must satisfy 0 <= src_start, src_start + length <= t_total,
+ * 0 <= dst_start, dst_start + length <= t_out. */
+int tribe_gather_windows(const void* const* src_ptrs, int32_t src_dtype, const int64_t* t_total, const int32_t* dst_start,
+                         const int32_t* src_start, const int32_t* length, float* out, int64_t n_windows, int64_t rows, int64_t t_out,
+                         void* stream);
+/* Ensemble averaging (algonauts2025/grids/average_submissions.py:107-125): weights from the members' per-parcel
+ * validation Pearson r (n_members, n_parcels): axis = 1 -> w[m, :] = softmax over PARCELS of r[m, :] / temperature, which
+ * is what the reference computes (`pearsons.softmax(dim=1)`, :108-109); axis = 0 -> softmax over MEMBERS per parcel
+ * (weights of a parcel sum to one).  out[n, p] = sum_m w[m, p] * preds[m, n, p] over stacked (n_members <= 48, n_rows,
+ * n_parcels) fp32 predictions (w == NULL: plain mean, :123). */
+int tribe_ensemble_weights(const float* r, int64_t n_members, int64_t n_parcels, float temperature, int32_t axis, float* w, void* stream);
+int tribe_ensemble_average(const float* preds, const float* w, int64_t n_members, int64_t n_rows, int64_t n_parcels, float* out,
+                           void* stream);
+/* Retrieval metric (modeling_utils/metrics/metrics.py:66-121, TopkAcc :194-218; pl_module.py:100-101 feeds it the
+ * time-averaged (B, O) predictions / targets): y[row] = mean(x[row, :t]); ranks[b] of the true candidate among
+ * scores[b, o] = <x_b, y_o> / (1e-15 + |y_o|), ties averaged, NaN comparisons false, negative -> n / 2.
+ * scores_out (optional) fp32 (n, n). */
+int tribe_mean_lastdim(const float* x, float* y, int64_t rows, int64_t t, void* stream);
+int tribe_retrieval_ranks(const float* x, const float* y, int64_t n, int64_t c, float* ranks, float* scores_out, void* stream);
+/* Stochastic weight averaging over the flat parameter buffer (algonauts2025/main.py:365-373; torch AveragedModel):
+ * avg += (params - avg) / (n_averaged + 1). */
+int tribe_swa_update(float* avg, const float* params, int64_t n, int64_t n_averaged, void* stream);
 
 #ifdef __cplusplus
 }

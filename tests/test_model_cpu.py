@@ -125,9 +125,16 @@ GLOO_WORKER = textwrap.dedent("""
     # ensemble: one member per rank
     member_pred = preds * (rank + 1)
     member_r = torch.linspace(0.0, 0.3, 13) * (rank + 1)
-    ens = parallel.ensemble_average(member_pred, member_r, 0.3)
-    want = O.ensemble_average(np.stack([preds.numpy(), 2 * preds.numpy()]), np.stack([member_r.numpy() / (rank + 1) * 1, member_r.numpy() / (rank + 1) * 2]), 0.3)
+    ens = parallel.ensemble_average(member_pred, member_r, 0.3, softmax_over="members")
+    stack_p = np.stack([preds.numpy(), 2 * preds.numpy()])
+    stack_r = np.stack([member_r.numpy() / (rank + 1) * 1, member_r.numpy() / (rank + 1) * 2])
+    want = O.ensemble_average(stack_p, stack_r, 0.3)
     np.testing.assert_allclose(ens.numpy(), want, rtol=1e-5, atol=1e-6)
+    # default = the reference's arithmetic (average_submissions.py:108-109: softmax over the voxel axis per member)
+    from oracle import aux_oracle as AO
+    ens_ref = parallel.ensemble_average(member_pred, member_r, 0.3)
+    want_ref = AO.average_members(stack_p, stack_r, weigh_by_score=True, per_voxel_weights=True, temperature=0.3)
+    np.testing.assert_allclose(ens_ref.numpy(), want_ref, rtol=1e-5, atol=1e-6)
     dist.destroy_process_group()
     print("OK", rank)
 """)

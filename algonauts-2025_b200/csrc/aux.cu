@@ -30,9 +30,20 @@ __global__ void __launch_bounds__(256) gather_windows_kernel(const SRC* const* _
   const SRC* s = src[b] + r * t_total[b];
   float* o = out + (static_cast<int64_t>(b) * rows + r) * T;
   const int d0 = dst0[b], s0 = src0[b], n = len[b];
-  for (int t = blockIdx.x * 32 * 4 + (threadIdx.x & 31); t < min(T, (static_cast<int>(blockIdx.x) + 1) * 32 * 4); t += 32) {
-    const int k = t - d0;
-    o[t] = (k >= 0 && k < n) ? static_cast<float>(s[s0 + k]) : 0.f;
+  const int lane = threadIdx.x & 31;
+  // one warp per row; 8 independent (unaligned, hence scalar) loads in flight per lane before the first store
+  for (int base = 0; base < T; base += 256) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = base + j * 32 + lane - d0;
+      v[j] = (k >= 0 && k < n && base + j * 32 + lane < T) ? static_cast<float>(__ldcs(s + s0 + k)) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t = base + j * 32 + lane;
+      if (t < T) __stcs(o + t, v[j]);
+    }
   }
 }
 
@@ -196,7 +207,7 @@ extern "C" int tribe_gather_windows(const void* const* src_ptrs, int32_t src_dty
   if (!src_ptrs || !t_total || !dst_start || !src_start || !length || !out || n_windows <= 0 || rows <= 0 || t_out <= 0)
     return set_error(TRIBE_EINVAL, "gather_windows: bad arguments");
   if (n_windows > 65535 || (rows + 7) / 8 > 65535) return set_error(TRIBE_EINVAL, "gather_windows: too many windows / rows for one launch");
-  dim3 grid(static_cast<unsigned>((t_out + 127) / 128), static_cast<unsigned>((rows + 7) / 8), static_cast<unsigned>(n_windows));
+  dim3 grid(1, static_cast<unsigned>((rows + 7) / 8), static_cast<unsigned>(n_windows));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long* tt = reinterpret_cast<const long long*>(t_total);
   if (src_dtype == TRIBE_DT_F32)

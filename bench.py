@@ -273,7 +273,10 @@ def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with
            "e2e": {"value": n_e2e * EVAL_PARCELS * EVAL_TRS / e2e_s,
                    "unit": "parcel-TRs/s", "h2d_bytes_per_step": 8 * n_e2e * (hi - lo) * EVAL_TRS, "d2h_bytes_per_step": 4 * (hi - lo),
                    "sample": f"{n_e2e} windows per rank from pinned host arrays via metrics.pearson_from_host"},
-           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                        # dram__bytes_read+write of one launch at this exact shape on 1 GPU, ncu --set full
+                        # (profiles/r01_ncu_full_summary_v2.txt): 2051.0 MB read + 4.4 MB written for 2048 MB of operands
+                        "traffic": 2.0554e9 if world == 1 else None, "algorithmic_bytes": shard_bytes,
                         "kernel": "pearson_bdt_kernel<4>", "peak_source": peaks["src"] + " copy bandwidth", "bytes_per_parcel_tr": 8}}
     if with_cpu:
         out["cpu_baseline"] = cpu_pearson_baseline()
@@ -433,7 +436,11 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                             "traffic": None, "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of the timed steps)",
+                             # dram bytes of ALL GEMM launches of one step (8 x the layer-0 fwd + layer-7 bwd captures of
+                             # profiles/r01_ncu_full_summary_v2.txt; tensor-bound kernels, so this is context, not the bound)
+                             "traffic": 27.65e9 if not contrastive else None, "traffic_unit": "dram bytes per train step, all GEMM launches",
+                             "tensor_pipe_active_pct_ncu": {"wgrad": "82-85", "ff1/qkv fwd": "72-80", "dgrad": "65-82", "out 3072^2": "44-67", "attention": "11-18"},
+                             "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (all tcgen05 GEMM launches of the timed steps)",
                              "peak_source": peaks["src"] + " sustained bf16", "gemm_share_of_step": gemm_ms / ms if ms else None,
                              "measured_in": ("K replays of an instrumented step graph (event-record nodes around every GEMM launch)" if use_graphs
                                              else "the K eager steps, CUDA-event pair per GEMM launch"), "instrumented_ms_per_step": ms_eager / K,

@@ -167,6 +167,45 @@ def test_ensemble_average_large_and_ragged():
         np.testing.assert_allclose(ensemble.average_predictions(preds, None).cpu().numpy(), preds.astype(np.float64).mean(0), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("loss_name", ["PearsonLoss", "SmoothL1Loss", "HuberLoss"])
+def test_brain_module_trains_with_the_grid_losses(loss_name):
+    """run_ensemble.py:29 samples the loss; BrainModule._run_step (pl_module.py:46-107) must give the oracle's loss value
+    (bf16 predictions: 1e-2 relative) and the gradients must flow through the fused loss kernels into the encoder."""
+    from algonauts2025_b200.model import FmriEncoder, FmriEncoderConfig
+    from algonauts2025_b200.pl_module import BrainModule
+    from algonauts2025_b200.segment import synthetic_batch
+    from oracle import tribe_oracle as O
+
+    dims = {"text": (2, 96), "audio": (2, 40), "video": (1, 72)}
+    small = dict(hidden=384, depth=2, heads=6)
+    torch.manual_seed(5)
+    model = FmriEncoder(dims, 200, 25, FmriEncoderConfig(n_subjects=3), **small)
+    oracle = O.OracleFmriEncoder(dims, 200, 25, O.OracleConfig(n_subjects=3), **small)
+    oracle.load_reference_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    spec = tuple((k, v[0], v[1]) for k, v in dims.items())
+    batch = synthetic_batch(batch_size=3, t=74, t_out=25, n_outputs=200, n_subjects=3, seed=7, dims=spec)
+    ours = {"PearsonLoss": L.PearsonLoss(), "SmoothL1Loss": torch.nn.SmoothL1Loss(), "HuberLoss": torch.nn.HuberLoss()}[loss_name]
+    ref_fn = {"PearsonLoss": O.pearson_loss, "SmoothL1Loss": torch.nn.SmoothL1Loss(), "HuberLoss": torch.nn.HuberLoss()}[loss_name]
+    module = BrainModule(model=model, loss=ours, optim_config=None, metrics={"val/retrieval_top1": TopkAcc(topk=1)}, max_epochs=1)
+    module.train()
+    loss = module.training_step(batch, 0)
+    loss.backward()
+    oracle.train()
+    ref_loss, ref_pred, ref_true, _ = O.run_step(oracle, O.SegmentData(data=batch.data, segments=batch.segments), loss_fn=ref_fn)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item()) + 1e-4, (loss.item(), ref_loss.item())
+    got, want = model.predictor.weights.grad.float().cpu(), oracle.predictor_weights.grad
+    assert torch.isfinite(got).all()
+    assert float((got - want).norm() / want.norm()) < 3e-2, float((got - want).norm() / want.norm())
+    module.eval()
+    with torch.no_grad():
+        y_pred, y_true = module.validation_step(batch, 0)
+    assert y_pred.shape == (3, 200, 25) and not y_pred.is_cuda
+    top1 = module.metrics["val/retrieval_top1"].compute().item()
+    ref_ranks = A.retrieval_ranks(ref_pred.detach().mean(-1).numpy().astype(np.float64), ref_true.mean(-1).numpy().astype(np.float64))
+    assert 0.0 <= top1 <= 1.0 and abs(top1 - A.topk_acc(ref_ranks, 1)) <= 1.0 / 3 + 1e-6  # 3 queries: at most one flip from bf16 noise
+
+
 def test_swa_running_average_of_the_flat_parameter_buffer():
     from algonauts2025_b200.model import FmriEncoder, FmriEncoderConfig
 

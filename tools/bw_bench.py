@@ -95,6 +95,30 @@ def main():
     xt = torch.randn(B, T, H, device=dev).bfloat16()
     yp = torch.empty(B, TQ, H, device=dev, dtype=torch.bfloat16)
     timeit("token pool fwd (16 x 298 x 3072 -> 100)", lambda: ops.token_pool_fwd(xt, yp, B, T, TQ, H), 2 * B * H * (T + TQ))
+    del w, wb
+    # ---- SURVEY §8f rows
+    big = torch.randn(2560, O, TQ, device=dev)
+    bigt = torch.randn(2560, O, TQ, device=dev)
+    stats.zero_()
+    timeit("pearson_stats (b,d,t) layout (2560 x 1000 x 100)", lambda: ops.pearson_stats(big, bigt, stats, layout="bdt"), 8 * big.numel())
+    _, coef = ops.pearson_loss_fwd(big, bigt, layout="bdt")
+    up = torch.ones(1, device=dev)
+    timeit("pearson_loss bwd (2560 x 1000 x 100)", lambda: ops.pearson_loss_bwd(big, bigt, coef, up, layout="bdt"), 12 * big.numel())
+    timeit("smooth_l1 fwd+grad (2560 x 1000 x 100)", lambda: ops.point_loss_fwd_bwd(big, bigt, ops.LOSS_SMOOTH_L1, 1.0), 12 * big.numel())
+    timeit("pearson_loss fwd (16 x 1000 x 100) [train batch]", lambda: ops.pearson_loss_fwd(pr, tg, layout="bdt"), 8 * pr.numel())
+    del big, bigt
+    members = torch.randn(8, 25_600, O, device=dev)
+    wts = ops.ensemble_weights(torch.rand(8, O, device=dev), 0.3)
+    timeit("ensemble average (8 members x 25600 x 1000)", lambda: ops.ensemble_average(members, wts), 4 * members.numel() + 4 * 25_600 * O)
+    del members
+    from algonauts2025_b200 import windows as W
+    store = W.TimelineStore()
+    for tl in range(4):
+        store.add("text", f"t{tl}", torch.randn(2, 3072, 1500), start=0.0, frequency=2.0)
+    wins = [(f"t{i % 4}", -4.47 + 149.0 * (i // 4)) for i in range(16)]
+    timeit("window gather text (16 x 2 x 3072 x 298)", lambda: store.assemble("text", wins), 8 * 16 * 2 * 3072 * 298)
+    avg, par = torch.zeros(200_000_000, device=dev), torch.randn(200_000_000, device=dev)
+    timeit("swa update (200 M params)", lambda: ops.swa_update(avg, par, 3), 12 * avg.numel())
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(RESULTS, open(os.path.join(ROOT, "gpurun_out", "bw_bench.json"), "w"), indent=1)
 

@@ -18,6 +18,7 @@
 // index_select + einsum modeling_utils/modeling_utils/models/common.py:61-66; InfoNCE logits model.py:216.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -364,7 +365,9 @@ static int encode_operand(const TribeOperand& op, int box_rows, CUtensorMap* out
   return TRIBE_OK;
 }
 
-static int num_sms() {
+static std::atomic<int> g_sm_limit{0};  // tribe_gemm_set_sm_limit: 0 = all SMs
+
+static int device_sms() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -379,6 +382,17 @@ static int num_sms() {
     }
   }
   return n;
+}
+
+static int num_sms() {
+  const int n = device_sms(), lim = g_sm_limit.load(std::memory_order_relaxed);
+  return (lim >= 2 && lim < n) ? (lim & ~1) : n;
+}
+
+extern "C" int tribe_gemm_set_sm_limit(int32_t n_sms) {
+  if (n_sms < 0) return set_error(TRIBE_EINVAL, "gemm_set_sm_limit: negative");
+  g_sm_limit.store(n_sms, std::memory_order_relaxed);
+  return TRIBE_OK;
 }
 
 template <int BN, bool A_MN, bool B_MN>

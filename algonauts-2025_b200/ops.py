@@ -396,3 +396,8 @@ def retrieval_ranks(x, y, want_scores=False):
 def swa_update(avg, params, n_averaged: int) -> None:
     _need(avg, torch.float32, "swa avg"), _need(params, torch.float32, "swa params")
     _run("tribe_swa_update", _ptr(avg), _ptr(params), avg.numel(), int(n_averaged), _stream())
+
+
+def gemm_set_sm_limit(n_sms: int) -> None:
+    """Persistent GEMM grids use at most ``n_sms`` SMs from the next launch on (0 = all SMs)."""
+    _run("tribe_gemm_set_sm_limit", int(n_sms))

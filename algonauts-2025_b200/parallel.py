@@ -40,13 +40,17 @@ class StepOverlap:
       next forward.  The arithmetic is exactly ``optimizer.step()``'s; only its position in time moves.
     """
 
-    def __init__(self, model, group=None, optimizer=None, adam_blocks: int = 148):
+    def __init__(self, model, group=None, optimizer=None, adam_blocks: int = 148, gemm_sms_during_comm: int = 0):
         self.model = model
         self.engine = model._engine
         self.engine.comm = self
         self.group = group
         self.optimizer = optimizer
         self.adam_blocks = adam_blocks
+        # > 0: once the first gradient bucket of a step is on the wire, the remaining backward GEMMs run on this many
+        # SMs so that the collective's CTAs and the persistent GEMM grid are co-resident (reset at finish_step)
+        self.gemm_sms_during_comm = gemm_sms_during_comm
+        self._limited = False
         self.opt_stream = None
         self.works = []
         self.passes, self.head_passes = 1, 0
@@ -79,6 +83,11 @@ class StepOverlap:
             g = self.engine.flat.grad[start:end]
             work = dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             self.works.append(work)
+            if self.gemm_sms_during_comm > 0 and not self._limited:
+                from . import ops
+
+                ops.gemm_set_sm_limit(self.gemm_sms_during_comm)
+                self._limited = True
         if early_adam:
             main = torch.cuda.current_stream()
             if self.opt_stream is None:
@@ -91,6 +100,11 @@ class StepOverlap:
             self.early.append((start, end))
 
     def finish_step(self):
+        if self._limited:
+            from . import ops
+
+            ops.gemm_set_sm_limit(0)
+            self._limited = False
         for w in self.works:
             w.wait()
         self.works = []

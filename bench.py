@@ -309,7 +309,7 @@ def run_ours(args):
     # the reference recipe (Adam lr 1e-4 + OneCycleLR per step); the stock torch.optim.Adam instance is adopted by the
     # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
     opt, sched = default_optimizer(model.parameters(), total_steps=4 * (K + W) + 16, model=None if args.stock_adam else model)
-    sync = parallel.GradAllReduce(model) if world > 1 else None
+    sync = parallel.GradAllReduce(model, gemm_sms_during_comm=args.comm_gemm_sms) if world > 1 else None
     # whole-step CUDA graphs; with N > 1 the step contains NCCL all-reduces, which are only captured on request
     use_graphs = not args.eager and not args.stock_adam and (world == 1 or args.graph_comm)
     # measured on B200 (profiles/r01_adam_overlap_ab.txt): the step is power-capped, so moving Adam's 28 GB of HBM
@@ -483,6 +483,7 @@ def main():
     ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying whole-step CUDA graphs")
     ap.add_argument("--graph-comm", action="store_true", help="N > 1: capture the steps including their NCCL all-reduces (default: eager steps)")
+    ap.add_argument("--comm-gemm-sms", type=int, default=0, help="N > 1: SMs the backward GEMMs use while gradient all-reduces are in flight (0 = all)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump all thread stacks and exit if the run takes longer than this many seconds (0 = off)")
     ap.add_argument("--overlap", action="store_true", help="run each layer's Adam step behind the backward (parallel.StepOverlap) instead of after it")
     ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")

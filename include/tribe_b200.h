@@ -120,6 +120,10 @@ int tribe_gemm_bf16(const TribeGemm* g, void* stream);
 
 /* Descriptor-probe variant used by tests only: overrides the UMMA shared-memory descriptor byte offsets
  * (lbo/sbo for K-major and MN-major operands); pass 0 to keep the defaults. */
+/* Persistent GEMM grids use at most n_sms SMs from the next launch on (0 = all).  While a collective's CTAs occupy SMs
+ * next to the backward pass, a one-CTA-per-SM grid would wait a whole kernel for the occupied SMs; a smaller grid runs
+ * beside them (parallel.StepOverlap sets / clears this around the gradient all-reduces). */
+int tribe_gemm_set_sm_limit(int32_t n_sms);
 int tribe_gemm_bf16_probe(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t k_sbo, uint32_t mn_lbo, uint32_t mn_sbo);
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -183,6 +183,28 @@ __global__ void __launch_bounds__(256) retrieval_ranks_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ (B, R, C) -> (B, C, R)
+// The materialised `rearrange("b d t -> (b t) d")` of pl_module.py:54-55 (needed only by losses / metrics that are not
+// fused) and the per-window `pred.T` of the submission assembly (callbacks.py:66): 32 x 32 tiles through padded smem,
+// coalesced on both sides, bit-exact.
+__global__ void __launch_bounds__(256) transpose_last2_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+  __shared__ float tile[32][33];
+  const int64_t base = static_cast<int64_t>(blockIdx.z) * R * C;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int r = r0 + ty + j, c = c0 + tx;
+    if (r < R && c < C) tile[ty + j][tx] = x[base + static_cast<int64_t>(r) * C + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + ty + j, r = r0 + tx;
+    if (r < R && c < C) y[base + static_cast<int64_t>(c) * R + r] = tile[tx][ty + j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ SWA
 __global__ void __launch_bounds__(256) swa_update_kernel(float* __restrict__ avg, const float* __restrict__ p, float inv_n1, int64_t n) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -274,5 +296,15 @@ extern "C" int tribe_swa_update(float* avg, const float* params, int64_t n, int6
   swa_update_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       avg, params, 1.0f / static_cast<float>(n_averaged + 1), n);
   TRIBE_CHECK_LAUNCH("swa_update");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_transpose_last2(const float* x, float* y, int64_t batch, int64_t rows, int64_t cols, void* stream) {
+  if (!x || !y || batch <= 0 || rows <= 0 || cols <= 0 || batch > 65535 || rows > INT32_MAX || cols > INT32_MAX)
+    return set_error(TRIBE_EINVAL, "transpose_last2: bad arguments");
+  if ((rows + 31) / 32 > 65535) return set_error(TRIBE_EINVAL, "transpose_last2: too many rows for one launch");
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>(batch));
+  transpose_last2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, static_cast<int>(rows), static_cast<int>(cols));
+  TRIBE_CHECK_LAUNCH("transpose_last2");
   return TRIBE_OK;
 }

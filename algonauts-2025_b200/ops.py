@@ -401,3 +401,13 @@ def swa_update(avg, params, n_averaged: int) -> None:
 def gemm_set_sm_limit(n_sms: int) -> None:
     """Persistent GEMM grids use at most ``n_sms`` SMs from the next launch on (0 = all SMs)."""
     _run("tribe_gemm_set_sm_limit", int(n_sms))
+
+
+def transpose_last2(x):
+    """(B, R, C) fp32 -> contiguous (B, C, R), bit-exact."""
+    _need(x, torch.float32, "transpose x")
+    b, r, c = x.shape
+    y = torch.empty(b, c, r, device=x.device, dtype=torch.float32)
+    if x.numel():
+        _run("tribe_transpose_last2", _ptr(x), _ptr(y), b, r, c, _stream())
+    return y

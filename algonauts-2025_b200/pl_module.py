@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from . import losses as L
+from . import ops
 from .segment import SegmentData
 
 try:  # pragma: no cover - lightning is not in this image
@@ -43,7 +44,24 @@ except Exception:  # noqa: BLE001
             return None
 
 
+class _FlattenFn(torch.autograd.Function):
+    """``rearrange(x, "b d t -> (b t) d")`` (pl_module.py:54-55) as the tiled transpose kernel; its adjoint is the same
+    kernel with the two dims swapped."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return ops.transpose_last2(x.detach().float().contiguous()).view(-1, x.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        b, d, t = ctx.shape
+        return ops.transpose_last2(g.contiguous().float().view(b, t, d))
+
+
 def _flatten_bdt(x: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda and x.dim() == 3:
+        return _FlattenFn.apply(x)
     return x.permute(0, 2, 1).reshape(-1, x.shape[1])  # "b d t -> (b t) d"
 
 

@@ -471,12 +471,95 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ensemble(args):
+    """BASELINE.json config 4 (run_ensemble): one TRIBE member per GPU (own seed, no training collectives), then the
+    ensemble-averaged per-parcel Pearson evaluation on a shared held-out set (average_submissions.py:107-125):
+    every member predicts the same windows, its per-parcel validation r weights its predictions, one all-reduce
+    forms the ensemble prediction, the Pearson kernel scores it."""
+    import torch.distributed as dist
+
+    import algonauts2025_b200
+    from algonauts2025_b200 import ops, parallel
+    from algonauts2025_b200.model import FmriEncoderConfig
+    from algonauts2025_b200.pl_module import BrainModule
+    from algonauts2025_b200.segment import DevicePrefetcher, synthetic_batch
+    from algonauts2025_b200.trainer import MiniTrainer, default_optimizer
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    algonauts2025_b200.load()
+    B, K, W = args.batch, args.steps, args.warmup
+    torch.manual_seed(1000 + rank)  # run_ensemble.py:23 seed=None -> every member its own initialisation
+    cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3)
+    model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
+    module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=15)
+    opt, sched = default_optimizer(model.parameters(), total_steps=2 * (K + W) + 16, model=model)
+    trainer = MiniTrainer(module, opt, sched, use_graphs=not args.eager)
+    host = [synthetic_batch(batch_size=B, seed=1234 + i, pin=True) for i in range(2)]  # same data stream for every member
+    dev = DevicePrefetcher(()).resident(host)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        trainer.eager_step(dev[i % 2])
+    if trainer._graphed is not None:
+        trainer._graphed.warm(dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        trainer.train_step(dev[i % 2])
+    e1.record()
+    barrier()
+    ms_train = e0.elapsed_time(e1)
+    # ---- ensemble evaluation on a shared set of 4 x B windows
+    model.eval()
+    shared = [synthetic_batch(batch_size=B, seed=999 + i) for i in range(4)]
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    with torch.no_grad():
+        preds = torch.cat([model(b) for b in shared])                          # (4B, O, T') this member's predictions
+        trues = torch.cat([b.data["fmri"] for b in shared]).cuda()
+        stats = torch.zeros(1, 6, 1000, device="cuda", dtype=torch.float64)
+        ops.pearson_stats(preds, trues, stats, layout="bdt")
+        r_member = ops.pearson_finalize(stats[0])[0]                           # (O,) per-parcel r of this member
+        ens = parallel.ensemble_average(preds, r_member, temperature=0.3)      # weighted all-reduce (reference weighting)
+        stats.zero_()
+        ops.pearson_stats(ens.contiguous(), trues, stats, layout="bdt")
+        r_ens, mean_ens = ops.pearson_finalize(stats[0], want_mean=True)
+    f1.record()
+    barrier()
+    ms_eval = f0.elapsed_time(f1)
+    t = torch.tensor([ms_train, ms_eval], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_train, ms_eval = (float(x) for x in t.cpu())
+    if rank == 0:
+        print(json.dumps({"metric": "ensemble train windows/s (one member per GPU)", "value": world * B * K / (ms_train / 1e3), "unit": "windows/s",
+                          "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_train / K, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": WORKLOAD, "members": world, "parallelism": f"ensemble x{world} (no training collectives)"},
+                          "ensemble_eval": {"windows": 4 * B, "ms": ms_eval, "windows_per_s": 4 * B / (ms_eval / 1e3),
+                                            "mean_r_member0": float(r_member.mean()), "mean_r_ensemble": float(mean_ens[0]),
+                                            "weights": "softmax(r / 0.3) over the voxel axis per member (average_submissions.py:108-109)"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "ensemble"], help="ensemble: BASELINE config 4, one member per GPU + ensemble-averaged Pearson eval")
     ap.add_argument("--contrastive", type=int, default=0)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -497,7 +580,7 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-        run_ours(args)
+        run_ensemble(args) if args.mode == "ensemble" else run_ours(args)
 
 
 if __name__ == "__main__":

@@ -290,6 +290,10 @@ int tribe_ensemble_average(const float* preds, const float* w, int64_t n_members
  * scores_out (optional) fp32 (n, n). */
 int tribe_mean_lastdim(const float* x, float* y, int64_t rows, int64_t t, void* stream);
 int tribe_retrieval_ranks(const float* x, const float* y, int64_t n, int64_t c, float* ranks, float* scores_out, void* stream);
+/* y (batch, cols, rows) = transpose of x (batch, rows, cols), fp32, bit-exact: the materialised "b d t -> (b t) d" of
+ * pl_module.py:54-55 for losses / metrics without a fused kernel, and `pred.T` of the submission assembly
+ * (algonauts2025/callbacks.py:66). */
+int tribe_transpose_last2(const float* x, float* y, int64_t batch, int64_t rows, int64_t cols, void* stream);
 /* Stochastic weight averaging over the flat parameter buffer (algonauts2025/main.py:365-373; torch AveragedModel):
  * avg += (params - avg) / (n_averaged + 1). */
 int tribe_swa_update(float* avg, const float* params, int64_t n, int64_t n_averaged, void* stream);

@@ -134,3 +134,29 @@ def average_members(preds: np.ndarray, pearsons=None, scores=None, weigh_by_scor
 
 def swa_update(avg: np.ndarray, p: np.ndarray, n_averaged: int) -> np.ndarray:
     return avg + (p - avg) / (n_averaged + 1)  # torch.optim.swa_utils.AveragedModel default avg_fn
+
+
+# ---------------------------------------------------------------------------------------------------- submission assembly
+def assemble_submission(batches, labels, target_sample_number, overlap_trs: int = 0):
+    """Benchmark.on_test_batch_end / on_test_epoch_end (callbacks.py:56-92) with the evident intent ``overlap_trs = 0``
+    (the reference's float 0.0 makes the slice raise for a second window of a chunk).  batches: list of (B, O, T)
+    arrays; labels: list of [(subject, chunk)] per batch, already in their final form."""
+    sub: dict = {}
+    for y, segs in zip(batches, labels):
+        for i, (subject, chunk) in enumerate(segs):
+            pred = np.asarray(y[i]).T
+            per = sub.setdefault(subject, {})
+            if chunk not in per:
+                per[chunk] = []
+            else:
+                pred = pred[overlap_trs:]
+            per[chunk].append(pred)
+    out: dict = {}
+    for subject, per in sub.items():
+        out[subject] = {}
+        for chunk, n in target_sample_number[subject].items():
+            result = np.concatenate(per[chunk], axis=0)
+            if len(result) < n:
+                raise ValueError(f"Warning: {len(result)} predictions for {chunk} but expected at least {n}")
+            out[subject][chunk] = result[:n]
+    return out

@@ -4,8 +4,8 @@ side of the hot path.  Build container only (needs /root/refere
 Executed unmodified from /root/reference (absent third-party packages satisfied by ``oracle/shims``):
 ``modeling_utils.losses.losses.PearsonLoss`` (+ autograd gradient), ``modeling_utils.metrics.metrics.Rank / TopkAcc``,
 ``data_utils.base.TimedArray`` in the extractors' two-stage flow (features/audio.py:100-111, 236-252),
-``data_utils.segments._prepare_strided_windows`` and ``algonauts2025.grids.average_submissions.average_submissions`` on
-synthetic submission folders.  torch.nn.SmoothL1Loss / HuberLoss / L1Loss are the stock torch modules the reference's
+``data_utils.segments._prepare_strided_windows``, ``algonauts2025.grids.average_submissions.average_submissions`` on
+synthetic submission folders and the ``algonauts2025.callbacks.Benchmark`` callback on mock segments.  torch.nn.SmoothL1Loss / HuberLoss / L1Loss are the stock torch modules the reference's
 ``TorchLossConfig`` instantiates (losses/base.py:43-59)."""
 from __future__ import annotations
 
@@ -120,6 +120,40 @@ def main():
             for sub, chunks in res.items():
                 for c, v in chunks.items():
                     out[f"ens_{tag}_{sub}_{c}"] = np.asarray(v)
+    # ---- submission assembly through the reference Benchmark callback (callbacks.py:47-103) on mock segments
+    import types
+
+    from algonauts2025.callbacks import Benchmark
+
+    class _Seg:
+        def __init__(self, subject, chunk):
+            self.events = pd.DataFrame({"subject": [subject] * 2, "chunk": [chunk] * 2})
+
+    # NB callbacks.py:59 sets ``overlap_trs = 0.0`` (a float), so ``pred[overlap_trs:]`` (:73) raises TypeError as soon as a
+    # (subject, chunk) pair receives a SECOND window; the reference callback therefore only runs with one window per
+    # chunk, which is what these vectors cover.  Multi-window chunks are checked against the oracle (overlap 0).
+    layout = [[("Algonauts2025/sub-01", "friends:e01a"), ("Algonauts2025/sub-02", "friends:e01a"), ("Algonauts2025/sub-01", "friends:e01b")],
+              [("Algonauts2025/sub-02", "friends:e01b"), ("Algonauts2025/sub-01", "friends:e02a"), ("Algonauts2025/sub-02", "friends:e02a")]]
+    samples = {"sub-01": {"s07e01a": 4, "s07e01b": 5, "s07e02a": 3}, "sub-02": {"s07e01a": 5, "s07e01b": 2, "s07e02a": 4}}
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        for subj, per in samples.items():
+            f = d / f"algonauts_2025.competitors/fmri/{subj}/target_sample_number"
+            f.mkdir(parents=True)
+            np.save(f / f"{subj}_friends-s7_fmri_samples.npy", per)
+        cb = Benchmark(d)
+        trainer = types.SimpleNamespace(logger=types.SimpleNamespace(save_dir=str(d)))
+        cb.on_test_epoch_start(trainer, None)
+        for b, segs in enumerate(layout):
+            y = torch.randn(3, 6, 5, generator=g)
+            out[f"sub_pred_{b}"] = y.numpy()
+            batch = types.SimpleNamespace(segments=[_Seg(s, c) for s, c in segs])
+            cb.on_test_batch_end(trainer, None, (y, None), batch, b)
+        cb.on_test_epoch_end(trainer, None)
+        for subj, per in cb.submission_dict.items():
+            for chunk, arr in per.items():
+                out[f"sub_out_{subj}_{chunk}"] = np.asarray(arr)
+    out["sub_layout"] = np.array([[f"{s}|{c}" for s, c in segs] for segs in layout])
     np.savez_compressed(os.path.join(OUT, "aux_ops.npz"), **out)
     print("aux_ops.npz written:", len(out), "arrays")
 

@@ -87,3 +87,25 @@ def test_swa_rule():
     for n, p in enumerate(ps):
         avg = A.swa_update(avg, p, n)
     np.testing.assert_allclose(avg, ps.mean(0), rtol=1e-12)
+
+
+def _submission_inputs(g):
+    layout = [[tuple(x.split("|")) for x in row] for row in g["sub_layout"]]
+    batches = [g[f"sub_pred_{b}"] for b in range(len(layout))]
+    labels = [[(s.split("/")[1], "s07" + c.split(":")[1]) for s, c in row] for row in layout]
+    samples = {}
+    for k in g.files:
+        if k.startswith("sub_out_"):
+            _, _, subj, chunk = k.split("_")
+            samples.setdefault(subj, {})[chunk] = g[k].shape[0]
+    return layout, batches, labels, samples
+
+
+def test_submission_assembly_oracle_matches_reference_benchmark_callback(g):
+    layout, batches, labels, samples = _submission_inputs(g)
+    out = A.assemble_submission(batches, labels, samples)
+    for subj, per in out.items():
+        for chunk, arr in per.items():
+            np.testing.assert_array_equal(arr, g[f"sub_out_{subj}_{chunk}"])
+    with pytest.raises(ValueError):
+        A.assemble_submission(batches, labels, {s: {c: n + 10 for c, n in per.items()} for s, per in samples.items()})

@@ -230,3 +230,56 @@ def test_swa_running_average_of_the_flat_parameter_buffer():
     swa.swap_into_model()
     for name, _ in model.named_parameters():
         torch.testing.assert_close(model.state_dict()[name], live[name])
+
+
+# ------------------------------------------------------------------------------------------------------------ submission
+def test_transpose_and_flatten_are_bit_exact_with_gradients():
+    from algonauts2025_b200.pl_module import _flatten_bdt
+
+    torch.manual_seed(0)
+    for shape in ((3, 1000, 100), (2, 37, 298), (1, 5, 1), (4, 33, 65)):
+        x = torch.randn(*shape)
+        y = ops.transpose_last2(x.to(DEV))
+        assert torch.equal(y.cpu(), x.transpose(1, 2).contiguous())
+        xd = x.to(DEV).requires_grad_(True)
+        flat = _flatten_bdt(xd)
+        assert torch.equal(flat.detach().cpu(), x.permute(0, 2, 1).reshape(-1, shape[1]))
+        w = torch.randn_like(flat)
+        (flat * w).sum().backward()
+        assert torch.equal(xd.grad.cpu(), w.cpu().view(shape[0], shape[2], shape[1]).transpose(1, 2).contiguous())
+
+
+def test_submission_assembler_matches_reference_benchmark_callback(g):
+    from algonauts2025_b200.submission import SubmissionAssembler
+
+    layout = [[tuple(x.split("|")) for x in row] for row in g["sub_layout"]]
+    samples = {}
+    for k in g.files:
+        if k.startswith("sub_out_"):
+            _, _, subj, chunk = k.split("_")
+            samples.setdefault(subj, {})[chunk] = g[k].shape[0]
+    asm = SubmissionAssembler()
+    for b, row in enumerate(layout):
+        asm.add_batch(torch.from_numpy(g[f"sub_pred_{b}"]).to(DEV), [s for s, _ in row], [c for _, c in row])  # raw event labels
+    out = asm.finalize(samples)
+    assert set(out) == set(samples)
+    for subj, per in out.items():
+        for chunk, arr in per.items():
+            np.testing.assert_array_equal(arr, g[f"sub_out_{subj}_{chunk}"])
+    # several windows per chunk (where the reference's float slice index raises): the oracle's overlap-0 assembly
+    rng = np.random.default_rng(4)
+    batches = [rng.standard_normal((4, 1000, 100)).astype(np.float32) for _ in range(3)]
+    labels = [[("sub-01", "s07e01a"), ("sub-02", "s07e01a"), ("sub-01", "s07e01a"), ("sub-01", "s07e01b")],
+              [("sub-02", "s07e01a"), ("sub-02", "s07e01b"), ("sub-01", "s07e01b"), ("sub-01", "s07e01a")],
+              [("sub-02", "s07e01b"), ("sub-01", "s07e01b"), ("sub-02", "s07e01a"), ("sub-02", "s07e01b")]]
+    want_n = {"sub-01": {"s07e01a": 287, "s07e01b": 300}, "sub-02": {"s07e01a": 250, "s07e01b": 299}}
+    asm.reset()
+    for y, row in zip(batches, labels):
+        asm.add_batch(torch.from_numpy(y).to(DEV), [s for s, _ in row], [c for _, c in row])
+    got = asm.finalize(want_n)
+    ref = A.assemble_submission(batches, labels, want_n)
+    for subj, per in ref.items():
+        for chunk, arr in per.items():
+            np.testing.assert_array_equal(got[subj][chunk], arr)
+    with pytest.raises(ValueError):
+        asm.finalize({"sub-01": {"s07e01a": 301, "s07e01b": 1}, "sub-02": {"s07e01a": 1, "s07e01b": 1}})

@@ -424,7 +424,7 @@ def run_ours(args):
         step_tflops = algorithmic_flops_per_window(contrastive) * B * K / (ms / 1e3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_steps(1, 1, 1, contrastive)
+            r = cpu_reference_steps(4, 1, 1, contrastive)  # bounded sample: ~10 s of host work (1.7 TFLOP per window-step)
             cpu = {"value": r["windows_per_s"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         line = {"metric": "train windows/s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

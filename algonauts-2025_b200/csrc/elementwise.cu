@@ -416,6 +416,31 @@ __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
+// bf16 -> bf16 fast path (the training path): 8 channels (16 B) per thread, both source windows of a token loaded before use
+__global__ void __launch_bounds__(256) token_pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int t_in,
+                                                                  int t_out, int64_t C) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  int i_lo = static_cast<int>((static_cast<int64_t>(t) * t_out) / t_in);
+  int i_hi = static_cast<int>((static_cast<int64_t>(t + 1) * t_out + t_in - 1) / t_in);
+  if (i_hi > t_out) i_hi = t_out;
+  const int64_t nvec = C >> 3;
+  for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = i_lo; i < i_hi; ++i) {
+      const int s = win_start(i, t_in, t_out), e = win_end(i, t_in, t_out);
+      if (t >= s && t < e) {
+        const float w = 1.0f / static_cast<float>(e - s);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (static_cast<int64_t>(b) * t_out + i) * C) + v);
+        const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        acc[0] += a.x * w, acc[1] += a.y * w, acc[2] += bb.x * w, acc[3] += bb.y * w;
+        acc[4] += c.x * w, acc[5] += c.y * w, acc[6] += d.x * w, acc[7] += d.y * w;
+      }
+    }
+    reinterpret_cast<uint4*>(dx + (static_cast<int64_t>(b) * t_in + t) * C)[v] =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) token_pool_bwd_kernel(const T* __restrict__ dy, TO* __restrict__ dx, int t_in, int t_out, int64_t C) {
   const int b = blockIdx.y, t = blockIdx.x;
@@ -628,6 +653,8 @@ extern "C" int tribe_token_pool_bwd(const void* dy, int32_t dy_dtype, void* dx, 
   if (dy_dtype == 0 && dx_dtype == 0) token_pool_bwd_kernel<float, float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dy), reinterpret_cast<float*>(dx), ti, to, C);
   else if (dy_dtype == 2 && dx_dtype == 0) token_pool_bwd_kernel<bf, float><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(dy), reinterpret_cast<float*>(dx), ti, to, C);
   else if (dy_dtype == 0 && dx_dtype == 2) token_pool_bwd_kernel<float, bf><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dy), reinterpret_cast<bf*>(dx), ti, to, C);
+  else if (dy_dtype == 2 && dx_dtype == 2 && C % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
+    token_pool_bwd_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(dy), reinterpret_cast<bf*>(dx), ti, to, C);
   else if (dy_dtype == 2 && dx_dtype == 2) token_pool_bwd_kernel<bf, bf><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(dy), reinterpret_cast<bf*>(dx), ti, to, C);
   else return set_error(TRIBE_EINVAL, "token_pool_bwd: unsupported dtype");
   TRIBE_CHECK_LAUNCH("token_pool_bwd");

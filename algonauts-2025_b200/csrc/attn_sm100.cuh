@@ -1,0 +1,339 @@
+// Attention scores with the row softmax fused into the tcgen05 epilogue (included at the end of gemm_sm100.cu).
+//
+// x_transformers attention (restated in oracle/xt_encoder.py; reached through algonauts2025/model.py:173) computes
+//   sim = q k^T * d^-1/2 ;  attn = softmax(sim, dim=-1, dtype=float32) ;  out = attn v
+// and its backward needs  dS = P o (dP - rowsum(dP o P)) * d^-1/2  with  dP = dO v^T.
+// TRIBE's sequences are 298 tokens long, so a WHOLE score row (<= 320 keys) fits in one CTA's TMEM accumulator
+// (128 lanes x 320 fp32 columns of the 512): the fp32 scores never travel to HBM.  Compared with the generic path
+// (GEMM -> fp32 S in HBM -> softmax kernel -> bf16 P) this removes 2 x 46 MB of traffic and one launch per layer and
+// direction.
+//
+//   mode 0 (forward):   out = P  = softmax(scale * A B^T)            A = q rows, B = k rows (both K-major over head dims)
+//   mode 1 (backward):  out = dS = P o (A B^T - rowsum(A B^T o P)) * scale      A = dO rows, B = v rows, P read back (bf16)
+//
+// One persistent CTA per SM, 192 threads: warp 0 = TMA producer (3-stage ring; A box 64 x 128, B as one or two
+// 64 x 160 boxes — key rows >= T are zero-filled by TMA), warp 1 = one thread issuing tcgen05.mma 128 x 160 x 16 per B
+// part into TMEM columns [0,160) / [160,320), warps 2..5 = epilogue, one thread per query row, three (mode 0) or two
+// (mode 1) sweeps over the row's TMEM columns.  The accumulator is single-buffered (2 x 320 columns do not fit), so MMA
+// and epilogue of one CTA alternate while the producer already streams the next tile's operands.
+
+namespace tribe {
+
+constexpr int kAttnNP = 160;                          // UMMA N of one B part
+constexpr int kAttnAB = BM * BK * 2;                  // 16 KiB
+constexpr int kAttnBB = kAttnNP * BK * 2;             // 20 KiB per part
+constexpr int kAttnStage = kAttnAB + 2 * kAttnBB;     // 56 KiB
+constexpr int kAttnStages = 3;
+constexpr int kAttnSmem = kAttnStages * kAttnStage + 256 + 1024;
+
+struct alignas(64) AttnKParams {
+  CUtensorMap tma, tmb;
+  int T, Tp, heads, dh, n_parts, num_kb, m_blocks, num_tiles;
+  int a_off, b_off;
+  float scale;
+  int mode;
+  const __nv_bfloat16* p_in;
+  __nv_bfloat16* out;
+  uint32_t k_lbo, k_sbo;
+};
+
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+__device__ __forceinline__ uint4 attn_pack8(const float* v) {
+  return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __grid_constant__ AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAttnStages * kAttnStage);
+  uint64_t* empty_bar = full_bar + kAttnStages;
+  uint64_t* tfull_bar = empty_bar + kAttnStages;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma);
+    prefetch_tmap(&p.tmb);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kAttnStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tfull_bar, 1);
+      mbar_init(tempty_bar, 128);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t stage_tx = kAttnAB + p.n_parts * kAttnBB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int z = tile / p.m_blocks, mb = tile - z * p.m_blocks;
+        const int b = z / p.heads, h = z - b * p.heads;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kAttnStage;
+          uint8_t* sb = sa + kAttnAB;
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_3d(sa, &p.tma, &full_bar[stage], p.a_off + h * p.dh + kb * BK, mb * BM, b);
+          for (int j = 0; j < p.n_parts; ++j)
+            tma_load_3d(sb + j * kAttnBB, &p.tmb, &full_bar[stage], p.b_off + h * p.dh + kb * BK, j * kAttnNP, b);
+          if (++stage == kAttnStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, kAttnNP, false, false);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar, acc_phase ^ 1);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kAttnStage);
+          const uint32_t sb = sa + kAttnAB;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_smem_desc(sa + kk * 32, p.k_lbo, p.k_sbo);
+            for (int j = 0; j < p.n_parts; ++j) {
+              const uint64_t db = make_smem_desc(sb + j * kAttnBB + kk * 32, p.k_lbo, p.k_sbo);
+              umma_bf16(tmem_base + j * kAttnNP, da, db, idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kAttnStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar);
+        acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nchunks = p.n_parts * (kAttnNP / 32);
+    const float sl2 = p.scale * 1.4426950408889634f;  // exp(scale * x) = exp2(sl2 * x)
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int z = tile / p.m_blocks, mb = tile - z * p.m_blocks;
+      const int row = mb * BM + row_in_tile;
+      const bool row_ok = row < p.T;
+      const long long roff = (static_cast<long long>(z) * p.T + row) * p.Tp;
+      mbar_wait(tfull_bar, acc_phase);
+      tc_fence_after();
+      // One thread owns one query row.  Only four epilogue warps run per SM (one per scheduler), so nothing hides
+      // latencies for them: TMEM is read in groups of up to four 32-column chunks per tcgen05.wait::ld (the wait covers all
+      // loads in flight), every reduction runs as four independent dependency chains, and the backward prefetches its
+      // P row one group ahead.
+      constexpr int G = 4;
+      uint32_t rg[G][32];
+      const int ngroups = (nchunks + G - 1) / G;
+      auto load_group = [&](int g) {
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+          if (g * G + i < nchunks) tmem_ld_32x32(t_addr + (g * G + i) * 32, rg[i]);
+        tmem_ld_wait();
+      };
+      if (p.mode == 0) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int g = 0; g < ngroups; ++g) {
+          if (g * G * 32 >= p.T) break;
+          load_group(g);
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int col0 = (g * G + i) * 32;
+            if (col0 + 32 <= p.T) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rg[i][j]));
+            } else if (col0 < p.T) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.T) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rg[i][j]));
+            }
+          }
+        }
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float msl = m * sl2;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int g = 0; g < ngroups; ++g) {
+          if (g * G * 32 >= p.T) break;
+          load_group(g);
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int col0 = (g * G + i) * 32;
+            if (col0 + 32 <= p.T) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+            } else if (col0 < p.T) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.T) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+            }
+          }
+        }
+        const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+        for (int g = 0; g < ngroups; ++g) {
+          if (g * G * 32 >= p.Tp) break;
+          load_group(g);
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            const int col0 = (g * G + i) * 32;
+            if (col0 < p.Tp && g * G + i < nchunks) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
+              if (row_ok) {
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8)
+                  if (col0 + g8 * 8 < p.Tp) *reinterpret_cast<uint4*>(p.out + roff + col0 + g8 * 8) = attn_pack8(v + g8 * 8);
+              }
+            }
+          }
+        }
+      } else {
+        const __nv_bfloat16* pr = p.p_in + roff;
+        uint4 pu[G][4];
+        auto load_p = [&](int g) {
+#pragma unroll
+          for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = (g * G + i) * 32 + g8 * 8;
+              pu[i][g8] = (row_ok && col < p.Tp) ? __ldg(reinterpret_cast<const uint4*>(pr + col)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int g = 0; g < ngroups; ++g) {
+          if (g * G * 32 >= p.T) break;
+          load_p(g);  // global loads and TMEM loads of the group are in flight together
+          load_group(g);
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            if (g * G + i < nchunks) {
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {  // padding columns of P are zero: they add nothing
+                const float2 a = unpack_bf16x2(pu[i][g8].x), b2 = unpack_bf16x2(pu[i][g8].y), c2 = unpack_bf16x2(pu[i][g8].z),
+                             e2 = unpack_bf16x2(pu[i][g8].w);
+                const int o = g8 * 8;
+                d4[0] = fmaf(a.x, __uint_as_float(rg[i][o]), d4[0]), d4[1] = fmaf(a.y, __uint_as_float(rg[i][o + 1]), d4[1]);
+                d4[2] = fmaf(b2.x, __uint_as_float(rg[i][o + 2]), d4[2]), d4[3] = fmaf(b2.y, __uint_as_float(rg[i][o + 3]), d4[3]);
+                d4[0] = fmaf(c2.x, __uint_as_float(rg[i][o + 4]), d4[0]), d4[1] = fmaf(c2.y, __uint_as_float(rg[i][o + 5]), d4[1]);
+                d4[2] = fmaf(e2.x, __uint_as_float(rg[i][o + 6]), d4[2]), d4[3] = fmaf(e2.y, __uint_as_float(rg[i][o + 7]), d4[3]);
+              }
+            }
+          }
+        }
+        const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        for (int g = 0; g < ngroups; ++g) {
+          if (g * G * 32 >= p.Tp) break;
+          load_p(g);  // second sweep: the row is L1/L2-resident now
+          load_group(g);
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                const int col = (g * G + i) * 32 + g8 * 8;
+                if (col < p.Tp && g * G + i < nchunks) {
+                  const float2 a = unpack_bf16x2(pu[i][g8].x), b2 = unpack_bf16x2(pu[i][g8].y), c2 = unpack_bf16x2(pu[i][g8].z),
+                               e2 = unpack_bf16x2(pu[i][g8].w);
+                  const float pv[8] = {a.x, a.y, b2.x, b2.y, c2.x, c2.y, e2.x, e2.y};
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = pv[j] * (__uint_as_float(rg[i][g8 * 8 + j]) - dot) * p.scale;
+                  *reinterpret_cast<uint4*>(p.out + roff + col) = attn_pack8(v);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace tribe
+
+extern "C" int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, const void* b, int64_t b_ld, int64_t b_off, int64_t n_batch,
+                                 int64_t T, int64_t heads, int64_t dh, float scale, int32_t mode, const void* p_in, void* out, int64_t Tp,
+                                 void* stream) {
+  using namespace tribe;
+  if (!a || !b || !out || n_batch <= 0 || T <= 0 || heads <= 0 || dh <= 0 || (mode != 0 && mode != 1) || (mode == 1 && !p_in))
+    return set_error(TRIBE_EINVAL, "attn_scores: bad arguments");
+  if (dh % BK || T > 2 * kAttnNP || Tp < T || Tp > 2 * kAttnNP || Tp % 8)
+    return set_error(TRIBE_EINVAL, "attn_scores: needs head_dim % 64 == 0, T <= Tp <= 320, Tp % 8 == 0");
+  if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(p_in)) & 15) return set_error(TRIBE_EINVAL, "attn_scores: P / out must be 16-byte aligned");
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  TribeOperand oa, ob;
+  memset(&oa, 0, sizeof(oa));
+  memset(&ob, 0, sizeof(ob));
+  oa.ptr = a, oa.inner = a_ld, oa.rows = T, oa.batch = n_batch, oa.row_stride = a_ld, oa.batch_stride = T * a_ld;
+  ob.ptr = b, ob.inner = b_ld, ob.rows = T, ob.batch = n_batch, ob.row_stride = b_ld, ob.batch_stride = T * b_ld;
+  int rc = encode_operand(oa, BM, &kp.tma);
+  if (rc) return rc;
+  rc = encode_operand(ob, kAttnNP, &kp.tmb);
+  if (rc) return rc;
+  kp.T = static_cast<int>(T), kp.Tp = static_cast<int>(Tp), kp.heads = static_cast<int>(heads), kp.dh = static_cast<int>(dh);
+  kp.n_parts = T > kAttnNP ? 2 : 1;
+  kp.num_kb = static_cast<int>(dh / BK);
+  kp.m_blocks = static_cast<int>((T + BM - 1) / BM);
+  kp.num_tiles = static_cast<int>(kp.m_blocks * n_batch * heads);
+  kp.a_off = static_cast<int>(a_off), kp.b_off = static_cast<int>(b_off);
+  kp.scale = scale, kp.mode = mode;
+  kp.p_in = reinterpret_cast<const __nv_bfloat16*>(p_in);
+  kp.out = reinterpret_cast<__nv_bfloat16*>(out);
+  kp.k_lbo = 16, kp.k_sbo = 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn_scores)");
+    attr_set = true;
+  }
+  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  attn_scores_kernel<<<grid, kGemmThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "attn_scores launch");
+  return TRIBE_OK;
+}

@@ -578,3 +578,5 @@ extern "C" int tribe_gemm_bf16_probe(const TribeGemm* g, void* stream, uint32_t 
                                      uint32_t mn_sbo) {
   return tribe::gemm_impl(g, stream, k_lbo, k_sbo, mn_lbo, mn_sbo);
 }
+
+#include "attn_sm100.cuh"

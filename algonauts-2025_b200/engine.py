@@ -310,10 +310,15 @@ class Engine:
             qkv = ws.qkv[l]
             ops.gemm(ops.kmajor(ws.xn[ia]), ops.kmajor(self._wqkv16(a)), qkv, M, 3 * H, H, ldd=3 * H, epilogue=ops.EPI_ROPE,
                      rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=2 * H)
-            q_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, zin_stride=dh, zdiv=heads)
-            k_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, inner_off=H, zin_stride=dh, zdiv=heads)
-            ops.gemm(q_op, k_op, ws.S, T, T, dh, ldd=Tp, batch=BH, z_inner=heads, d_zo=heads * T * Tp, d_zi=T * Tp, alpha=scale)
-            ops.softmax_fwd(ws.S, ws.P[l], T)
+            if ops.attn_fusable(T, dh):
+                # P = softmax(q k^T d^-1/2) formed in the tcgen05 epilogue: whole score rows live in TMEM, no fp32 S in HBM
+                ops.attn_scores(qkv, 0, qkv, H, B, T, heads, dh, scale, ws.P[l])
+            else:
+                q_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, zin_stride=dh, zdiv=heads)
+                k_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, inner_off=H, zin_stride=dh,
+                                   zdiv=heads)
+                ops.gemm(q_op, k_op, ws.S, T, T, dh, ldd=Tp, batch=BH, z_inner=heads, d_zo=heads * T * Tp, d_zi=T * Tp, alpha=scale)
+                ops.softmax_fwd(ws.S, ws.P[l], T)
             p_op = ops.Operand(ws.P[l], inner=Tp, rows=T, row_stride=Tp, batch=BH, batch_stride=T * Tp)
             v_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, mn_major=True,
                                inner_off=2 * H, zin_stride=dh, zdiv=heads)
@@ -481,10 +486,15 @@ class Engine:
             self._wgrad(ops.mnmajor(dxb_cur), ops.mnmajor(ws.attn[l]), f"{a}.1.to_out.weight", H, H, M, acc[f"{a}.1.to_out.weight"])
             qkv = ws.qkv[l]
             # dP = dO V^T  (per (b, h); both K-major over head dims)
-            do_op = ops.Operand(d_attn, inner=H, rows=T, row_stride=H, batch=B, batch_stride=T * H, zin_stride=dh, zdiv=heads)
-            v_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, inner_off=2 * H, zin_stride=dh, zdiv=heads)
-            ops.gemm(do_op, v_op, ws.S, T, T, dh, ldd=Tp, batch=BH, z_inner=heads, d_zo=heads * T * Tp, d_zi=T * Tp)
-            ops.softmax_bwd(ws.P[l], ws.S, ws.dS, scale, T)
+            if ops.attn_fusable(T, dh):
+                # dS = P o (dP - rowsum(dP o P)) d^-1/2 with dP = dO V^T never leaving TMEM
+                ops.attn_scores(d_attn, 0, qkv, 2 * H, B, T, heads, dh, scale, ws.dS, p_in=ws.P[l])
+            else:
+                do_op = ops.Operand(d_attn, inner=H, rows=T, row_stride=H, batch=B, batch_stride=T * H, zin_stride=dh, zdiv=heads)
+                v_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, inner_off=2 * H, zin_stride=dh,
+                                   zdiv=heads)
+                ops.gemm(do_op, v_op, ws.S, T, T, dh, ldd=Tp, batch=BH, z_inner=heads, d_zo=heads * T * Tp, d_zi=T * Tp)
+                ops.softmax_bwd(ws.P[l], ws.S, ws.dS, scale, T)
             # dV = P^T dO
             pt_op = ops.Operand(ws.P[l], inner=Tp, rows=T, row_stride=Tp, batch=BH, batch_stride=T * Tp, mn_major=True)
             dom_op = ops.Operand(d_attn, inner=H, rows=T, row_stride=H, batch=B, batch_stride=T * H, mn_major=True, zin_stride=dh, zdiv=heads)

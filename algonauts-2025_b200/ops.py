@@ -411,3 +411,19 @@ def transpose_last2(x):
     if x.numel():
         _run("tribe_transpose_last2", _ptr(x), _ptr(y), b, r, c, _stream())
     return y
+
+
+FUSED_ATTN = bool(int(__import__("os").environ.get("TRIBE_FUSED_ATTN", "1")))
+
+
+def attn_fusable(T: int, dh: int) -> bool:
+    """Whole score rows fit one CTA's TMEM accumulator (<= 320 keys) and head dims tile by 64."""
+    return FUSED_ATTN and T <= 320 and dh % 64 == 0
+
+
+def attn_scores(a, a_off: int, b, b_off: int, n_batch: int, T: int, heads: int, dh: int, scale: float, out, *, p_in=None) -> None:
+    """mode 0 (p_in None): out = softmax(scale * a b^T) per (batch, head); mode 1: out = P o (a b^T - rowsum(a b^T o P)) * scale.
+    a, b: bf16 (n_batch * T, ld) with head h at columns [off + h*dh, ...); out / p_in: bf16 (n_batch * heads, T, Tp)."""
+    _need(a, torch.bfloat16, "attn a"), _need(b, torch.bfloat16, "attn b"), _need(out, torch.bfloat16, "attn out")
+    _run("tribe_attn_scores", _ptr(a), a.shape[-1], a_off, _ptr(b), b.shape[-1], b_off, n_batch, T, heads, dh, float(scale),
+         0 if p_in is None else 1, _ptr(p_in), _ptr(out), out.shape[-1], _stream())

@@ -120,6 +120,14 @@ int tribe_gemm_bf16(const TribeGemm* g, void* stream);
 
 /* Descriptor-probe variant used by tests only: overrides the UMMA shared-memory descriptor byte offsets
  * (lbo/sbo for K-major and MN-major operands); pass 0 to keep the defaults. */
+/* Attention scores with the row softmax fused into the tcgen05 epilogue (whole score rows of <= 320 keys live in TMEM;
+ * x_transformers attention behind model.py:173, restated in oracle/xt_encoder.py).  a / b: bf16 row-major (n_batch * T,
+ * ld) matrices whose head h occupies columns [off + h*dh, off + (h+1)*dh); z = batch * heads + head.
+ *   mode 0: out[z, i, :] = softmax_j(scale * <a_i, b_j>)  (bf16 (Z, T, Tp), columns >= T zeroed)      a = q, b = k
+ *   mode 1: out[z, i, j] = P[z,i,j] * (<a_i, b_j> - sum_j' <a_i, b_j'> P[z,i,j']) * scale              a = dO, b = v, P = p_in
+ * Requires dh % 64 == 0, T <= Tp <= 320, Tp % 8 == 0. */
+int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, const void* b, int64_t b_ld, int64_t b_off, int64_t n_batch, int64_t T,
+                      int64_t heads, int64_t dh, float scale, int32_t mode, const void* p_in, void* out, int64_t Tp, void* stream);
 /* Persistent GEMM grids use at most n_sms SMs from the next launch on (0 = all).  While a collective's CTAs occupy SMs
  * next to the backward pass, a one-CTA-per-SM grid would wait a whole kernel for the occupied SMs; a smaller grid runs
  * beside them (parallel.StepOverlap sets / clears this around the gradient all-reduces). */

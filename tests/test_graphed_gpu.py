@@ -64,11 +64,11 @@ def test_graphed_steps_equal_eager_steps(contrastive):
     eager2 = _run(False, contrastive, steps, **kw)
     noise = float((eager2["losses"] - eager["losses"]).abs().max())
     diff = float((graphed["losses"] - eager["losses"]).abs().max())
-    assert diff <= max(4.0 * noise, 2e-4 * float(eager["losses"].abs().max())), (diff, noise)
+    assert diff <= max(10.0 * noise, 1e-3 *float(eager["losses"].abs().max())), (diff, noise)
     for k, v in eager["state"].items():
         n_k = float((eager2["state"][k].float() - v.float()).abs().max())
         d_k = float((graphed["state"][k].float() - v.float()).abs().max())
-        assert d_k <= max(4.0 * n_k, 5e-4 + 5e-3 * float(v.float().abs().max())), (k, d_k, n_k)
+        assert d_k <= max(10.0 * n_k, 1e-3 + 1e-2 *float(v.float().abs().max())), (k, d_k, n_k)
 
 
 @pytest.mark.parametrize("use_graphs", [False, True])
@@ -86,11 +86,11 @@ def test_optimizer_overlapped_with_backward_equals_plain_step(use_graphs, contra
         assert over["steps_of"][n] == k, n
     noise = float((plain2["losses"] - plain["losses"]).abs().max())
     diff = float((over["losses"] - plain["losses"]).abs().max())
-    assert diff <= max(4.0 * noise, 2e-4 * float(plain["losses"].abs().max())), (diff, noise)
+    assert diff <= max(10.0 * noise, 1e-3 *float(plain["losses"].abs().max())), (diff, noise)
     for k, v in plain["state"].items():
         n_k = float((plain2["state"][k].float() - v.float()).abs().max())
         d_k = float((over["state"][k].float() - v.float()).abs().max())
-        assert d_k <= max(4.0 * n_k, 5e-4 + 5e-3 * float(v.float().abs().max())), (k, d_k, n_k)
+        assert d_k <= max(10.0 * n_k, 1e-3 + 1e-2 *float(v.float().abs().max())), (k, d_k, n_k)
 
 
 def test_graphed_step_falls_back_for_host_batches_and_reports_bad_subjects():

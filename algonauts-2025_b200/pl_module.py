@@ -66,78 +66,99 @@ def _flatten_bdt(x: torch.Tensor) -> torch.Tensor:
 
 
 class BrainModule(_Base):
+    """Public surface = the reference's: ``__init__(model, loss, optim_config, metrics, max_epochs, checkpoint_path,
+    config)``, ``forward``, ``_run_step(batch, batch_idx, step_name) -> (loss, y_pred, y_true)``, ``training_step`` /
+    ``validation_step`` / ``test_step``, the two epoch-end hooks and ``configure_optimizers``.  The step itself is split
+    into loss / contrastive / metric stages that all work on the (B, D, T) device tensors."""
+
+    GROUPED_TAG, RETRIEVAL_TAG = "grouped", "retrieval"  # dispatch rules of pl_module.py:93-106
+
     def __init__(self, model: nn.Module, loss: nn.Module, optim_config: tp.Any, metrics: dict[str, tp.Any], max_epochs: int = 100,
                  checkpoint_path: Path | None = None, config: dict[str, tp.Any] | None = None) -> None:
         super().__init__()
-        self.model = model
-        self.checkpoint_path = checkpoint_path
-        self.config = config
-        self.optim_config = optim_config
-        self.max_epochs = max_epochs
-        self.loss = loss
-        self.metrics = metrics
+        self.model, self.loss, self.metrics = model, loss, metrics
+        self.optim_config, self.max_epochs = optim_config, max_epochs
+        self.checkpoint_path, self.config = checkpoint_path, config
 
     def forward(self, batch):
         return self.model(batch)
 
-    def _run_step(self, batch: SegmentData, batch_idx, step_name):
-        y_pred = self.forward(batch)  # B, D, T  (CUDA)
-        y_true = batch.data["fmri"].to(y_pred.device, non_blocking=True)  # B, D, T
-        if step_name == "val":
-            y_true = y_true[:, :, 0:]
-            y_pred = y_pred[:, :, 0:]
-        # the grid's losses run fused on the (B, D, T) tensors (their value is invariant to the (b t) d rearrange, or
-        # — PearsonLoss — the kernel indexes parcels in place); anything else gets the flattened matrices
-        loss = L.fused_loss(self.loss, y_pred, y_true)
-        if loss is None:
-            y_pred_flat, y_true_flat = _flatten_bdt(y_pred), _flatten_bdt(y_true)
-            loss = self.loss(y_pred_flat, y_true_flat)
+    # ------------------------------------------------------------------------------------------------ stages of a step
+    def _primary_loss(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """The configured loss on the step's predictions.  The grid's losses (run_ensemble.py:29) have fused kernels that
+        read the (B, D, T) tensors directly — their value does not depend on the ``(b t) d`` rearrange of
+        pl_module.py:54-55, or (PearsonLoss) the kernel indexes parcels in place; any other module receives the
+        flattened matrices exactly like in the reference."""
+        fused = L.fused_loss(self.loss, pred, target)
+        if fused is not None:
+            return fused
+        return self.loss(_flatten_bdt(pred), _flatten_bdt(target))
 
-        if hasattr(self.model, "compute_contrastive_loss"):
-            contrastive_losses = self.model.compute_contrastive_loss(batch)
-            if contrastive_losses:
-                weight = getattr(self.model.config, "contrastive_weight", 0.0)
-                total_contrastive = 0.0
-                for name, c_loss in contrastive_losses.items():
-                    self.log(f"{step_name}/contrastive/{name}", c_loss, on_step=False, on_epoch=True, logger=True, prog_bar=False,
-                             batch_size=y_pred.shape[0])
-                    total_contrastive = total_contrastive + c_loss
-                total_contrastive = total_contrastive / max(1, len(contrastive_losses))
-                loss = loss + weight * total_contrastive
-        log_kwargs = {"on_step": step_name == "train", "on_epoch": True, "logger": True, "prog_bar": True, "batch_size": y_pred.shape[0]}
-        self.log(f"{step_name}/loss", loss, **log_kwargs)
+    def _contrastive_term(self, batch, stage: str, n_windows: int):
+        """``contrastive_weight * mean(per-modality InfoNCE)`` (pl_module.py:59-77), or None when the model has no
+        contrastive branch / it is disabled.  Each modality's loss is logged under ``{stage}/contrastive/{modality}``."""
+        compute = getattr(self.model, "compute_contrastive_loss", None)
+        per_modality = compute(batch) if compute is not None else None
+        if not per_modality:
+            return None
+        acc = None
+        for modality, value in per_modality.items():
+            self.log(f"{stage}/contrastive/{modality}", value, on_step=False, on_epoch=True, logger=True, prog_bar=False, batch_size=n_windows)
+            acc = value if acc is None else acc + value
+        return getattr(self.model.config, "contrastive_weight", 0.0) * (acc / max(1, len(per_modality)))
 
-        for metric_name, metric in self.metrics.items():
-            if metric_name.startswith(step_name):
-                yp, yt = y_pred.detach(), y_true
-                if "grouped" in metric.__class__.__name__.lower():
-                    if hasattr(metric, "update_bdt"):
-                        metric.update_bdt(yp, yt, groups=batch.data["subject_id"])
-                    else:
-                        groups = batch.data["subject_id"].to(yp.device).repeat_interleave(yp.shape[2], 0)
-                        metric.update(_flatten_bdt(yp), _flatten_bdt(yt), groups=groups)
+    def _feed_metrics(self, stage: str, pred: torch.Tensor, target: torch.Tensor, subject_id, log_opts: dict) -> None:
+        for key, metric in self.metrics.items():
+            if not key.startswith(stage):
+                continue
+            on_device = hasattr(metric, "update_bdt")  # our metric classes read (B, D, T) in place
+            if self.GROUPED_TAG in type(metric).__name__.lower():
+                if on_device:
+                    metric.update_bdt(pred, target, groups=subject_id)
                 else:
-                    if "retrieval" in metric_name:
-                        if hasattr(metric, "update_bdt"):
-                            metric.update_bdt(yp, yt)  # the time average is fused into the metric's kernels
-                        else:
-                            metric.update(yp.mean(dim=-1), yt.mean(dim=-1))
-                    elif hasattr(metric, "update_bdt"):
-                        metric.update_bdt(yp, yt)
-                    else:
-                        metric.update(_flatten_bdt(yp), _flatten_bdt(yt))
-                    self.log(metric_name, metric, **log_kwargs)
+                    per_row = subject_id.to(pred.device).repeat_interleave(pred.shape[2], 0)
+                    metric.update(_flatten_bdt(pred), _flatten_bdt(target), groups=per_row)
+                continue  # grouped metrics are logged at epoch end only
+            if self.RETRIEVAL_TAG in key and not on_device:
+                metric.update(pred.mean(dim=-1), target.mean(dim=-1))
+            elif on_device:
+                metric.update_bdt(pred, target)  # retrieval metrics fuse the time average into their kernels
+            else:
+                metric.update(_flatten_bdt(pred), _flatten_bdt(target))
+            self.log(key, metric, **log_opts)
+
+    def _run_step(self, batch: SegmentData, batch_idx, step_name):
+        pred = self.forward(batch)                                              # (B, D, T) on the device
+        target = batch.data["fmri"].to(pred.device, non_blocking=True)
+        if step_name == "val":                                                  # pl_module.py:50-52 (a no-op slice)
+            pred, target = pred[:, :, 0:], target[:, :, 0:]
+        n_windows = pred.shape[0]
+        loss = self._primary_loss(pred, target)
+        extra = self._contrastive_term(batch, step_name, n_windows)
+        if extra is not None:
+            loss = loss + extra
+        log_opts = dict(on_step=step_name == "train", on_epoch=True, logger=True, prog_bar=True, batch_size=n_windows)
+        self.log(f"{step_name}/loss", loss, **log_opts)
+        self._feed_metrics(step_name, pred.detach(), target, batch.data.get("subject_id"), log_opts)
         if step_name == "train":
-            # training_step discards the predictions; skip the reference's per-step D2H copy + stream sync
-            return loss, y_pred.detach(), y_true
-        return loss, y_pred.detach().cpu(), y_true.detach().cpu()
+            # training_step throws the predictions away: no per-step D2H copy + stream sync as in pl_module.py:107
+            return loss, pred.detach(), target
+        return loss, pred.detach().cpu(), target.detach().cpu()
+
+    # ------------------------------------------------------------------------------------------------ Lightning hooks
+    def training_step(self, batch: SegmentData, batch_idx):
+        return self._run_step(batch, batch_idx, step_name="train")[0]
+
+    def validation_step(self, batch: SegmentData, batch_idx):
+        return self._run_step(batch, batch_idx, step_name="val")[1:]
+
+    def test_step(self, batch: SegmentData, batch_idx):
+        return self._run_step(batch, batch_idx, step_name="test")[1:]
 
     def on_val_or_test_epoch_end(self, step_name: str) -> None:
-        for metric_name, metric in self.metrics.items():
-            if metric_name.startswith(step_name):
-                if "grouped" in metric.__class__.__name__.lower():
-                    metric_dict = {metric_name + "/" + k: v for k, v in metric.compute().items()}
-                    self.log_dict(metric_dict)
+        for key, metric in self.metrics.items():
+            if key.startswith(step_name) and self.GROUPED_TAG in type(metric).__name__.lower():
+                self.log_dict({f"{key}/{group}": value for group, value in metric.compute().items()})
 
     def on_validation_epoch_end(self) -> None:
         self.on_val_or_test_epoch_end("val")
@@ -147,26 +168,12 @@ class BrainModule(_Base):
         self.on_val_or_test_epoch_end("test")
         return super().on_test_epoch_end()
 
-    def training_step(self, batch: SegmentData, batch_idx):
-        loss, _, _ = self._run_step(batch, batch_idx, step_name="train")
-        return loss
-
-    def validation_step(self, batch: SegmentData, batch_idx):
-        _, y_pred, y_true = self._run_step(batch, batch_idx, step_name="val")
-        return y_pred, y_true
-
-    def test_step(self, batch: SegmentData, batch_idx):
-        _, y_pred, y_true = self._run_step(batch, batch_idx, step_name="test")
-        return y_pred, y_true
-
     def configure_optimizers(self):
-        optim_config = self.optim_config.copy()
-        unfrozen_params = [p for p in self.parameters() if p.requires_grad]
-        out = optim_config.build(unfrozen_params, total_steps=self.trainer.estimated_stepping_batches)
-        # A stock torch.optim.Adam (the reference recipe, defaults.py:126-141) is adopted in place by the fused
-        # Adam(+bf16 shadow) kernel; any other optimizer is left untouched.
+        trainable = [p for p in self.parameters() if p.requires_grad]
+        built = self.optim_config.copy().build(trainable, total_steps=self.trainer.estimated_stepping_batches)
+        # a stock torch.optim.Adam (the reference recipe, defaults.py:126-141) is adopted in place by the fused
+        # Adam(+bf16 shadow) kernel; any other optimizer is left untouched
         from .optim import TribeAdam
 
-        opt = out["optimizer"] if isinstance(out, dict) else out
-        TribeAdam.adopt(opt, self.model)
-        return out
+        TribeAdam.adopt(built["optimizer"] if isinstance(built, dict) else built, self.model)
+        return built

@@ -6,6 +6,7 @@
 // (restated in oracle/tm_pearson.py); the final scipy.stats.pearsonr loop at algonauts2025/main.py:459-477.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tribe_b200.h"
 #include "tribe_internal.h"
@@ -370,6 +371,14 @@ extern "C" int tribe_pearson_stats(const float* pred, const float* target, int64
     if (pb > 64) pb = 64;
     const int64_t pblocks = (n_parcels + pb - 1) / pb;
     int64_t chunks = (148 * 8 + pblocks - 1) / pblocks;
+    // every chunk of a parcel block ends in fp64 atomics on the SAME 6 x pb addresses: narrow parcel shards (1000 / 8
+    // parcels per GPU) must not buy their parallelism with ~100-way atomic contention
+    static const int64_t chunk_cap = [] {
+      const char* e = getenv("TRIBE_PEARSON_MAX_CHUNKS");
+      const int v = e ? atoi(e) : 0;
+      return static_cast<int64_t>(v > 0 ? v : 24);
+    }();
+    if (chunks > chunk_cap) chunks = chunk_cap;
     const int64_t max_chunks = (n_b + kBdtUnroll - 1) / kBdtUnroll;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks > 65535) chunks = 65535;

@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "ptx_sm100.cuh"
@@ -37,10 +38,12 @@
 
 namespace tribe {
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, bool A_MN, bool B_MN, bool SMALL = false>
+__global__ void __launch_bounds__(kGemmThreads, SMALL ? 2 : 1) gemm_bf16_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = typename std::conditional<SMALL, GemmCfgSmall<BN>, GemmCfg<BN>>::type;
+  constexpr uint32_t kCols = SMALL ? 256 : kTmemCols;  // TMEM columns this CTA allocates (two CTAs per SM when SMALL)
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(!SMALL || 2 * BN <= 256, "two accumulators must fit half of TMEM");
   static_assert(!B_MN || BN % 64 == 0, "MN-major B tiles are loaded in 64-wide chunks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_holder, kTmemCols);
+    tmem_alloc(tmem_holder, kCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, kCols);
   }
 }
 
@@ -395,11 +398,11 @@ extern "C" int tribe_gemm_set_sm_limit(int32_t n_sms) {
   return TRIBE_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SMALL = false>
 static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = typename std::conditional<SMALL, GemmCfgSmall<BN>, GemmCfg<BN>>::type;
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, SMALL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
@@ -449,6 +452,13 @@ static int dispatch_major(const GemmKParams& kp, int grid, bool a_mn, bool b_mn,
   }
 }
 
+static int dispatch_major_small(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm<128, false, false, true>(kp, grid, s);
+  if (a_mn && !b_mn) return launch_gemm<128, true, false, true>(kp, grid, s);
+  if (!a_mn && b_mn) return launch_gemm<128, false, true, true>(kp, grid, s);
+  return launch_gemm<128, true, true, true>(kp, grid, s);
+}
+
 static int pick_block_n(const TribeGemm& g) {
   if (g.block_n) return g.block_n;
   const bool b_mn = g.b.mn_major != 0;
@@ -464,7 +474,17 @@ static int pick_block_n(const TribeGemm& g) {
 static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t k_sbo, uint32_t mn_lbo, uint32_t mn_sbo) {
   if (!g || !g->a.ptr || !g->b.ptr || !g->d) return set_error(TRIBE_EINVAL, "gemm: null pointer");
   if (g->m <= 0 || g->n <= 0 || g->k <= 0 || g->batch <= 0) return set_error(TRIBE_EINVAL, "gemm: empty problem");
-  const int bn = pick_block_n(*g);
+  int bn = pick_block_n(*g);
+  // short-K batched problems (attention P.V, dV, dQ, dK: 5-6 k-blocks per tile): 128-wide tiles, two CTAs per SM.
+  // Measured on B200 (profiles/r01_attention_microbench.txt): P.V 35.8 us vs 32.8 us with the 192-wide single-CTA tiles and
+  // no difference in the train step, so this stays opt-in (TRIBE_GEMM_SMALL=1).
+  static const int allow_small = [] {
+    const char* e = getenv("TRIBE_GEMM_SMALL");
+    return e ? atoi(e) : 0;
+  }();
+  const bool small = allow_small && g->block_n == 0 && !g->kgroup && (g->k + BK - 1) / BK <= 8 && (g->n % 128 == 0 || g->n <= 128) &&
+                     static_cast<int64_t>(g->batch) * ((g->m + BM - 1) / BM) * ((g->n + 127) / 128) >= 2 * num_sms();
+  if (small) bn = 128;
   if (bn != 128 && bn != 160 && bn != 192 && bn != 256) return set_error(TRIBE_EINVAL, "gemm: block_n must be 128/160/192/256");
   if (g->epilogue == TRIBE_EPI_ROPE) {
     if (!g->rope || g->rope_t <= 0 || g->head_dim % 32 || g->rope_dim % 32 || g->rope_dim > g->head_dim)
@@ -524,7 +544,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.vec_ok = vec ? 1 : 0;
 
   // ---- schedule: whole tiles round-robin; the ragged last wave is split along K when a workspace is provided
-  const int workers_max = use2 ? num_sms() / 2 : num_sms();  // persistent CTAs, or CTA pairs
+  const int workers_max = use2 ? num_sms() / 2 : (small ? 2 * num_sms() : num_sms());  // persistent CTAs, or CTA pairs
   const int grid = kp.num_tiles < workers_max ? kp.num_tiles : workers_max;
   kp.full_tiles = kp.num_tiles, kp.tail_units = 0, kp.split = 1, kp.kb_per = kp.num_kb;
   // (measured on B200: the tail split pays off for deep contractions — +15..18 % at K >= 9216 — and is neutral to
@@ -562,6 +582,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (use2) return dispatch_major2<256>(kp, 2 * grid, a_mn, b_mn, s);
+  if (small) return dispatch_major_small(kp, grid, a_mn, b_mn, s);
   switch (bn) {
     case 128: return dispatch_major<128>(kp, grid, a_mn, b_mn, s);
     case 160: return dispatch_major<160>(kp, grid, a_mn, b_mn, s);

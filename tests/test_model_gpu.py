@@ -313,3 +313,33 @@ def test_full_model_train_step_matches_reference_gradients(full_model, golden_di
     assert rel_l2(grads["encoder.layers.0.1.to_q.weight"][::193, ::211], torch.from_numpy(g["grad_l0_toq_sub"])) <= 5e-2
     assert rel_l2(grads["encoder.layers.15.1.ff.2.weight"][::193, ::811], torch.from_numpy(g["grad_l15_ff2_sub"])) <= 5e-2
     assert rel_l2(grads["encoder.layers.7.2.residual_scale"], torch.from_numpy(g["grad_residual_scale_l7"])) <= 5e-2
+
+
+# ----------------------------------------------------------------------------------------------- BASELINE.json config 1
+@pytest.mark.parametrize("subject_embedding", [False, True])
+def test_config1_single_subject_short_clips_match_oracle(subject_embedding):
+    """``grids/test_run``-shaped case (BASELINE.json configs[0]): ONE subject, short clips (T = 61 feature steps -> 20 TRs),
+    1000 parcels, tiny batch — forward, loss and readout gradient against the CPU oracle; the subject gather degenerates
+    to a single weight slice and the pooling windows are ragged (61 -> 20)."""
+    dims = {"text": (2, 96), "audio": (2, 40), "video": (1, 72)}
+    cfg_kw = dict(n_subjects=1, subject_embedding=subject_embedding)
+    torch.manual_seed(9)
+    model = FmriEncoder(dims, 1000, 20, FmriEncoderConfig(**cfg_kw), **SMALL)
+    oracle = O.OracleFmriEncoder(dims, 1000, 20, O.OracleConfig(**cfg_kw), **SMALL)
+    oracle.load_reference_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    spec = tuple((k, v[0], v[1]) for k, v in dims.items())
+    batch = synthetic_batch(batch_size=2, t=61, t_out=20, n_outputs=1000, n_subjects=1, seed=3, dims=spec)
+    assert int(batch.data["subject_id"].max()) == 0
+    model.train(), oracle.train()
+    y = model(batch)
+    loss = mse_loss(y, batch.data["fmri"])
+    loss.backward()
+    ref_loss, ref_y, *_ = O.run_step(oracle, as_oracle_batch(batch))
+    ref_loss.backward()
+    assert y.shape == (2, 1000, 20)
+    assert_pred_close(y.detach(), ref_y.detach())
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * ref_loss.item()
+    got, want = model.predictor.weights.grad.float().cpu(), oracle.predictor_weights.grad
+    assert rel_l2(got, want) <= 3e-2
+    with torch.no_grad():
+        assert_pred_close(model(batch, pool_outputs=False), oracle(as_oracle_batch(batch), pool_outputs=False))

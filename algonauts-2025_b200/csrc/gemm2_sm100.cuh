@@ -224,17 +224,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
       const uint32_t leader_tempty = acc ? leader_tempty1 : leader_tempty0;
 
       if (!w.partial) {
+        // GELU' epilogue (dgrad of FF2): the bf16 pre-activations of the NEXT chunk are requested before this chunk's
+        // accumulator is read, one chunk ahead of their use
+        const bool pre = p.epilogue == TRIBE_EPI_GELU_BWD && p.vec_ok && row_ok;
+        uint4 ax_cur[4], ax_nxt[4];
+        auto ld_aux = [&](int c, uint4 (&a)[4]) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + static_cast<long long>(row) * p.ld_aux + t.n0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = __ldg(ap + j);
+        };
+        if (pre && t.n0 + chalf * 32 + 32 <= p.n) ld_aux(chalf, ax_cur);
 #pragma unroll 1
         for (int c = chalf; c < BN / 32; c += 2) {
           const int col0 = t.n0 + c * 32;
           if (col0 >= p.n) break;
+          const bool have = pre && col0 + 32 <= p.n;
+          if (pre && c + 2 < BN / 32 && col0 + 64 + 32 <= p.n) ld_aux(c + 2, ax_nxt);
           uint32_t raw[32];
           tmem_ld_32x32(t_addr + c * 32, raw);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-          epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
+          epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos, have ? ax_cur : nullptr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ax_cur[j] = ax_nxt[j];
         }
         tc_fence_before();
         mbar_arrive_remote(leader_tempty);

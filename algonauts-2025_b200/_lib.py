@@ -97,6 +97,7 @@ def _build_locked(verbose: bool) -> None:
 
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+c_f64 = ctypes.c_double
 
 
 class TribeOperand(ctypes.Structure):
@@ -145,9 +146,9 @@ _SIGS = {
     "tribe_nce_loss": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp],
     "tribe_nce_grad": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp],
     "tribe_cast_bf16_f32": [c_vp, c_vp, c_i64, c_vp],
-    "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_i32, c_vp],
+    "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, c_vp],
     "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
-    "tribe_adam_hyper": [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp],
+    "tribe_adam_hyper": [c_vp, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_vp],
     "tribe_point_loss_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp, c_vp],
     "tribe_pearson_loss_finalize": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp],
     "tribe_pearson_loss_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_vp],

@@ -64,18 +64,21 @@ __global__ void set_floats_kernel(float* __restrict__ dst, int n, float v0, floa
 
 }  // namespace tribe
 
-extern "C" int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
-                               float weight_decay, int64_t step, int32_t max_blocks, void* stream) {
+extern "C" int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr, double beta1, double beta2,
+                               double eps, double weight_decay, int64_t step, int32_t max_blocks, void* stream) {
   using namespace tribe;
   if (!p || !g || !m || !v || n <= 0 || step <= 0) return set_error(TRIBE_EINVAL, "adam_step: bad arguments");
   const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v);
   if ((al & 15) || (reinterpret_cast<uintptr_t>(p_bf16) & 7)) return set_error(TRIBE_EINVAL, "adam_step: buffers must be 16-byte aligned (bf16: 8)");
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  // hyper-parameters arrive as doubles (Python floats) and the bias corrections are formed in fp64 like torch does
+  // (torch/optim/adam.py: bias_correction = 1 - beta ** step with Python floats): 1 - 0.999^k is ill-conditioned for small k
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  const float step_size = static_cast<float>(lr / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   adam_kernel<<<grid_for(n / 4 + 1, 256, max_blocks > 0 ? max_blocks : 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, beta1, beta2, step_size, inv_bc2_sqrt, eps, weight_decay, nullptr);
+      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, static_cast<float>(beta1), static_cast<float>(beta2), step_size, inv_bc2_sqrt,
+      static_cast<float>(eps), static_cast<float>(weight_decay), nullptr);
   TRIBE_CHECK_LAUNCH("adam_step");
   return TRIBE_OK;
 }
@@ -91,13 +94,15 @@ extern "C" int tribe_adam_step_dev(float* p, const float* g, float* m, float* v,
   return TRIBE_OK;
 }
 
-extern "C" int tribe_adam_hyper(float* hyper_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+extern "C" int tribe_adam_hyper(float* hyper_dev, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                                void* stream) {
   using namespace tribe;
   if (!hyper_dev || step <= 0) return set_error(TRIBE_EINVAL, "adam_hyper: bad arguments");
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-  set_floats_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hyper_dev, 6, beta1, beta2, static_cast<float>(static_cast<double>(lr) / bc1),
-                                                                        static_cast<float>(1.0 / sqrt(bc2)), eps, weight_decay, 0.f, 0.f);
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  set_floats_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hyper_dev, 6, static_cast<float>(beta1), static_cast<float>(beta2),
+                                                                        static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)),
+                                                                        static_cast<float>(eps), static_cast<float>(weight_decay), 0.f, 0.f);
   TRIBE_CHECK_LAUNCH("adam_hyper");
   return TRIBE_OK;
 }

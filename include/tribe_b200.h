@@ -245,15 +245,15 @@ int tribe_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* strea
  * `step` is the 1-based step count used for the bias corrections.  max_blocks > 0 bounds the grid (a step that runs
  * beside the backward GEMMs on a side stream should leave SM slots to them); 0 = fill the device.
  */
-int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int64_t step, int32_t max_blocks, void* stream);
+int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int64_t step, int32_t max_blocks, void* stream);
 /* The same step with its scalars read from DEVICE memory — hyper[6] = {beta1, beta2, lr / (1 - beta1^step),
  * 1 / sqrt(1 - beta2^step), eps, weight_decay} — so that a captured CUDA graph of the whole train step replays with the
  * scheduler's current lr / momentum (OneCycleLR cycles both per batch).  tribe_adam_hyper fills such a block from the
  * host-side values (one 1-block launch; the bias corrections are computed in fp64 on the host like torch does). */
 int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, int32_t max_blocks,
                         void* stream);
-int tribe_adam_hyper(float* hyper_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+int tribe_adam_hyper(float* hyper_dev, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Alternative training losses (grid: algonauts2025/grids/run_ensemble.py:29; built by modeling_utils/losses/base.py:

@@ -11,8 +11,6 @@ weights and gradients.  All buffers are torch allocations; all math is in ``libt
 """
 from __future__ import annotations
 
-import math
-
 import torch
 
 from . import ops

@@ -9,7 +9,6 @@ maximize, capturable, foreign parameters) falls through to the stock implementat
 from __future__ import annotations
 
 import ctypes
-import math
 
 import torch
 

@@ -293,7 +293,7 @@ def run_ours(args):
     from algonauts2025_b200 import ops, parallel
     from algonauts2025_b200.model import FmriEncoderConfig
     from algonauts2025_b200.pl_module import BrainModule
-    from algonauts2025_b200.segment import DevicePrefetcher, SegmentData, synthetic_batch
+    from algonauts2025_b200.segment import DevicePrefetcher, synthetic_batch
     from algonauts2025_b200.trainer import MiniTrainer, default_optimizer
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))

@@ -108,6 +108,7 @@ class TribeAdam(torch.optim.Adam):
         param group and the same step count (and, with ``split``, the same run class) share one launch.  ``only``:
         optional (lo, hi) window of the flat buffer (one gradient bucket)."""
         name_of = {id(p): n for n, p in flat.params.items()}
+        flat.ensure_grad()  # gradients assigned by hand (no engine backward yet) are copied into the flat buffer below
         todo = []
         for gi, group in enumerate(self.param_groups):
             for p in group["params"]:

@@ -158,6 +158,8 @@ _SIGS = {
     "tribe_mean_lastdim": [c_vp, c_vp, c_i64, c_i64, c_vp],
     "tribe_retrieval_ranks": [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "tribe_swa_update": [c_vp, c_vp, c_i64, c_i64, c_vp],
+    "tribe_scale_dev": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "tribe_memset_zero": [c_vp, c_i64, c_vp],
     "tribe_transpose_last2": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["tribe_last_error", "tribe_abi_version", "tribe_launch_count"])

@@ -165,6 +165,20 @@ __global__ void __launch_bounds__(256) pearson_loss_bwd_kernel(const float* __re
   }
 }
 
+// dst[i] = src[i] * scalar[0]  (autograd's upstream gradient of a fused loss is a DEVICE scalar: no host read)
+__global__ void __launch_bounds__(256) scale_dev_kernel(const float* __restrict__ src, const float* __restrict__ scalar, float* __restrict__ dst,
+                                                        int64_t n) {
+  const float a = __ldg(scalar);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const int64_t nvec = vec ? (n >> 2) : 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(src) + i);
+    __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(x.x * a, x.y * a, x.z * a, x.w * a));
+  }
+  for (int64_t i = (nvec << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i] * a;
+}
+
 }  // namespace tribe
 
 using namespace tribe;
@@ -204,5 +218,20 @@ extern "C" int tribe_pearson_loss_bwd(const float* pred, const float* target, co
   pearson_loss_bwd_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, coef, upstream, scale,
                                                                                                                grad, n, n_parcels, t_len);
   TRIBE_CHECK_LAUNCH("pearson_loss_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_scale_dev(const float* src, const float* scalar_dev, float* dst, int64_t n, void* stream) {
+  if (!src || !scalar_dev || !dst || n <= 0) return set_error(TRIBE_EINVAL, "scale_dev: bad arguments");
+  scale_dev_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, scalar_dev, dst, n);
+  TRIBE_CHECK_LAUNCH("scale_dev");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_memset_zero(void* ptr, int64_t n_bytes, void* stream) {
+  if (!ptr || n_bytes < 0) return set_error(TRIBE_EINVAL, "memset_zero: bad arguments");
+  if (n_bytes == 0) return TRIBE_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(n_bytes), reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_cuda_error(e, "memset_zero");
   return TRIBE_OK;
 }

@@ -410,7 +410,7 @@ class Engine:
         dxb_cur, dxb_nxt = ws.dxb[0], ws.dxb[1]
         gfin = tgt("encoder.final_norm.g")
         if not acc["encoder.final_norm.g"]:
-            gfin.zero_()
+            ops.zero_(gfin)
 
         if plan.mode == "latents":
             d_xnf = ws.dtmp
@@ -436,7 +436,7 @@ class Engine:
             if m.predictor.bias is not None:
                 gB = tgt("predictor.bias")
                 if not acc["predictor.bias"]:
-                    gB.zero_()
+                    ops.zero_(gB)
                 ops.subject_bias_grad(dyT, plan.subjects, gB, B, Tq, O, S)
             if plan.pool:
                 d_xnf = ws.dtmp
@@ -456,11 +456,11 @@ class Engine:
             atomics = (f"{a}.0.0.g", f"{a}.2.residual_scale", f"{f}.0.0.g", f"{f}.2.residual_scale")  # adjacent in the flat layout
             if not any(acc[n] for n in atomics):
                 lo, hi = fl.offsets[atomics[0]], fl.offsets[atomics[-1]] + H
-                fl.grad[lo:hi].zero_()  # one fill per layer for every atomically accumulated small gradient
+                ops.zero_(fl.grad[lo:hi])  # one fill per layer for every atomically accumulated small gradient
             else:
                 for n in atomics:
                     if not acc[n]:
-                        gs[n].zero_()
+                        ops.zero_(gs[n])
             # ================= feed-forward sub-layer (x_out = FF(norm(x_in)) + x_in * rs)
             w2, w1 = self._w16(f"{f}.1.ff.2.weight"), self._w16(f"{f}.1.ff.0.0.weight")
             # d_hpre = (dx @ W2) * gelu'(hpre)          W2 (H, F): MN-major B (N = F contiguous, K = H rows)
@@ -526,12 +526,12 @@ class Engine:
         # ---- encoder input: positional embedding, projectors
         gpos = tgt("time_pos_embed")
         if not acc["time_pos_embed"]:
-            gpos.zero_()
+            ops.zero_(gpos)
         ops.colsum(dx_cur.view(B, T * H), gpos.view(-1)[: T * H], accumulate=acc["time_pos_embed"])
         if hasattr(m, "subject_embed"):
             gE = tgt("subject_embed.weight")
             if not acc["subject_embed.weight"]:
-                gE.zero_()
+                ops.zero_(gE)
             gE.index_add_(0, plan.subjects, dx_cur.view(B, T, H).sum(1))
         if not plan.x_input:
             mods = list(m.feature_dims.keys())

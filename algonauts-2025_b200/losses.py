@@ -22,7 +22,7 @@ class _MseFn(torch.autograd.Function):
         if not ctx.has_grad:
             return None, None
         (grad,) = ctx.saved_tensors
-        return grad * g, None
+        return ops.scale_dev(grad, g), None
 
 
 def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -50,7 +50,7 @@ class _PointFn(torch.autograd.Function):
         if not ctx.has_grad:
             return None, None, None, None
         (grad,) = ctx.saved_tensors
-        return grad * g, None, None, None
+        return ops.scale_dev(grad, g), None, None, None
 
 
 class _PearsonFn(torch.autograd.Function):

@@ -66,7 +66,7 @@ class MultidimPearsonCorrCoef(nn.Module):
         return mean[0]
 
     def reset(self) -> None:
-        self.stats.zero_()
+        ops.zero_(self.stats) if self.stats.is_cuda else self.stats.zero_()
 
     def forward(self, preds, target):
         self.update(preds, target)
@@ -123,8 +123,8 @@ class GroupedMetric(nn.Module):
         return out
 
     def reset(self) -> None:
-        self.stats.zero_()
-        self.bad_group.zero_()
+        ops.zero_(self.stats) if self.stats.is_cuda else self.stats.zero_()
+        ops.zero_(self.bad_group) if self.bad_group.is_cuda else self.bad_group.zero_()
 
     def __repr__(self) -> str:
         return "GroupedMetric(MultidimPearsonCorrCoef)"

@@ -427,3 +427,20 @@ def attn_scores(a, a_off: int, b, b_off: int, n_batch: int, T: int, heads: int, 
     _need(a, torch.bfloat16, "attn a"), _need(b, torch.bfloat16, "attn b"), _need(out, torch.bfloat16, "attn out")
     _run("tribe_attn_scores", _ptr(a), a.shape[-1], a_off, _ptr(b), b.shape[-1], b_off, n_batch, T, heads, dh, float(scale),
          0 if p_in is None else 1, _ptr(p_in), _ptr(out), out.shape[-1], _stream())
+
+
+def zero_(t) -> None:
+    """Stream-ordered zero fill of a contiguous CUDA tensor (cudaMemsetAsync through the C ABI; capturable)."""
+    if not t.is_contiguous():
+        raise TribeError("zero_: tensor must be contiguous")
+    if t.numel():
+        _run("tribe_memset_zero", _ptr(t), t.numel() * t.element_size(), _stream())
+
+
+def scale_dev(src, scalar):
+    """src * scalar with ``scalar`` a one-element CUDA tensor (no host read)."""
+    _need(src, torch.float32, "scale src")
+    s = scalar.detach().to(src.device, torch.float32).reshape(1).contiguous()
+    out = torch.empty_like(src)
+    _run("tribe_scale_dev", _ptr(src), _ptr(s), _ptr(out), src.numel(), _stream())
+    return out

@@ -272,6 +272,11 @@ int tribe_pearson_loss_finalize(const double* stats, int64_t n_parcels, int32_t 
 int tribe_pearson_loss_bwd(const float* pred, const float* target, const float* coef, const float* upstream, int32_t reduction_mean,
                            float* grad, int64_t n, int64_t n_parcels, int64_t t_len, void* stream);
 
+/* dst[i] = src[i] * scalar_dev[0]: backward of the fused losses (autograd hands the upstream gradient as a device
+ * scalar); tribe_memset_zero: stream-ordered zero fill of gradient slices / statistics blocks (no kernel). */
+int tribe_scale_dev(const float* src, const float* scalar_dev, float* dst, int64_t n, void* stream);
+int tribe_memset_zero(void* ptr, int64_t n_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * The steps either side of the path.
  */

@@ -143,6 +143,33 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restr
   }
 }
 
+// Warp-per-row variant (dim = 128 * NV): the whole row lives in one warp's registers, every global load of the row is
+// issued before the first use and the reduction is five shuffles — no block barrier between the load and store phases,
+// eight independent rows in flight per block.
+template <int NV>
+__global__ void __launch_bounds__(256) scalenorm_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                                 __nv_bfloat16* __restrict__ y, float* __restrict__ rnorm, int64_t rows) {
+  constexpr int dim = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const float scale_g = sqrtf(static_cast<float>(dim)) * __ldg(g);
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    float4 c[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c[i] = __ldg(xr + lane + i * 32);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
+    ss = warp_sum(ss);
+    const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0 && rnorm) rnorm[row] = rn;
+    const float sc = rn * scale_g;
+    uint2* yr = reinterpret_cast<uint2*>(y + row * dim);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) yr[lane + i * 32] = make_uint2(pack_bf16x2(c[i].x * sc, c[i].y * sc), pack_bf16x2(c[i].z * sc, c[i].w * sc));
+  }
+}
+
 // Backward tail of one pre-norm residual sub-layer  x_out = branch(ScaleNorm(x_in)) + x_in * rs :
 //   dot      = sum_c d_xn[c] * x_in[c] * rnorm
 //   dx_in[c] = sqrt(dim) g rnorm (d_xn[c] - x_in[c] rnorm dot) + dy_out[c] * rs[c]
@@ -533,9 +560,20 @@ extern "C" int tribe_ingest_features(const void* x, int32_t src_dtype, int64_t B
 
 extern "C" int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, void* stream) {
   if (!x || !g || !y_bf16 || rows <= 0 || dim <= 0 || dim % 4) return set_error(TRIBE_EINVAL, "scalenorm_fwd: bad arguments (dim % 4)");
-  const int grid = grid_for(rows, 1, kMaxBlocks * 4);
-  scalenorm_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, g, reinterpret_cast<__nv_bfloat16*>(y_bf16), rnorm, rows,
-                                                                                  static_cast<int>(dim));
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(y_bf16) & 7)) == 0;
+  const int wgrid = grid_for(rows, 8, 148 * 2);
+  if (al && dim == 3072) {
+    scalenorm_fwd_warp_kernel<24><<<wgrid, 256, 0, st_>>>(x, g, yb, rnorm, rows);
+  } else if (al && dim == 384) {
+    scalenorm_fwd_warp_kernel<3><<<wgrid, 256, 0, st_>>>(x, g, yb, rnorm, rows);
+  } else if (al && dim == 1024) {
+    scalenorm_fwd_warp_kernel<8><<<wgrid, 256, 0, st_>>>(x, g, yb, rnorm, rows);
+  } else {
+    const int grid = grid_for(rows, 1, kMaxBlocks * 4);
+    scalenorm_fwd_kernel<<<grid, 256, 0, st_>>>(x, g, yb, rnorm, rows, static_cast<int>(dim));
+  }
   TRIBE_CHECK_LAUNCH("scalenorm_fwd");
   return TRIBE_OK;
 }

@@ -304,6 +304,12 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
     contrastive = bool(args.contrastive)
 
+    # The Pearson-eval leg is an independent metric of a bandwidth kernel "timed alone": it runs FIRST, before the train legs
+    # put the board under its power cap (tools/pearson_variance_probe.py: 6.1-6.3 TB/s on a cool chip, 5.5 TB/s right after
+    # 20 s of GEMM load with the SM clock at 1342 MHz — the HBM peak in MEASURED_PEAKS.json is a cool-chip figure too).
+    pe = pearson_eval_leg(rank, world, max(K, 5), W, measured_peaks(), world == 1 and not args.no_cpu_baseline) if not args.no_pearson else None
+    torch.cuda.empty_cache()
+
     torch.manual_seed(33)  # identical seeds on every rank -> identical weights and dropout masks (main.py:492-495)
     cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3, feature_aggregation="cat", layer_aggregation="cat", contrastive_enabled=contrastive)
     model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
@@ -457,7 +463,6 @@ def run_ours(args):
         line["eval_predict"] = ev
     del model
     torch.cuda.empty_cache()
-    pe = pearson_eval_leg(rank, world, max(K, 5), W, measured_peaks(), world == 1 and not args.no_cpu_baseline) if not args.no_pearson else None
     if rank == 0:
         if pe is not None:
             line["pearson_eval"] = pe

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(CSRC, "libtribe_b200.so")
-SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu", "contrastive.cu", "pool.cu", "optim.cu", "losses.cu", "aux.cu"]
+SOURCES = ["core.cu", "gemm_sm100.cu", "elementwise.cu", "reduce.cu", "contrastive.cu", "pool.cu", "optim.cu", "losses.cu", "aux.cu", "xgpu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               f"-I{INCLUDE}", f"-I{CSRC}"]
 
@@ -117,6 +117,19 @@ class TribeGemm(ctypes.Structure):
                 ("block_n", c_i32), ("splitk_ws", c_vp), ("splitk_ws_bytes", c_i64)]
 
 
+XGPU_MAX_WORLD, XGPU_SLOTS = 16, 64
+
+
+class TribeXgpuPeers(ctypes.Structure):
+    _fields_ = [("ptr", c_vp * XGPU_MAX_WORLD)]
+
+
+class TribeShardedAdam(ctypes.Structure):
+    _fields_ = [("param", c_vp), ("m", c_vp), ("v", c_vp), ("hyper", c_vp), ("grad_mc", c_vp), ("shadow_mc", c_vp), ("param_mc", c_vp),
+                ("grad_peer", TribeXgpuPeers), ("shadow_peer", TribeXgpuPeers), ("param_peer", TribeXgpuPeers), ("n", c_i64),
+                ("world", c_i32), ("rank", c_i32), ("bcast_master", c_i32), ("max_blocks", c_i32)]
+
+
 # name -> (argtypes); every function returns int except the three introspection calls.
 _SIGS = {
     "tribe_gemm_bf16": [ctypes.POINTER(TribeGemm), c_vp],
@@ -149,6 +162,8 @@ _SIGS = {
     "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, c_vp],
     "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
     "tribe_adam_hyper": [c_vp, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_vp],
+    "tribe_sharded_adam_step": [ctypes.POINTER(TribeShardedAdam), c_vp],
+    "tribe_xgpu_barrier": [ctypes.POINTER(TribeXgpuPeers), c_i32, c_i32, c_i32, c_vp, c_f64, c_vp],
     "tribe_point_loss_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp, c_vp],
     "tribe_pearson_loss_finalize": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp],
     "tribe_pearson_loss_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_vp],

@@ -77,6 +77,7 @@ class FlatParams:
         self._sig = None
         self.param_ids = {id(p) for p in self.params.values()}
         self.opt_steps = 0
+        self.sharded = None  # parallel.ShardedStep: fp32 masters / Adam moments are only current on their owner rank
         import weakref
 
         _FLATS.append(weakref.ref(self))
@@ -108,8 +109,31 @@ class FlatParams:
             self.bf16 = torch.empty(self.total, device=self.device, dtype=torch.bfloat16)
             self._sig = None
         if sig != self._sig:
+            if self.sharded is not None:
+                # rank-sharded optimizer: a foreign in-place change (load_state_dict, SWA swap — the same calls on every
+                # rank) must not be cast from masters that are stale outside this rank's slices
+                self.sharded.gather_masters()
             ops.cast_f32_bf16(self.flat, self.bf16)
             self._sig = sig
+
+    def rehome(self, alloc):
+        """Move the flat fp32 masters, the gradient buffer and the bf16 shadow into buffers from ``alloc(numel, dtype)``
+        (symmetric memory for the NVLink step tail, parallel.ShardedStep); every parameter / gradient view follows."""
+        flat, grad, bf16 = alloc(self.total, torch.float32), alloc(self.total, torch.float32), alloc(self.total, torch.bfloat16)
+        flat.copy_(self.flat)
+        grad.zero_()
+        if self.bf16 is not None:
+            bf16.copy_(self.bf16)
+        else:
+            ops.cast_f32_bf16(flat, bf16)
+            self._sig = (sum(p._version for p in self.params.values()), self.opt_steps)
+        versions = sum(p._version for p in self.params.values())
+        self.flat, self.grad, self.bf16 = flat, grad, bf16
+        for n, p in self.params.items():
+            p.data = self.flat[self.offsets[n]: self.offsets[n] + p.numel()].view(p.shape)
+            p.grad = None
+        if self._sig is not None:  # re-pointing .data must not look like a weight change
+            self._sig = (self._sig[0] + sum(p._version for p in self.params.values()) - versions, self._sig[1])
 
 
 class Workspace:

@@ -41,9 +41,11 @@ class GraphedTrainStep:
         if model is None or not hasattr(model, "_draw_dropout") or not isinstance(tr.optimizer, TribeAdam):
             return False
         if tr.grad_sync is not None and not tr.graph_collectives:
-            from .parallel import world
+            from .parallel import ShardedStep, world
 
-            if world()[1] > 1:  # NCCL all-reduces inside the step: captured only when asked to
+            # NCCL all-reduces inside the step are captured only when asked to; the NVLink step tail (our kernels, no
+            # NCCL call) always is
+            if world()[1] > 1 and not isinstance(tr.grad_sync, ShardedStep):
                 return False
         return all(torch.is_tensor(v) and v.is_cuda for v in batch.data.values())
 
@@ -133,6 +135,8 @@ class GraphedTrainStep:
         tr = self.trainer
         tr.optimizer.prepare_replay(entry["runs"])
         entry["graph"].replay()
+        if hasattr(tr.grad_sync, "masters_stale"):
+            tr.grad_sync.masters_stale = tr.grad_sync.state_stale = True
         for p, g in entry["grads"]:
             p.grad = g
         _lib.REPLAYED_LAUNCHES += entry["launches"]
@@ -143,4 +147,4 @@ class GraphedTrainStep:
         flags = tr.module.model.__dict__.get("_subject_flags")
         if flags is not None and int(flags[1].item()) != 0:
             tr.module.model.flush_subject_check()
-        return entry["loss"]
+        return entry["loss"].clone()  # the graph's static output buffer is overwritten by the next replay

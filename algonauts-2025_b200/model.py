@@ -253,6 +253,12 @@ class FmriEncoder(nn.Module):
     def device(self):
         return self._engine.device
 
+    def state_dict(self, *args, **kwargs):
+        flat = self._engine.flat
+        if flat is not None and flat.sharded is not None:
+            flat.sharded.gather_masters()  # collective: rank-sharded optimizer keeps fp32 masters on their owner
+        return super().state_dict(*args, **kwargs)
+
     # -- forward paths ----------------------------------------------------------------------------------------------
     def _draw_dropout(self) -> list[str]:
         """model.py:134-141 verbatim in behaviour: one CPU ``torch.rand(1)`` per modality *evaluated before*

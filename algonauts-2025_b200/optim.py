@@ -17,6 +17,8 @@ from ._lib import check
 
 
 class TribeAdam(torch.optim.Adam):
+    _tribe_sharded = None  # parallel.ShardedStep when the step tail runs rank-sharded over NVLink
+
     @classmethod
     def adopt(cls, optimizer: torch.optim.Optimizer, model) -> torch.optim.Optimizer:
         """Turn a stock ``torch.optim.Adam`` instance into a TribeAdam in place (no-op for other optimizers)."""
@@ -210,6 +212,47 @@ class TribeAdam(torch.optim.Adam):
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         self._apply_runs(flat, self._plan_runs(flat, split=capturing, only=lo_hi), capturing, stream, max_blocks)
         self._early = (getattr(self, "_early", None) or []) + [tuple(lo_hi)]
+
+    @torch.no_grad()
+    def step_bucket_sharded(self, idx: int) -> None:
+        """Data-parallel step of gradient bucket ``idx`` through ``parallel.ShardedStep`` on the CURRENT stream: the
+        fused (in-switch gradient reduction -> Adam -> shadow multicast) kernel on the part of every run this rank owns.
+        Host bookkeeping (step counters, hyper-parameter slots) covers the whole bucket on every rank."""
+        sh = self._tribe_sharded
+        flat = self._flat()
+        if not self._fusable(flat):
+            raise _lib.TribeError("ShardedStep needs the fused TribeAdam path (no amsgrad / maximize / foreign parameters)")
+        self._buffers(flat)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing and getattr(self, "_graph_runs", None) is None:
+            raise _lib.TribeError("TribeAdam.step_bucket_sharded() inside a CUDA graph capture needs graph_begin()")
+        lib = _lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lo_hi = flat.bucket_ranges[idx]
+        own_lo, own_hi = sh.owned[idx][sh.rank]
+        for run in self._plan_runs(flat, split=capturing, only=lo_hi):
+            slot = flat.adam_slot.setdefault(run["lo"], len(flat.adam_slot))
+            hyper = flat.adam_hyper[slot].data_ptr()
+            if capturing:
+                self._graph_runs.append(run)  # prepare_replay() advances the counters and refreshes the slot
+            else:
+                for p in run["params"]:
+                    self.state[p]["step"] += 1
+                group = self.param_groups[run["group"]]
+                beta1, beta2 = (float(b) for b in group["betas"])
+                check(lib.tribe_adam_hyper(ctypes.c_void_p(hyper), float(group["lr"]), beta1, beta2, float(group["eps"]),
+                                           float(group["weight_decay"]), run["k"] + 1, stream), "tribe_adam_hyper")
+            a, b = max(run["lo"], own_lo), min(run["hi"], own_hi)
+            if b > a:
+                for x, y, bcast in sh.pieces(a, b):
+                    sh.launch(x, y, bcast, hyper)
+        self._early = (getattr(self, "_early", None) or []) + [tuple(lo_hi)]
+
+    def state_dict(self):
+        sh = getattr(self, "_tribe_sharded", None)
+        if sh is not None:
+            sh.gather_optimizer_state()  # collective: Adam moments live on their owner rank only
+        return super().state_dict()
 
     @torch.no_grad()
     def step(self, closure=None):

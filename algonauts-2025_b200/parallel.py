@@ -115,6 +115,223 @@ class StepOverlap:
 GradAllReduce = StepOverlap  # the data-parallel use of the same pipeline
 
 
+# ------------------------------------------------------------------------------------------------ NVLink step tail
+BF16_ONLY = ("projectors.", "contrastive_heads.", "encoder.layers.")  # ... whose ".weight" matrices the kernels read as bf16
+
+
+def _fp32_consumed(name: str) -> bool:
+    """True for parameters the kernels read as fp32 (biases, norm gains, residual scales, positional / subject
+    embeddings, readout bias): the owner broadcasts their fp32 value; weight matrices travel as bf16 shadow only."""
+    if name == "predictor.weights":
+        return False
+    return not (name.startswith(BF16_ONLY) and name.endswith(".weight"))
+
+
+class ShardedStep:
+    """Data-parallel step tail on NVLink 5 / NVSwitch with OUR kernel instead of NCCL all-reduce + replicated Adam
+    (reference: Lightning DDP + ``torch.optim.Adam`` on every rank, algonauts2025/main.py:388-394).
+
+    The flat gradient buffer, the bf16 shadow and the fp32 masters are re-homed into symmetric memory
+    (``torch.distributed._symmetric_memory``: same allocation on every rank, peer-mapped, NVLS multicast mapping when the
+    fabric has one).  Every bucket of the flat layout (0 = head, 1..depth = encoder layers) is statically cut into
+    ``world`` contiguous slices; when ``engine.backward`` reports a bucket complete, a side stream runs
+
+        cross-rank barrier (all ranks finished writing the bucket)  ->  ``tribe_sharded_adam_step`` on the owned slice:
+        ``multimem.ld_reduce`` (in-switch sum of all ranks' gradients) -> Adam -> ``multimem.st`` of the bf16 shadow
+        (and of the fp32 value for parameters the kernels read as fp32) into every rank's copy,
+
+    beside the backward GEMMs of the earlier layers; ``finish_step`` closes with one more barrier and joins the stream.
+    No NCCL call is part of the step, so whole steps are captured in CUDA graphs for N > 1 as well.
+
+    Consequences: Adam moments exist only on the owner of a slice, and the fp32 master of weight matrices is current
+    only there; ``gather_masters()`` / ``gather_optimizer_state()`` (collective, lazy — ``state_dict()`` calls them)
+    complete them.  Reduction order: one in-switch add per element (NVLS) or rank order 0..N-1 (peer-load variant); the
+    mean is the sum times 1/N.  Every rank receives the SAME bits for every parameter by construction.
+    """
+
+    FINAL_SLOT = 40
+
+    def __init__(self, model, optimizer, group=None, max_blocks: int = 0, use_multicast: bool | None = None, timeout_s: float = 30.0):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.model, self.optimizer = model, optimizer
+        self.engine = model._engine
+        self.engine._check_flat()
+        flat = self.flat = self.engine.flat
+        self.rank, self.world = world()
+        if self.world < 2 or self.world > _lib.XGPU_MAX_WORLD:
+            raise _lib.TribeError(f"ShardedStep needs 2..{_lib.XGPU_MAX_WORLD} ranks, got {self.world}")
+        if not hasattr(optimizer, "step_bucket_sharded"):
+            raise _lib.TribeError("ShardedStep needs a TribeAdam optimizer (TribeAdam.adopt)")
+        self.group = group if group is not None else dist.group.WORLD
+        self.max_blocks, self.timeout_s = max_blocks, timeout_s
+        dev = flat.device
+        flat.rehome(lambda n, dtype: symm.empty(n, dtype=dtype, device=dev))
+        self.flags = symm.empty(_lib.XGPU_SLOTS * _lib.XGPU_MAX_WORLD, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        torch.cuda.synchronize(dev)
+        self.handles = {k: symm.rendezvous(t, self.group) for k, t in (("grad", flat.grad), ("bf16", flat.bf16), ("flat", flat.flat), ("flags", self.flags))}
+        mc = all(int(self.handles[k].multicast_ptr) != 0 for k in ("grad", "bf16", "flat"))
+        self.multicast = mc if use_multicast is None else (bool(use_multicast) and mc)
+        self.err = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._peers = {k: [int(x) for x in h.buffer_ptrs] for k, h in self.handles.items()}
+        self._flag_peers = _lib.TribeXgpuPeers()
+        for r in range(self.world):
+            self._flag_peers.ptr[r] = self._peers["flags"][r]
+        self._ctypes = ctypes
+        # static ownership: bucket b = [s, e) -> rank r owns [s + r * c, min(e, s + (r + 1) * c)), c a multiple of 8 elements
+        self.owned = []
+        for s, e in flat.bucket_ranges:
+            c = -(-(e - s) // self.world)
+            c = (c + 7) // 8 * 8
+            self.owned.append([(min(e, s + r * c), min(e, s + (r + 1) * c)) for r in range(self.world)])
+        # maximal flat ranges of parameters the kernels read as fp32
+        self.bcast = []
+        for n in sorted(flat.offsets, key=flat.offsets.get):
+            if _fp32_consumed(n):
+                lo = flat.offsets[n]
+                hi = lo + (flat.params[n].numel() + 63) // 64 * 64
+                if self.bcast and self.bcast[-1][1] == lo:
+                    self.bcast[-1][1] = hi
+                else:
+                    self.bcast.append([lo, hi])
+        self.stream = torch.cuda.Stream(dev)
+        self.counts, self.passes, self.head_passes = {}, 1, 0
+        self.masters_stale = self.state_stale = False
+        self.engine.comm = self
+        flat.sharded = self
+        optimizer._tribe_sharded = self
+        dist.barrier(group=self.group)
+
+    # -------------------------------------------------------------------------------------------- kernel plumbing
+    def barrier(self, slot: int) -> None:
+        from . import _lib
+
+        st = self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().tribe_xgpu_barrier(self._ctypes.byref(self._flag_peers), self.rank, self.world, slot,
+                                                  self._ctypes.c_void_p(self.err.data_ptr()), float(self.timeout_s), st), "tribe_xgpu_barrier")
+
+    def pieces(self, lo: int, hi: int):
+        """[lo, hi) cut at the borders of the fp32-consumed ranges -> (lo, hi, bcast) pieces."""
+        cuts = {lo, hi}
+        for a, b in self.bcast:
+            for x in (a, b):
+                if lo < x < hi:
+                    cuts.add(x)
+        cuts = sorted(cuts)
+        out = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            out.append((a, b, any(x <= a and b <= y for x, y in self.bcast)))
+        return out
+
+    def launch(self, lo: int, hi: int, bcast: bool, hyper_ptr: int) -> None:
+        """The fused reduce -> Adam -> multicast kernel on [lo, hi) of the flat layout (a range this rank owns)."""
+        from . import _lib
+
+        fl = self.flat
+        a = _lib.TribeShardedAdam()
+        a.param, a.m, a.v = fl.flat.data_ptr() + 4 * lo, fl.adam_m.data_ptr() + 4 * lo, fl.adam_v.data_ptr() + 4 * lo
+        a.hyper = hyper_ptr
+        if self.multicast:
+            a.grad_mc = int(self.handles["grad"].multicast_ptr) + 4 * lo
+            a.shadow_mc = int(self.handles["bf16"].multicast_ptr) + 2 * lo
+            a.param_mc = int(self.handles["flat"].multicast_ptr) + 4 * lo
+        for r in range(self.world):
+            a.grad_peer.ptr[r] = self._peers["grad"][r] + 4 * lo
+            a.shadow_peer.ptr[r] = self._peers["bf16"][r] + 2 * lo
+            a.param_peer.ptr[r] = self._peers["flat"][r] + 4 * lo
+        a.n, a.world, a.rank, a.bcast_master, a.max_blocks = hi - lo, self.world, self.rank, int(bcast), self.max_blocks
+        st = self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().tribe_sharded_adam_step(self._ctypes.byref(a), st), "tribe_sharded_adam_step")
+
+    # -------------------------------------------------------------------------------------------- step protocol
+    def begin_step(self, backward_passes: int | None = None, head_passes: int | None = None):
+        cfg = getattr(self.model, "config", None)
+        contrastive = bool(getattr(cfg, "contrastive_enabled", False))
+        self.passes = backward_passes if backward_passes is not None else (2 if contrastive else 1)
+        self.head_passes = head_passes if head_passes is not None else (len(getattr(self.model, "contrastive_heads", ())) if contrastive else 0)
+        self.counts = {}
+
+    def bucket_ready(self, idx: int):
+        self.counts[idx] = self.counts.get(idx, 0) + 1
+        if self.counts[idx] < self.passes + (self.head_passes if idx == 0 else 0):
+            return
+        main = torch.cuda.current_stream()
+        self.stream.wait_stream(main)  # this rank's contributions to the bucket are final
+        with torch.cuda.stream(self.stream):
+            self.barrier(idx)          # ... and so are every other rank's
+            self.optimizer.step_bucket_sharded(idx)
+        self.masters_stale = self.state_stale = True
+
+    def finish_step(self):
+        """All ranks have read every gradient and written every shadow slice: the next forward may start and the next
+        backward may overwrite the gradient buffer."""
+        with torch.cuda.stream(self.stream):
+            self.barrier(self.FINAL_SLOT)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def check(self) -> None:
+        """Raise if a cross-rank wait timed out (synchronises the device)."""
+        code = int(self.err.item())
+        if code:
+            from ._lib import TribeError
+
+            raise TribeError(f"cross-GPU barrier timed out at slot {code - 1} on rank {self.rank}: a peer never arrived")
+
+    # -------------------------------------------------------------------------------------------- lazy completion
+    def _gather(self, buffers) -> None:
+        for owners in self.owned:
+            for r, (lo, hi) in enumerate(owners):
+                if hi > lo:
+                    for buf in buffers:
+                        dist.broadcast(buf[lo:hi], src=dist.get_global_rank(self.group, r), group=self.group)
+
+    def gather_masters(self) -> None:
+        """Every rank receives the owners' fp32 masters (collective; called by ``state_dict()`` and before a re-cast)."""
+        if self.masters_stale:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self._gather([self.flat.flat])
+            self.masters_stale = False
+
+    def gather_optimizer_state(self) -> None:
+        """Every rank receives the owners' Adam moments (collective; called by ``TribeAdam.state_dict()``)."""
+        if self.state_stale and getattr(self.flat, "adam_m", None) is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self._gather([self.flat.adam_m, self.flat.adam_v])
+            self.state_stale = False
+
+
+def data_parallel(model, optimizer, group=None, prefer: str = "nvlink", **kw):
+    """The gradient-synchronisation object for ``trainer.MiniTrainer(grad_sync=...)``: ``ShardedStep`` (our NVLink kernel,
+    rank-sharded Adam) when symmetric memory can be set up on every rank, else ``GradAllReduce`` (NCCL all-reduce +
+    replicated Adam).  The decision is collective."""
+    rank, ws = world()
+    if ws == 1:
+        return None
+    ok, sync, why = 0, None, ""
+    if prefer == "nvlink" and hasattr(optimizer, "step_bucket_sharded"):
+        try:
+            sync = ShardedStep(model, optimizer, group=group, **kw)
+            ok = 1
+        except Exception as e:  # noqa: BLE001 - any failure of the symmetric-memory setup selects the NCCL path
+            why = f"{type(e).__name__}: {e}"
+    flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        return sync
+    if sync is not None:  # another rank failed: undo
+        model._engine.comm = None
+        model._engine.flat.sharded = None
+        optimizer._tribe_sharded = None
+    if rank == 0 and prefer == "nvlink":
+        print(f"[tribe] NVLink step tail unavailable ({why or 'a peer failed'}); using NCCL all-reduce", flush=True)
+    return GradAllReduce(model, group=group)
+
+
 # ------------------------------------------------------------------------------------------------ parcel-sharded eval
 def parcel_bounds(n_parcels: int, world_size: int) -> list[tuple[int, int]]:
     """Contiguous, balanced parcel shards (first ``n % G`` shards get one extra parcel)."""

@@ -256,6 +256,53 @@ int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf
 int tribe_adam_hyper(float* hyper_dev, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Data-parallel step tail over NVLink 5 / NVSwitch.  Replaces Lightning DDP's gradient all-reduce + the replicated
+ * optimizer step (algonauts2025/main.py:388-394, strategy "ddp_find_unused_parameters_true"; Adam recipe
+ * algonauts2025/grids/defaults.py:126-141).  The flat fp32 gradient buffer, the bf16 shadow and the fp32 masters of every
+ * rank live in SYMMETRIC memory (same size on every rank, peer-mapped, with an NVLS multicast mapping when the fabric
+ * offers one; allocated and exchanged by the host side, parallel.ShardedStep).
+ *
+ * tribe_sharded_adam_step: ONE kernel for the [lo, lo + n) range THIS rank owns —
+ *   g = (sum over ranks of grad[i]) / world   multimem.ld_reduce.add.f32 on grad_mc (in-switch reduction), or, when
+ *                                             grad_mc == NULL, loads from grad_peer[0..world) summed in rank order;
+ *   Adam on the local param / m / v (same arithmetic as tribe_adam_step_dev, scalars from the device block `hyper`);
+ *   bf16(param) -> every rank's shadow         multimem.st on shadow_mc, or stores to shadow_peer[r];
+ *   bcast_master != 0: the fp32 param too      (parameters the kernels read as fp32: biases, gains, residual scales,
+ *                                              positional embedding) — param_mc / param_peer.
+ * All pointers already include the offset `lo`; n is a multiple of 8 and every pointer 16-byte aligned.  m / v (and the
+ * fp32 master of ranges without bcast_master) are only current on the owner (gathered on demand for checkpoints).
+ * max_blocks bounds the grid (default 148: one 128-thread CTA per SM, co-resident with the persistent GEMM CTAs).
+ *
+ * tribe_xgpu_barrier: all `world` ranks meet at `slot` (< TRIBE_XGPU_SLOTS).  flags->ptr[r] = rank r's flag block
+ * (TRIBE_XGPU_SLOTS * TRIBE_XGPU_MAX_WORLD zero-initialised uint32 words of symmetric memory) as mapped into THIS
+ * process.  Release/acquire at system scope: writes made before the barrier by any rank's earlier kernels on the
+ * calling stream are visible to every rank's later kernels.  A rank that waits longer than timeout_s (<= 0: 30 s) stores
+ * 1 + slot into err_flag (device uint32, sticky) and proceeds instead of hanging the GPU.  Capturable in CUDA graphs.
+ */
+#define TRIBE_XGPU_MAX_WORLD 16
+#define TRIBE_XGPU_SLOTS 64
+typedef struct TribeXgpuPeers {
+  void* ptr[TRIBE_XGPU_MAX_WORLD];
+} TribeXgpuPeers;
+typedef struct TribeShardedAdam {
+  float* param;            /* local fp32 master, m, v of the owned range */
+  float* m;
+  float* v;
+  const float* hyper;      /* device: {beta1, beta2, lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step), eps, weight_decay} */
+  const float* grad_mc;    /* multicast addresses of the owned range (NULL: use the *_peer tables) */
+  void* shadow_mc;         /* bf16 */
+  float* param_mc;
+  TribeXgpuPeers grad_peer;   /* per-rank addresses of the owned range as mapped into this process */
+  TribeXgpuPeers shadow_peer;
+  TribeXgpuPeers param_peer;
+  int64_t n;
+  int32_t world, rank, bcast_master, max_blocks;
+} TribeShardedAdam;
+int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream);
+int tribe_xgpu_barrier(const TribeXgpuPeers* flags, int32_t rank, int32_t world, int32_t slot, uint32_t* err_flag, double timeout_s,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Alternative training losses (grid: algonauts2025/grids/run_ensemble.py:29; built by modeling_utils/losses/base.py:
  * 43-59 from torch.nn, PearsonLoss from modeling_utils/losses/losses.py:11-42).  Same contract as tribe_mse_fwd_bwd:
  * reduction="mean", loss_out[0] fp32, grad (optional) = grad_scale * dloss/dpred, partial >= 1024 doubles.

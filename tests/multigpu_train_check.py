@@ -1,8 +1,16 @@
-"""Data-parallel training check on real NCCL (run under torchrun on >= 2 GPUs): every rank trains on its own windows with
-bucketed gradient all-reduce (parallel.GradAllReduce); after a few Adam steps (a) all ranks hold bit-identical weights,
-(b) they match a single-process run on the concatenated batch (mean loss over equal shards = mean of per-rank gradients)
-up to bf16 noise, (c) with modality dropout the skipped projectors stay skipped on every rank, (d) the same holds when
-the steps are replayed as CUDA graphs that contain the all-reduces (--graph-comm path)."""
+"""Data-parallel training check on real NVLink / NCCL (run under torchrun on >= 2 GPUs; collected by
+tests/test_multigpu_gpu.py).  Every rank trains on its own windows.  Paths compared:
+
+  allreduce   parallel.GradAllReduce: bucketed NCCL all-reduce (mean) + replicated fused Adam
+  nvlink      parallel.ShardedStep: our fused kernel (in-switch multimem.ld_reduce -> rank-sharded Adam -> multimem.st of
+              the bf16 shadow), eager and replayed as whole-step CUDA graphs
+  p2p         the same kernel's peer-pointer variant (no multicast)
+
+After a few Adam steps (a) all ranks hold bit-identical weights (fp32 masters after the lazy gather AND the bf16 shadow
+the kernels read), (b) on 2 ranks every path gives the SAME bits as the all-reduce path (a two-term sum has one
+rounding; mean = x 0.5), on more ranks it agrees to fp32 rounding, (c) the all-reduce path matches a single-process run
+on the concatenated batch up to bf16 noise, (d) with modality dropout the skipped projectors stay skipped on every
+rank, (e) Adam moments gathered from their owners equal the replicated ones, (f) no cross-rank wait timed out."""
 import os
 import sys
 
@@ -36,35 +44,70 @@ def cat(batches):
     return SegmentData(data={k: torch.cat([b.data[k] for b in batches]) for k in batches[0].data}, segments=sum((b.segments for b in batches), []))
 
 
-def train(p_drop, sync, graphs, batches, steps=6):
+def train(p_drop, path, graphs, batches, steps=6, contrastive=False):
     torch.manual_seed(7), np.random.seed(7)
-    model = FmriEncoder(DIMS, 200, 25, FmriEncoderConfig(n_subjects=3, modality_dropout=p_drop), **SMALL)
+    cfg = FmriEncoderConfig(n_subjects=3, modality_dropout=p_drop, contrastive_enabled=contrastive)
+    model = FmriEncoder(DIMS, 200, 25, cfg, **SMALL)
     module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=1)
     opt, sched = default_optimizer(model.parameters(), total_steps=steps + 2, lr=1e-3, model=model)
-    gs = parallel.GradAllReduce(model) if sync else None
+    if path == "single":
+        gs = None
+    elif path == "allreduce":
+        gs = parallel.GradAllReduce(model)
+    else:
+        gs = parallel.ShardedStep(model, opt, use_multicast=(path == "nvlink"))
+        if path == "nvlink" and not gs.multicast and rank == 0:
+            print("note: no multicast mapping on this box — 'nvlink' runs the peer-pointer variant", flush=True)
     tr = MiniTrainer(module, opt, sched, grad_sync=gs, use_graphs=graphs, graph_collectives=True)
     losses = [tr.train_step(batches[i % len(batches)]).clone() for i in range(steps)]
     torch.cuda.synchronize()
-    return {k: v.detach().clone() for k, v in model.state_dict().items()}, torch.stack(losses), tr
+    if hasattr(gs, "check"):
+        gs.check()
+    shadow = model._engine.flat.bf16.clone()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}            # lazy gather of the fp32 masters
+    osd = opt.state_dict()["state"]                                                # ... and of the Adam moments
+    moments = torch.cat([osd[i]["exp_avg"].flatten() for i in sorted(osd)] + [osd[i]["exp_avg_sq"].flatten() for i in sorted(osd)])
+    return sd, torch.stack(losses), tr, shadow, moments.clone()
+
+
+def same_on_all_ranks(t, what):
+    others = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(others, t.contiguous())
+    assert all(torch.equal(o, others[0]) for o in others), f"ranks diverged: {what}"
 
 
 mine = [batch_of(100 + 10 * rank + i) for i in range(2)]
 everyone = [cat([batch_of(100 + 10 * r + i) for r in range(world)]) for i in range(2)]
-for p_drop, graphs in ((0.0, False), (0.5, False), (0.0, True), (0.5, True)):
-    sd, losses, tr = train(p_drop, True, graphs, mine)
-    flat = torch.cat([v.flatten().float() for v in sd.values()])
-    others = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(others, flat)
-    assert all(torch.equal(o, others[0]) for o in others), "ranks diverged"
-    if graphs:
-        assert tr._graphed.replays >= 1, "graphs with collectives were not replayed"
+for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
+    base_sd, base_losses, _, base_shadow, base_mom = train(p_drop, "allreduce", False, mine, contrastive=contrastive)
+    flat = torch.cat([v.flatten().float() for v in base_sd.values()])
+    same_on_all_ranks(flat, "allreduce masters")
     if p_drop == 0.0:
-        ref_sd, ref_losses, _ = train(0.0, False, False, everyone)
-        for k in sd:
-            d = float((sd[k].float() - ref_sd[k].float()).abs().max())
+        ref_sd, _, _, _, _ = train(0.0, "single", False, everyone)
+        for k in base_sd:
+            d = float((base_sd[k].float() - ref_sd[k].float()).abs().max())
             assert d <= 2e-3 + 2e-2 * float(ref_sd[k].float().abs().max()), (k, d)
-    dist.barrier()
-    if rank == 0:
-        print(f"dp train check p_drop={p_drop} graphs={graphs}: ranks bit-identical" + (", matches the single-process run on the concatenated batch" if p_drop == 0.0 else ""), flush=True)
+    for path, graphs in (("nvlink", False), ("nvlink", True), ("p2p", True), ("allreduce", True)):
+        if contrastive and path == "allreduce":
+            continue
+        sd, losses, tr, shadow, mom = train(p_drop, path, graphs, mine, contrastive=contrastive)
+        same_on_all_ranks(torch.cat([v.flatten().float() for v in sd.values()]), f"{path} masters")
+        same_on_all_ranks(shadow.view(torch.int16), f"{path} bf16 shadow")
+        if graphs:
+            assert tr._graphed.replays >= 1, f"{path}: graphs were not replayed"
+        for k in sd:
+            if world == 2:
+                assert torch.equal(sd[k], base_sd[k]), f"{path} graphs={graphs} p_drop={p_drop}: {k} differs from the all-reduce path"
+            else:
+                d = float((sd[k].float() - base_sd[k].float()).abs().max())
+                assert d <= 1e-5 + 1e-4 * float(base_sd[k].float().abs().max()), (path, k, d)
+        if world == 2:
+            assert torch.equal(shadow, base_shadow) and torch.equal(mom, base_mom) and torch.equal(losses, base_losses), (path, graphs)
+        dist.barrier()
+        if rank == 0:
+            print(f"dp train check p_drop={p_drop} contrastive={contrastive} path={path} graphs={graphs}: ranks bit-identical"
+                  + (", bit-equal to the all-reduce path" if world == 2 else ", equal to the all-reduce path within fp32 rounding"), flush=True)
+if rank == 0:
+    print("multi-GPU data-parallel training OK", flush=True)
 sys.stdout.flush()
-os._exit(0)  # graphs that captured NCCL work keep the communicator busy at teardown (see bench.py)
+os._exit(0)  # graphs that captured NCCL work keep the communicator busy at teardown

@@ -1,0 +1,113 @@
+"""torchrun probe of the NVLink step tail (parallel.ShardedStep / csrc/xgpu.cu): does symmetric memory come up, is there an
+NVLS multicast mapping, what do the barrier and the fused reduce->Adam->multicast kernel cost on one encoder-layer
+bucket (113 M parameters) as a function of the CTA count, multicast vs peer-pointer variant.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/xgpu_probe.py"""
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import algonauts2025_b200  # noqa: E402
+from algonauts2025_b200 import parallel  # noqa: E402
+from algonauts2025_b200.model import FmriEncoder, FmriEncoderConfig  # noqa: E402
+from algonauts2025_b200.trainer import default_optimizer  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+algonauts2025_b200.load()
+
+
+def log(*a):
+    if rank == 0:
+        print(*a, flush=True)
+
+
+torch.manual_seed(3)
+dims = {"text": (2, 3072), "audio": (2, 1024), "video": (2, 1408)}
+depth = int(os.environ.get("PROBE_DEPTH", "2"))
+model = FmriEncoder(dims, 1000, 100, FmriEncoderConfig(n_subjects=4), depth=depth)
+opt, _ = default_optimizer(model.parameters(), total_steps=100, model=model)
+t0 = time.perf_counter()
+sh = parallel.ShardedStep(model, opt)
+torch.cuda.synchronize()
+log(f"symmetric memory up in {time.perf_counter() - t0:.2f} s: world {world}, multicast {sh.multicast}, "
+    f"multicast_ptr grad {int(sh.handles['grad'].multicast_ptr):#x}, total {sh.flat.total / 1e6:.1f} M params")
+opt.init_all_state()
+fl = sh.flat
+fl.grad.normal_()
+torch.cuda.synchronize()
+dist.barrier()
+
+# barrier latency
+for _ in range(5):
+    sh.barrier(1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50):
+    sh.barrier(1)
+e1.record()
+torch.cuda.synchronize()
+sh.check()
+log(f"xgpu barrier: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per barrier kernel")
+
+# one encoder-layer bucket
+lo, hi = sh.owned[1][rank]
+hyper = torch.tensor([0.9, 0.999, 1e-4, 1.0, 1e-8, 0.0, 0, 0], device="cuda")
+n_own = hi - lo
+for mc in ([True, False] if sh.multicast else [False]):
+    sh.multicast = mc
+    for blocks in (16, 32, 74, 148, 296, 592):
+        sh.max_blocks = blocks
+        for _ in range(2):
+            sh.barrier(2)
+            for x, y, b in sh.pieces(lo, hi):
+                sh.launch(x, y, b, hyper.data_ptr())
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        reps = 5
+        for _ in range(reps):
+            for x, y, b in sh.pieces(lo, hi):
+                sh.launch(x, y, b, hyper.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        log(f"{'multicast' if mc else 'peer-ptr '} blocks {blocks:4d}: {ms:7.3f} ms for {n_own / 1e6:.1f} M owned params  "
+            f"local HBM {24 * n_own / ms / 1e6:7.1f} GB/s  reduced-in {4 * n_own / ms / 1e6:6.1f} GB/s  peer-read total {4 * n_own * (world - 1) / ms / 1e6:6.1f} GB/s")
+sh.check()
+# correctness of one launch against torch on the gathered gradients
+sh.multicast = all(int(sh.handles[k].multicast_ptr) != 0 for k in ("grad", "bf16", "flat"))
+sh.max_blocks = 0
+fl.grad.normal_()
+fl.adam_m.zero_(), fl.adam_v.zero_()
+torch.cuda.synchronize()
+dist.barrier()
+gs = [torch.empty_like(fl.grad[lo:hi]) for _ in range(world)]
+mine = fl.grad[lo:hi].clone()
+allg = [torch.empty(fl.total, device="cuda") for _ in range(world)]
+dist.all_gather(allg, fl.grad.clone())
+gmean = sum(a[lo:hi] for a in allg) / world
+p_before = fl.flat[lo:hi].clone()
+sh.barrier(3)
+for x, y, b in sh.pieces(lo, hi):
+    sh.launch(x, y, b, hyper.data_ptr())
+sh.barrier(4)
+torch.cuda.synchronize()
+m = gmean * (1 - 0.9)
+v = (1 - 0.999) * gmean * gmean
+want = p_before - 1e-4 * (m / (v.sqrt() * 1.0 + 1e-8))
+err = float((fl.flat[lo:hi] - want).abs().max())
+shadow_all = [torch.empty(fl.total, device="cuda", dtype=torch.bfloat16) for _ in range(world)]
+dist.all_gather(shadow_all, fl.bf16.clone())
+ok_shadow = all(torch.equal(s, shadow_all[0]) for s in shadow_all)
+own_ok = torch.equal(fl.bf16[lo:hi], fl.flat[lo:hi].to(torch.bfloat16))
+print(f"rank {rank}: adam max err {err:.2e}; shadow equal on all ranks {ok_shadow}; shadow == bf16(master) on owned slice {own_ok}", flush=True)
+sh.check()
+dist.barrier()
+os._exit(0)

@@ -153,7 +153,9 @@ _SIGS = {
     "tribe_subject_bias_grad": [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
     "tribe_check_subjects": [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "tribe_mse_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp],
-    "tribe_pearson_stats": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp],
+    "tribe_pearson_stats": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "tribe_pearson_pick_shift": [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp],
+    "tribe_pearson_recenter": [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "tribe_pearson_finalize": [c_vp, c_i64, c_vp, c_vp, c_vp],
     "tribe_nce_expsums": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp],
     "tribe_nce_loss": [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp],
@@ -165,7 +167,7 @@ _SIGS = {
     "tribe_sharded_adam_step": [ctypes.POINTER(TribeShardedAdam), c_vp],
     "tribe_xgpu_barrier": [ctypes.POINTER(TribeXgpuPeers), c_i32, c_i32, c_i32, c_vp, c_f64, c_vp],
     "tribe_point_loss_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp, c_vp],
-    "tribe_pearson_loss_finalize": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp],
+    "tribe_pearson_loss_finalize": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp],
     "tribe_pearson_loss_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_vp],
     "tribe_gather_windows": [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp],
     "tribe_ensemble_weights": [c_vp, c_i64, c_i64, c_f32, c_i32, c_vp, c_vp],

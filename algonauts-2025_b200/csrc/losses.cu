@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(256) loss_final_kernel(const double* __restric
 //   d pcc / d x_i = (y_i - my) / D - a sy (x_i - mx) / (D^2 sx)        (centering is its own adjoint here)
 // coef[0..3][p] = mx, my, c1 = 1/D, c2 = a sy / (D^2 sx)   (c2 = 0 for a constant prediction, like autograd's 0 * inf guard
 // does NOT do — the reference would produce NaN there; we keep NaN out of the weights and document it).
-__global__ void __launch_bounds__(256) pearson_loss_finalize_kernel(const double* __restrict__ stats, int64_t n_parcels, float* __restrict__ coef,
-                                                                    float* __restrict__ loss, double scale) {
+__global__ void __launch_bounds__(256) pearson_loss_finalize_kernel(const double* __restrict__ stats, int64_t n_parcels, const float* __restrict__ shift,
+                                                                    float* __restrict__ coef, float* __restrict__ loss, double scale) {
   __shared__ double red[8];
   double acc = 0.0;
   for (int64_t p = threadIdx.x; p < n_parcels; p += blockDim.x) {
@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(256) pearson_loss_finalize_kernel(const double
     const double D = sx * sy + 1e-8;
     acc += 1.0 - a / D;
     if (coef) {
-      coef[p] = static_cast<float>(sx1 / n);
-      coef[n_parcels + p] = static_cast<float>(sy1 / n);
+      // the statistics are sums of (x - pivot): the means the backward centres with are pivot + S1 / n
+      coef[p] = static_cast<float>((shift ? static_cast<double>(shift[p]) : 0.0) + sx1 / n);
+      coef[n_parcels + p] = static_cast<float>((shift ? static_cast<double>(shift[n_parcels + p]) : 0.0) + sy1 / n);
       coef[2 * n_parcels + p] = static_cast<float>(1.0 / D);
       coef[3 * n_parcels + p] = sx > 0.0 ? static_cast<float>(a * sy / (D * D * sx)) : 0.f;
     }
@@ -202,9 +203,10 @@ extern "C" int tribe_point_loss_fwd_bwd(const float* pred, const float* target, 
   return TRIBE_OK;
 }
 
-extern "C" int tribe_pearson_loss_finalize(const double* stats, int64_t n_parcels, int32_t reduction_mean, float* coef, float* loss_out, void* stream) {
+extern "C" int tribe_pearson_loss_finalize(const double* stats, int64_t n_parcels, int32_t reduction_mean, const float* shift, float* coef,
+                                           float* loss_out, void* stream) {
   if (!stats || !loss_out || n_parcels <= 0) return set_error(TRIBE_EINVAL, "pearson_loss_finalize: bad arguments");
-  pearson_loss_finalize_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stats, n_parcels, coef, loss_out,
+  pearson_loss_finalize_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stats, n_parcels, shift, coef, loss_out,
                                                                                      reduction_mean ? 1.0 / static_cast<double>(n_parcels) : 1.0);
   TRIBE_CHECK_LAUNCH("pearson_loss_finalize");
   return TRIBE_OK;

@@ -86,9 +86,14 @@ constexpr int kInner = 8;
 
 __global__ void __launch_bounds__(256) pearson_rowmajor_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_rows,
                                                                int64_t n_parcels, int64_t rows_per_block, const long long* __restrict__ group,
-                                                               double* __restrict__ stats) {
+                                                               const float* __restrict__ shift, double* __restrict__ stats) {
   const int64_t p0 = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
   if (p0 >= n_parcels) return;
+  float kx[4] = {0, 0, 0, 0}, ky[4] = {0, 0, 0, 0};  // per-parcel pivots: sums of (x - kx), (y - ky) keep fp32 products well conditioned
+  if (shift) {
+    for (int j = 0; j < 4; ++j)
+      if (p0 + j < n_parcels) kx[j] = shift[p0 + j], ky[j] = shift[n_parcels + p0 + j];
+  }
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
   const int64_t r1 = min(n_rows, r0 + rows_per_block);
   if (r0 >= r1) return;
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(256) pearson_rowmajor_kernel(const float* __re
           }
           float x[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0};
           for (int j = 0; j < 4; ++j)
-            if (p0 + j < n_parcels) x[j] = pred[(r + k) * n_parcels + p0 + j], y[j] = target[(r + k) * n_parcels + p0 + j];
+            if (p0 + j < n_parcels) x[j] = pred[(r + k) * n_parcels + p0 + j] - kx[j], y[j] = target[(r + k) * n_parcels + p0 + j] - ky[j];
           for (int j = 0; j < 4; ++j) sx[j] += x[j], sy[j] += y[j], sxx[j] += (double)x[j] * x[j], syy[j] += (double)y[j] * y[j], sxy[j] += (double)x[j] * y[j];
           ++n_in_group;
         }
@@ -146,7 +151,8 @@ __global__ void __launch_bounds__(256) pearson_rowmajor_kernel(const float* __re
 #pragma unroll
       for (int k = 0; k < kInner; ++k) {
         if (k < nr) {
-          const float x[4] = {xs[k].x, xs[k].y, xs[k].z, xs[k].w}, y[4] = {ys[k].x, ys[k].y, ys[k].z, ys[k].w};
+          const float x[4] = {xs[k].x - kx[0], xs[k].y - kx[1], xs[k].z - kx[2], xs[k].w - kx[3]};
+          const float y[4] = {ys[k].x - ky[0], ys[k].y - ky[1], ys[k].z - ky[2], ys[k].w - ky[3]};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             fx[j] += x[j], fy[j] += y[j];
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(256) pearson_rowmajor_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (p0 + j < n_parcels) {
-            const float x = pred[(r + k) * n_parcels + p0 + j], y = target[(r + k) * n_parcels + p0 + j];
+            const float x = pred[(r + k) * n_parcels + p0 + j] - kx[j], y = target[(r + k) * n_parcels + p0 + j] - ky[j];
             fx[j] += x, fy[j] += y, fxx[j] = fmaf(x, x, fxx[j]), fyy[j] = fmaf(y, y, fyy[j]), fxy[j] = fmaf(x, y, fxy[j]);
           }
         }
@@ -176,18 +182,20 @@ __global__ void __launch_bounds__(256) pearson_rowmajor_kernel(const float* __re
 // "(b t) d" view of a (B, D, T) prediction tensor, pl_module.py:54-55).  One warp per (b, parcel): lanes run along t.
 __global__ void __launch_bounds__(256) pearson_strided_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_b,
                                                               int64_t n_parcels, int64_t t_len, int64_t stride_b, int64_t stride_p, int64_t stride_t,
-                                                              const long long* __restrict__ group, double* __restrict__ stats) {
+                                                              const long long* __restrict__ group, const float* __restrict__ shift,
+                                                              double* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t p = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int64_t b = blockIdx.y;
   if (p >= n_parcels || b >= n_b) return;
+  const float kx = shift ? shift[p] : 0.f, ky = shift ? shift[n_parcels + p] : 0.f;
   const float* xp = pred + b * stride_b + p * stride_p;
   const float* yp = target + b * stride_b + p * stride_p;
   float fx = 0, fy = 0, fxx = 0, fyy = 0, fxy = 0;
   double dx = 0, dy = 0, dxx = 0, dyy = 0, dxy = 0;
   int cnt = 0;
   for (int64_t t = lane; t < t_len; t += 32) {
-    const float x = __ldg(xp + t * stride_t), y = __ldg(yp + t * stride_t);
+    const float x = __ldg(xp + t * stride_t) - kx, y = __ldg(yp + t * stride_t) - ky;
     fx += x, fy += y, fxx = fmaf(x, x, fxx), fyy = fmaf(y, y, fyy), fxy = fmaf(x, y, fxy);
     if (++cnt == 16) {
       dx += fx, dy += fy, dxx += fxx, dyy += fyy, dxy += fxy;
@@ -217,7 +225,8 @@ constexpr int kBdtUnroll = 4;
 template <int VEC>
 __global__ void __launch_bounds__(256) pearson_bdt_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_b,
                                                           int64_t n_parcels, int t_len, int64_t stride_b, int pb, int64_t b_per_block,
-                                                          const long long* __restrict__ group, double* __restrict__ stats) {
+                                                          const long long* __restrict__ group, const float* __restrict__ shift,
+                                                          double* __restrict__ stats) {
   __shared__ double sh[64 * 5];  // pb <= 64 parcels x 5 sums
   const int tv = t_len / VEC;
   const int item = threadIdx.x;
@@ -228,6 +237,9 @@ __global__ void __launch_bounds__(256) pearson_bdt_kernel(const float* __restric
   const int64_t b1 = min(n_b, b0 + b_per_block);
   if (b0 >= b1) return;
   const int64_t off = static_cast<int64_t>(blockIdx.x) * pb * t_len + static_cast<int64_t>(item) * VEC;
+  // per-parcel pivot (a thread keeps ONE parcel for its whole life): the products below are of O(sigma) values even when
+  // |mean| >> sigma, which raw fp32 moments cannot represent (scipy / torchmetrics centre before multiplying)
+  const float kx = (shift && active) ? shift[p] : 0.f, ky = (shift && active) ? shift[n_parcels + p] : 0.f;
   double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
   long long cur = group ? group[b0] : 0;
   int64_t cnt = 0;
@@ -277,7 +289,8 @@ __global__ void __launch_bounds__(256) pearson_bdt_kernel(const float* __restric
 #pragma unroll
         for (int k = 0; k < kBdtUnroll; ++k) {
           if (k < nk) {
-            const float x[4] = {xs[k].x, xs[k].y, xs[k].z, xs[k].w}, y[4] = {ys[k].x, ys[k].y, ys[k].z, ys[k].w};
+            const float x[4] = {xs[k].x - kx, xs[k].y - kx, xs[k].z - kx, xs[k].w - kx};
+            const float y[4] = {ys[k].x - ky, ys[k].y - ky, ys[k].z - ky, ys[k].w - ky};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               fx += x[j], fy += y[j];
@@ -293,7 +306,10 @@ __global__ void __launch_bounds__(256) pearson_bdt_kernel(const float* __restric
         }
 #pragma unroll
         for (int k = 0; k < kBdtUnroll; ++k) {
-          if (k < nk) fx += xs[k], fy += ys[k], fxx = fmaf(xs[k], xs[k], fxx), fyy = fmaf(ys[k], ys[k], fyy), fxy = fmaf(xs[k], ys[k], fxy);
+          if (k < nk) {
+            const float x = xs[k] - kx, y = ys[k] - ky;
+            fx += x, fy += y, fxx = fmaf(x, x, fxx), fyy = fmaf(y, y, fyy), fxy = fmaf(x, y, fxy);
+          }
         }
       }
       sx += fx, sy += fy, sxx += fxx, syy += fyy, sxy += fxy;
@@ -301,6 +317,32 @@ __global__ void __launch_bounds__(256) pearson_bdt_kernel(const float* __restric
     b += nk, cnt += nk;
   }
   flush(cur, cnt);
+}
+
+// pivot = the FIRST sample of every parcel (row 0): within a few sigma of the mean for any sane column, and EXACTLY the
+// column for a constant one, whose shifted sums are then exactly zero -> r = 0/0 = NaN like scipy's constant-input result
+__global__ void __launch_bounds__(256) pearson_pick_shift_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n_parcels,
+                                                                 int64_t stride_p, float* __restrict__ shift) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p < n_parcels) shift[p] = pred[p * stride_p], shift[n_parcels + p] = target[p * stride_p];
+}
+
+// sums about pivot k -> sums about pivot k' (fp64; d = k - k'):  S1' = S1 + n d,  S2' = S2 + 2 d S1 + n d^2,
+// Sxy' = Sxy + dx Sy + dy Sx + n dx dy.  Used to merge statistics taken with different pivots (ranks, checkpoints).
+__global__ void __launch_bounds__(256) pearson_recenter_kernel(double* __restrict__ stats, int64_t n_groups, int64_t n_parcels,
+                                                               const float* __restrict__ shift_old, const float* __restrict__ shift_new) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_groups * n_parcels) return;
+  const int64_t g = i / n_parcels, p = i - g * n_parcels;
+  double* st = stats + g * 6 * n_parcels;
+  const double dx = (shift_old ? static_cast<double>(shift_old[p]) : 0.0) - (shift_new ? static_cast<double>(shift_new[p]) : 0.0);
+  const double dy = (shift_old ? static_cast<double>(shift_old[n_parcels + p]) : 0.0) - (shift_new ? static_cast<double>(shift_new[n_parcels + p]) : 0.0);
+  const double n = st[p], sx = st[n_parcels + p], sy = st[2 * n_parcels + p];
+  st[3 * n_parcels + p] += 2.0 * dx * sx + n * dx * dx;
+  st[4 * n_parcels + p] += 2.0 * dy * sy + n * dy * dy;
+  st[5 * n_parcels + p] += dx * sy + dy * sx + n * dx * dy;
+  st[n_parcels + p] = sx + n * dx;
+  st[2 * n_parcels + p] = sy + n * dy;
 }
 
 __global__ void __launch_bounds__(256) pearson_finalize_kernel(const double* __restrict__ stats, int64_t n_parcels, float* __restrict__ r_out,
@@ -312,7 +354,10 @@ __global__ void __launch_bounds__(256) pearson_finalize_kernel(const double* __r
     const double sxx = stats[3 * n_parcels + p], syy = stats[4 * n_parcels + p], sxy = stats[5 * n_parcels + p];
     const double cov = sxy - sx * sy / n, vx = sxx - sx * sx / n, vy = syy - sy * sy / n;
     double r = cov / sqrt(vx * vy);
-    r = fmin(1.0, fmax(-1.0, r));  // NaN (constant input) propagates like scipy / torchmetrics
+    // NaN (constant column: var == 0 -> 0/0; NaN input) propagates like scipy / torchmetrics.  fmin/fmax would
+    // silently turn it into -1 (they return the non-NaN operand), so clamp only ordered values.
+    if (r > 1.0) r = 1.0;
+    if (r < -1.0) r = -1.0;
     if (r_out) r_out[p] = static_cast<float>(r);
     acc += r;
   }
@@ -344,7 +389,8 @@ extern "C" int tribe_mse_fwd_bwd(const float* pred, const float* target, float* 
 }
 
 extern "C" int tribe_pearson_stats(const float* pred, const float* target, int64_t n_rows, int64_t n_parcels, int64_t t_len, int64_t stride_b,
-                                   int64_t stride_p, int64_t stride_t, const int64_t* group, int64_t n_groups, double* stats, void* stream) {
+                                   int64_t stride_p, int64_t stride_t, const int64_t* group, int64_t n_groups, const float* shift, double* stats,
+                                   void* stream) {
   if (!pred || !target || !stats || n_rows <= 0 || n_parcels <= 0 || t_len <= 0 || n_rows % t_len)
     return set_error(TRIBE_EINVAL, "pearson_stats: bad arguments (n_rows must be a multiple of t_len)");
   if (group && n_groups <= 0) return set_error(TRIBE_EINVAL, "pearson_stats: group given without n_groups");
@@ -359,7 +405,7 @@ extern "C" int tribe_pearson_stats(const float* pred, const float* target, int64
     int64_t rpb = (n_rows + chunks - 1) / chunks;
     rpb = (rpb + kInner - 1) / kInner * kInner;
     dim3 grid(static_cast<unsigned>(pblocks), static_cast<unsigned>((n_rows + rpb - 1) / rpb));
-    pearson_rowmajor_kernel<<<grid, 256, 0, s>>>(pred, target, n_rows, n_parcels, rpb, g, stats);
+    pearson_rowmajor_kernel<<<grid, 256, 0, s>>>(pred, target, n_rows, n_parcels, rpb, g, shift, stats);
     TRIBE_CHECK_LAUNCH("pearson_rowmajor");
   } else if (stride_t == 1 && stride_p == t_len && t_len <= 1024 &&
              (((t_len & 3) == 0 && (stride_b & 3) == 0 && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target)) & 15) == 0) ||
@@ -386,17 +432,35 @@ extern "C" int tribe_pearson_stats(const float* pred, const float* target, int64
     bpb = (bpb + kBdtUnroll - 1) / kBdtUnroll * kBdtUnroll;
     dim3 grid(static_cast<unsigned>(pblocks), static_cast<unsigned>((n_b + bpb - 1) / bpb));
     if (vec)
-      pearson_bdt_kernel<4><<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, static_cast<int>(t_len), stride_b, pb, bpb, g, stats);
+      pearson_bdt_kernel<4><<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, static_cast<int>(t_len), stride_b, pb, bpb, g, shift, stats);
     else
-      pearson_bdt_kernel<1><<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, static_cast<int>(t_len), stride_b, pb, bpb, g, stats);
+      pearson_bdt_kernel<1><<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, static_cast<int>(t_len), stride_b, pb, bpb, g, shift, stats);
     TRIBE_CHECK_LAUNCH("pearson_bdt");
   } else {
     const int64_t n_b = n_rows / t_len;
     if (n_b > 65535) return set_error(TRIBE_EINVAL, "pearson_stats: more than 65535 strided blocks per call");
     dim3 grid(static_cast<unsigned>((n_parcels + 7) / 8), static_cast<unsigned>(n_b));
-    pearson_strided_kernel<<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, t_len, stride_b, stride_p, stride_t, g, stats);
+    pearson_strided_kernel<<<grid, 256, 0, s>>>(pred, target, n_b, n_parcels, t_len, stride_b, stride_p, stride_t, g, shift, stats);
     TRIBE_CHECK_LAUNCH("pearson_strided");
   }
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_pearson_pick_shift(const float* pred, const float* target, int64_t n_parcels, int64_t stride_p, float* shift, void* stream) {
+  if (!pred || !target || !shift || n_parcels <= 0 || stride_p <= 0) return set_error(TRIBE_EINVAL, "pearson_pick_shift: bad arguments");
+  pearson_pick_shift_kernel<<<static_cast<unsigned>((n_parcels + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, target, n_parcels,
+                                                                                                                             stride_p, shift);
+  TRIBE_CHECK_LAUNCH("pearson_pick_shift");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_pearson_recenter(double* stats, int64_t n_groups, int64_t n_parcels, const float* shift_old, const float* shift_new, void* stream) {
+  if (!stats || n_groups <= 0 || n_parcels <= 0) return set_error(TRIBE_EINVAL, "pearson_recenter: bad arguments");
+  if (!shift_old && !shift_new) return TRIBE_OK;
+  const int64_t n = n_groups * n_parcels;
+  pearson_recenter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(stats, n_groups, n_parcels, shift_old,
+                                                                                                                   shift_new);
+  TRIBE_CHECK_LAUNCH("pearson_recenter");
   return TRIBE_OK;
 }
 

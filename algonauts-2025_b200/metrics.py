@@ -17,11 +17,24 @@ from . import ops
 from ._lib import TribeError
 
 
-def _dist_sum_(t: torch.Tensor) -> None:
+def _world_size() -> int:
     import torch.distributed as dist
 
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _merged_stats(stats: torch.Tensor, shift: torch.Tensor | None) -> torch.Tensor:
+    """A copy of the local statistics ready for ``pearson_finalize``: under ``torch.distributed`` every rank's block is
+    re-expressed about pivot 0 in fp64 (ranks picked their pivots from their own first rows) and summed with one
+    all-reduce (48 KB for 1000 parcels) — the reduction torchmetrics does by gathering its states."""
+    st = stats.clone()
+    if _world_size() > 1:
+        import torch.distributed as dist
+
+        if shift is not None:
+            ops.pearson_recenter(st, shift, None)
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    return st
 
 
 class MultidimPearsonCorrCoef(nn.Module):
@@ -34,39 +47,48 @@ class MultidimPearsonCorrCoef(nn.Module):
         super().__init__()
         self.num_outputs = num_outputs
         self.register_buffer("stats", torch.zeros(1, 6, num_outputs, dtype=torch.float64), persistent=False)
+        # per-parcel pivots (first sample seen since the last reset): the kernels accumulate moments of (x - pivot), which
+        # stay well conditioned when |mean| >> sigma (torchmetrics / scipy centre before multiplying)
+        self.register_buffer("shift", torch.zeros(2, num_outputs, dtype=torch.float32), persistent=False)
+        self._has_shift = False
 
     def _dev(self, like: torch.Tensor):
         if not like.is_cuda:
             raise TribeError("Pearson metric needs CUDA tensors (no CPU fallback)")
         if self.stats.device != like.device:
-            self.stats = self.stats.to(like.device)
+            self.stats, self.shift = self.stats.to(like.device), self.shift.to(like.device)
+
+    def _update(self, preds, target, layout, **kw):
+        self._dev(preds)
+        preds, target = preds.detach().float().contiguous(), target.detach().to(preds.device).float().contiguous()
+        if preds.numel() == 0:
+            return
+        if not self._has_shift:
+            ops.pearson_pick_shift(preds, target, self.shift, layout=layout)
+            self._has_shift = True
+        ops.pearson_stats(preds, target, self.stats, layout=layout, shift=self.shift, **kw)
 
     def update(self, preds: torch.Tensor, target: torch.Tensor) -> None:
         """preds/target: (N, O) — the flattened ``(b t) d`` matrices of pl_module.py:54-55."""
-        self._dev(preds)
         if preds.ndim == 1:
             preds, target = preds[:, None], target[:, None]
-        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="no")
+        self._update(preds, target, "no")
 
     def update_bdt(self, preds: torch.Tensor, target: torch.Tensor) -> None:
         """Same statistics straight from (B, D, T) tensors (no materialised rearrange)."""
-        self._dev(preds)
-        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="bdt")
+        self._update(preds, target, "bdt")
 
     def per_output(self) -> torch.Tensor:
-        st = self.stats.clone()
-        _dist_sum_(st)
-        r, _ = ops.pearson_finalize(st[0])
+        r, _ = ops.pearson_finalize(_merged_stats(self.stats, self.shift if self._has_shift else None)[0])
         return r
 
     def compute(self) -> torch.Tensor:
-        st = self.stats.clone()
-        _dist_sum_(st)
-        _, mean = ops.pearson_finalize(st[0], want_mean=True)
+        _, mean = ops.pearson_finalize(_merged_stats(self.stats, self.shift if self._has_shift else None)[0], want_mean=True)
         return mean[0]
 
     def reset(self) -> None:
         ops.zero_(self.stats) if self.stats.is_cuda else self.stats.zero_()
+        self._has_shift = False
 
     def forward(self, preds, target):
         self.update(preds, target)
@@ -87,12 +109,14 @@ class GroupedMetric(nn.Module):
         self.num_outputs = int(self.metric_kwargs.get("num_outputs", 1))
         self.register_buffer("stats", torch.zeros(self.MAX_GROUPS, 6, self.num_outputs, dtype=torch.float64), persistent=False)
         self.register_buffer("bad_group", torch.zeros(1, dtype=torch.int32), persistent=False)
+        self.register_buffer("shift", torch.zeros(2, self.num_outputs, dtype=torch.float32), persistent=False)  # one pivot per parcel for all groups
+        self._has_shift = False
 
     def _prep(self, preds, groups, n_expected):
         if not preds.is_cuda:
             raise TribeError("GroupedMetric needs CUDA tensors (no CPU fallback)")
         if self.stats.device != preds.device:
-            self.stats, self.bad_group = self.stats.to(preds.device), self.bad_group.to(preds.device)
+            self.stats, self.bad_group, self.shift = self.stats.to(preds.device), self.bad_group.to(preds.device), self.shift.to(preds.device)
         if groups is None:
             groups = torch.zeros(n_expected, dtype=torch.int64, device=preds.device)
         groups = groups.flatten().to(preds.device, torch.int64).contiguous()
@@ -100,21 +124,26 @@ class GroupedMetric(nn.Module):
         ops.check_subjects(groups, self.MAX_GROUPS, self.bad_group)
         return groups
 
-    def update(self, preds: torch.Tensor, target: torch.Tensor, groups: tp.Optional[torch.Tensor] = None) -> None:
+    def _update(self, preds, target, groups, layout):
         groups = self._prep(preds, groups, preds.shape[0])
-        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="no",
-                          group=groups, n_groups=self.MAX_GROUPS)
+        preds, target = preds.detach().float().contiguous(), target.detach().to(preds.device).float().contiguous()
+        if preds.numel() == 0:
+            return
+        if not self._has_shift:
+            ops.pearson_pick_shift(preds, target, self.shift, layout=layout)
+            self._has_shift = True
+        ops.pearson_stats(preds, target, self.stats, layout=layout, group=groups, n_groups=self.MAX_GROUPS, shift=self.shift)
+
+    def update(self, preds: torch.Tensor, target: torch.Tensor, groups: tp.Optional[torch.Tensor] = None) -> None:
+        self._update(preds, target, groups, "no")
 
     def update_bdt(self, preds: torch.Tensor, target: torch.Tensor, groups: tp.Optional[torch.Tensor] = None) -> None:
-        groups = self._prep(preds, groups, preds.shape[0])
-        ops.pearson_stats(preds.detach().float().contiguous(), target.detach().float().contiguous(), self.stats, layout="bdt",
-                          group=groups, n_groups=self.MAX_GROUPS)
+        self._update(preds, target, groups, "bdt")
 
     def compute(self) -> dict[str, float]:
         if int(self.bad_group.item()):
             raise TribeError(f"GroupedMetric saw a group id outside [0, {self.MAX_GROUPS})")
-        st = self.stats.clone()
-        _dist_sum_(st)
+        st = _merged_stats(self.stats, self.shift if self._has_shift else None)
         counts = st[:, 0, 0].cpu()
         out = {}
         for gid in torch.nonzero(counts > 0).flatten().tolist():
@@ -125,19 +154,30 @@ class GroupedMetric(nn.Module):
     def reset(self) -> None:
         ops.zero_(self.stats) if self.stats.is_cuda else self.stats.zero_()
         ops.zero_(self.bad_group) if self.bad_group.is_cuda else self.bad_group.zero_()
+        self._has_shift = False
 
     def __repr__(self) -> str:
         return "GroupedMetric(MultidimPearsonCorrCoef)"
 
 
 @torch.no_grad()
-def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice: slice | None = None) -> np.ndarray:
+def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice: slice | None = None, distributed: str | None = "auto",
+                             n_outputs: int | None = None) -> np.ndarray:
     """``Experiment.compute_multidim_pearson`` (main.py:459-477): eval-mode batched predict, then per-parcel Pearson r
     over all (window, TR) rows.  Predictions never leave the device; the 1000-iteration scipy loop becomes one
-    statistics kernel per batch + one finalize.  ``parcel_slice`` restricts the statistics to a shard of parcels
-    (parcel-sharded evaluation, see parallel.py)."""
+    statistics kernel per batch + one finalize.  ``parcel_slice`` restricts the statistics to a shard of parcels.
+
+    Rank-aware: under ``torch.distributed`` (world size > 1) every rank passes ITS shard of the windows and every rank
+    receives r over ALL ranks' windows.  ``distributed="stats"`` (what "auto" selects) all-reduces the fp64 sufficient
+    statistics (6 x O doubles); ``"parcels"`` keeps the predictions, re-lays them to parcel shards with one all-to-all
+    and reduces 1000/G parcels per rank (BASELINE config 5, ``parallel.sharded_pearson``); ``None`` = local windows only."""
     model.eval()
-    stats = None
+    ws = _world_size()
+    mode = ("stats" if ws > 1 else None) if distributed == "auto" else distributed
+    if ws == 1:
+        mode = None
+    stats = shift = None
+    kept_p, kept_t = [], []
     for batch in loader:
         y_pred = model(batch)
         y_true = batch.data["fmri"].to(y_pred.device, torch.float32)
@@ -145,9 +185,30 @@ def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice
             y_true = y_true.squeeze(-1)
         if parcel_slice is not None:
             y_pred, y_true = y_pred[:, parcel_slice], y_true.contiguous()[:, parcel_slice]  # read in place by the kernel
+        if mode == "parcels":
+            kept_p.append(y_pred.float().contiguous()), kept_t.append(y_true.contiguous())
+            continue
         if stats is None:
             stats = torch.zeros(1, 6, y_pred.shape[1], device=y_pred.device, dtype=torch.float64)
-        ops.pearson_stats(y_pred.float(), y_true, stats, layout="bdt")
+            shift = torch.empty(2, y_pred.shape[1], device=y_pred.device, dtype=torch.float32)
+            ops.pearson_pick_shift(y_pred.float(), y_true, shift, layout="bdt")
+        ops.pearson_stats(y_pred.float(), y_true, stats, layout="bdt", shift=shift)
+    if mode == "parcels":
+        from . import parallel
+
+        r = parallel.sharded_pearson(torch.cat(kept_p), torch.cat(kept_t))
+        return r.cpu().numpy().astype(np.float32)
+    if stats is None:  # a rank without windows still has to take part in the reduction
+        if mode != "stats":
+            raise TribeError("compute_multidim_pearson: empty loader")
+        o = n_outputs if n_outputs is not None else getattr(model, "n_outputs", None)
+        if o is None:
+            raise TribeError("compute_multidim_pearson: a rank without windows needs n_outputs")
+        if parcel_slice is not None:
+            o = len(range(*parcel_slice.indices(o)))
+        stats = torch.zeros(1, 6, o, device=torch.device("cuda", torch.cuda.current_device()), dtype=torch.float64)
+    if mode == "stats":
+        stats = _merged_stats(stats, shift)
     r, _ = ops.pearson_finalize(stats[0])
     return r.cpu().numpy().astype(np.float32)
 
@@ -167,6 +228,7 @@ def pearson_from_host(preds: torch.Tensor, trues: torch.Tensor, chunk_windows: i
     if layout == "no":
         chunk_windows *= 100
     stats = torch.zeros(1, 6, o, device=dev, dtype=torch.float64)
+    shift = torch.empty(2, o, device=dev, dtype=torch.float32)
     main, copy = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
     slots = [(torch.empty((min(chunk_windows, n),) + tuple(preds.shape[1:]), device=dev), torch.empty((min(chunk_windows, n),) + tuple(preds.shape[1:]), device=dev))
              for _ in range(2)]
@@ -181,7 +243,9 @@ def pearson_from_host(preds: torch.Tensor, trues: torch.Tensor, chunk_windows: i
             slots[s][1][: hi - lo].copy_(trues[lo:hi], non_blocking=True)
             ready[s].record(copy)
         main.wait_event(ready[s])
-        ops.pearson_stats(slots[s][0][: hi - lo], slots[s][1][: hi - lo], stats, layout=layout)
+        if i == 0:
+            ops.pearson_pick_shift(slots[s][0][: hi - lo], slots[s][1][: hi - lo], shift, layout=layout)
+        ops.pearson_stats(slots[s][0][: hi - lo], slots[s][1][: hi - lo], stats, layout=layout, shift=shift)
         free[s].record(main)
     r, _ = ops.pearson_finalize(stats[0])
     return r.cpu().numpy().astype(np.float32)

@@ -263,8 +263,41 @@ def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):
     return loss, grad
 
 
-def pearson_stats(pred, target, stats, *, layout: str, group=None, n_groups: int = 1) -> None:
-    """Accumulate per-parcel sufficient statistics into ``stats`` (fp64 [n_groups, 6, O]).
+def _bdt_view(pred, target):
+    """(B, D, T) operands as the stats kernels address them; a parcel slice of a contiguous tensor is read in place."""
+    b, d, t = pred.shape
+    for x, name in ((pred, "pearson pred"), (target, "pearson target")):
+        if x.dtype != torch.float32 or not x.is_cuda or x.shape != pred.shape:
+            raise TribeError(f"{name}: expected CUDA float32 of shape {tuple(pred.shape)}, got {x.dtype} {x.device} {tuple(x.shape)}")
+    if not (pred.stride(2) == 1 and pred.stride(1) == t and pred.stride() == target.stride()) and b * d * t > 0:
+        pred, target = pred.contiguous(), target.contiguous()
+    return pred, target
+
+
+def pearson_pick_shift(pred, target, shift, *, layout: str) -> None:
+    """shift fp32 (2, O) <- the first sample of every parcel of pred / target (per-parcel pivots for ``pearson_stats``)."""
+    _need(shift, torch.float32, "pearson shift")
+    if layout == "no":
+        _need(pred, torch.float32, "pearson pred"), _need(target, torch.float32, "pearson target")
+        o, stride_p = pred.shape[1], 1
+    else:
+        pred, target = _bdt_view(pred, target)
+        o, stride_p = pred.shape[1], pred.shape[2]
+    if shift.shape != (2, o):
+        raise TribeError(f"pearson shift must be (2, {o})")
+    if pred.numel():
+        _run("tribe_pearson_pick_shift", _ptr(pred), _ptr(target), o, stride_p, _ptr(shift), _stream())
+
+
+def pearson_recenter(stats, shift_old, shift_new) -> None:
+    """In place: statistics about pivots ``shift_old`` -> about ``shift_new`` (None = 0); stats fp64 (G, 6, O)."""
+    g, _, o = stats.shape
+    _run("tribe_pearson_recenter", _ptr(stats), g, o, _ptr(shift_old), _ptr(shift_new), _stream())
+
+
+def pearson_stats(pred, target, stats, *, layout: str, group=None, n_groups: int = 1, shift=None) -> None:
+    """Accumulate per-parcel sufficient statistics into ``stats`` (fp64 [n_groups, 6, O]); ``shift`` fp32 (2, O): per-parcel
+    pivots subtracted before the products (every call accumulating into one block must pass the same ones).
 
     layout "no": pred/target are row-major (N, O).  layout "bdt": they are (B, D, T) and rows are the flattened
     ``(b t)`` of ``rearrange(x, "b d t -> (b t) d")`` (pl_module.py:54-55, main.py:472-473) without materialising it."""
@@ -277,16 +310,25 @@ def pearson_stats(pred, target, stats, *, layout: str, group=None, n_groups: int
     elif layout == "bdt":
         # a parcel slice x[:, lo:hi] of a contiguous (B, D, T) tensor is read in place (stride_b stays D_full * T)
         b, d, t = pred.shape
-        for x, name in ((pred, "pearson pred"), (target, "pearson target")):
-            if x.dtype != torch.float32 or not x.is_cuda or x.shape != pred.shape:
-                raise TribeError(f"{name}: expected CUDA float32 of shape {tuple(pred.shape)}, got {x.dtype} {x.device} {tuple(x.shape)}")
-        if not (pred.stride(2) == 1 and pred.stride(1) == t and pred.stride() == target.stride()) and b * d * t > 0:
-            pred, target = pred.contiguous(), target.contiguous()
+        pred, target = _bdt_view(pred, target)
         args = (b * t, d, t, pred.stride(0) if b > 1 else d * t, t, 1)
     else:
         raise TribeError(f"unknown layout {layout}")
+    if shift is not None and (shift.dtype != torch.float32 or tuple(shift.shape) != (2, args[1]) or not shift.is_contiguous()):
+        raise TribeError(f"pearson shift must be contiguous float32 (2, {args[1]})")
     _run("tribe_pearson_stats", _ptr(pred), _ptr(target), *args, _ptr(group), n_groups if group is not None else 0,
-                                          _ptr(stats), _stream())
+                                          _ptr(shift), _ptr(stats), _stream())
+
+
+def pearson_r(pred, target, *, layout: str, want_mean=False):
+    """One-shot per-parcel Pearson r of a whole (N, O) / (B, O, T) pair: pivots from the first row, pivoted statistics,
+    finalize -> (r (O,), mean or None)."""
+    o = pred.shape[1]
+    shift = torch.empty(2, o, device=pred.device, dtype=torch.float32)
+    stats = torch.zeros(1, 6, o, device=pred.device, dtype=torch.float64)
+    pearson_pick_shift(pred, target, shift, layout=layout)
+    pearson_stats(pred, target, stats, layout=layout, shift=shift)
+    return pearson_finalize(stats[0], want_mean=want_mean)
 
 
 def pearson_finalize(stats_one_group, want_mean=False):
@@ -333,10 +375,12 @@ def pearson_loss_fwd(pred, target, *, layout: str, reduction_mean: bool = True, 
     """PearsonLoss(dim=1) forward on (N, O) ("no") or (B, O, T) ("bdt") tensors -> (loss[1], coef (4, O) or None)."""
     o = pred.shape[1]
     stats = torch.zeros(1, 6, o, device=pred.device, dtype=torch.float64)
-    pearson_stats(pred, target, stats, layout=layout)
+    shift = torch.empty(2, o, device=pred.device, dtype=torch.float32)
+    pearson_pick_shift(pred, target, shift, layout=layout)
+    pearson_stats(pred, target, stats, layout=layout, shift=shift)
     loss = torch.empty(1, device=pred.device, dtype=torch.float32)
     coef = torch.empty(4, o, device=pred.device, dtype=torch.float32) if want_coef else None
-    _run("tribe_pearson_loss_finalize", _ptr(stats), o, int(reduction_mean), _ptr(coef), _ptr(loss), _stream())
+    _run("tribe_pearson_loss_finalize", _ptr(stats), o, int(reduction_mean), _ptr(shift), _ptr(coef), _ptr(loss), _stream())
     return loss, coef
 
 

@@ -392,9 +392,7 @@ def sharded_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=
     O = preds_local.shape[1]
     p_shard, _ = exchange_parcel_shards(preds_local, group)
     t_shard, _ = exchange_parcel_shards(trues_local, group)
-    stats = torch.zeros(1, 6, p_shard.shape[1], device=p_shard.device, dtype=torch.float64)
-    ops.pearson_stats(p_shard.contiguous(), t_shard.contiguous(), stats, layout="no" if p_shard.dim() == 2 else "bdt")
-    r, _ = ops.pearson_finalize(stats[0])
+    r, _ = ops.pearson_r(p_shard.contiguous(), t_shard.contiguous(), layout="no" if p_shard.dim() == 2 else "bdt")
     return gather_parcels(r, O, group)
 
 
@@ -402,10 +400,15 @@ def allreduced_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, gro
     """Alternative without re-laying the data: local statistics over all parcels + one all-reduce of 6 x O fp64."""
     from . import ops
 
+    layout = "no" if preds_local.dim() == 2 else "bdt"
     stats = torch.zeros(1, 6, preds_local.shape[1], device=preds_local.device, dtype=torch.float64)
-    ops.pearson_stats(preds_local.contiguous(), trues_local.contiguous(), stats, layout="no" if preds_local.dim() == 2 else "bdt")
+    shift = torch.zeros(2, preds_local.shape[1], device=preds_local.device, dtype=torch.float32)
+    if preds_local.numel():
+        ops.pearson_pick_shift(preds_local.contiguous(), trues_local.contiguous(), shift, layout=layout)
+        ops.pearson_stats(preds_local.contiguous(), trues_local.contiguous(), stats, layout=layout, shift=shift)
     _, ws = world()
     if ws > 1:
+        ops.pearson_recenter(stats, shift, None)  # ranks picked different pivots: merge about pivot 0 in fp64
         dist.all_reduce(stats, group=group)
     r, _ = ops.pearson_finalize(stats[0])
     return r

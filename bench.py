@@ -224,10 +224,12 @@ def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with
     trues = torch.randn(EVAL_WINDOWS, hi - lo, EVAL_TRS, device="cuda", generator=g)
     preds = 0.2 * trues + torch.randn(EVAL_WINDOWS, hi - lo, EVAL_TRS, device="cuda", generator=g)
     stats = torch.zeros(1, 6, hi - lo, device="cuda", dtype=torch.float64)
+    shift = torch.empty(2, hi - lo, device="cuda", dtype=torch.float32)
 
     def one():
-        stats.zero_()
-        ops.pearson_stats(preds, trues, stats, layout="bdt")
+        ops.zero_(stats)
+        ops.pearson_pick_shift(preds, trues, shift, layout="bdt")  # per-parcel pivots (first row): centred moments
+        ops.pearson_stats(preds, trues, stats, layout="bdt", shift=shift)
         return ops.pearson_finalize(stats[0])[0]
 
     for _ in range(max(warmup, 3)):
@@ -238,9 +240,10 @@ def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b, c in ev:  # operands (2 x 1.02 GB / G) exceed L2, every pass streams from HBM
         a.record()
-        stats.zero_()
+        ops.zero_(stats)
+        ops.pearson_pick_shift(preds, trues, shift, layout="bdt")
         b.record()
-        ops.pearson_stats(preds, trues, stats, layout="bdt")
+        ops.pearson_stats(preds, trues, stats, layout="bdt", shift=shift)
         c.record()
         r = ops.pearson_finalize(stats[0])[0]
     end = torch.cuda.Event(enable_timing=True)
@@ -547,13 +550,9 @@ def run_ensemble(args):
     with torch.no_grad():
         preds = torch.cat([model(b) for b in shared])                          # (4B, O, T') this member's predictions
         trues = torch.cat([b.data["fmri"] for b in shared]).cuda()
-        stats = torch.zeros(1, 6, 1000, device="cuda", dtype=torch.float64)
-        ops.pearson_stats(preds, trues, stats, layout="bdt")
-        r_member = ops.pearson_finalize(stats[0])[0]                           # (O,) per-parcel r of this member
+        r_member = ops.pearson_r(preds, trues, layout="bdt")[0]                # (O,) per-parcel r of this member
         ens = parallel.ensemble_average(preds, r_member, temperature=0.3)      # weighted all-reduce (reference weighting)
-        stats.zero_()
-        ops.pearson_stats(ens.contiguous(), trues, stats, layout="bdt")
-        r_ens, mean_ens = ops.pearson_finalize(stats[0], want_mean=True)
+        r_ens, mean_ens = ops.pearson_r(ens.contiguous(), trues, layout="bdt", want_mean=True)
     f1.record()
     barrier()
     ms_eval = f0.elapsed_time(f1)

@@ -215,13 +215,23 @@ int tribe_mse_fwd_bwd(const float* pred, const float* target, float* loss_out, f
  * element(r, p) = base[(r / t_len) * stride_b + p * stride_p + (r % t_len) * stride_t], which covers both the
  * flattened (b t) x d view of a (B, D, T) tensor (stride_b=D*T, stride_p=T, stride_t=1, t_len=T) and a plain
  * row-major (N, O) matrix (t_len=1, stride_b=O, stride_p=1).
- * stats: fp64 [6][n_parcels] = n, sum_x, sum_y, sum_xx, sum_yy, sum_xy (shifted by `shift_x/shift_y` per parcel when
- * non-NULL for conditioning); accumulated (+=) so that batches can be streamed; group: optional int64 per row/t_len
- * block selecting stats + group*6*n_parcels (GroupedMetric, metrics/base.py:52-78). */
+ * stats: fp64 [6][n_parcels] = n, sum_x', sum_y', sum_x'x', sum_y'y', sum_x'y' with x' = x - shift[p], y' = y -
+ * shift[n_parcels + p] (shift: fp32 [2][n_parcels] per-parcel pivots, NULL = 0).  scipy / torchmetrics centre before
+ * they multiply; raw fp32 moments lose the variance once |mean| >> sigma, pivoted ones do not, and r is invariant to the
+ * pivot.  All calls that accumulate into one stats block must pass the SAME pivots (tribe_pearson_pick_shift takes them
+ * from the first row; tribe_pearson_recenter re-expresses a block about other pivots, e.g. before merging ranks).
+ * Accumulated (+=) so that batches can be streamed; group: optional int64 per row/t_len block selecting
+ * stats + group*6*n_parcels (GroupedMetric, metrics/base.py:52-78). */
 int tribe_pearson_stats(const float* pred, const float* target, int64_t n_rows, int64_t n_parcels, int64_t t_len,
                         int64_t stride_b, int64_t stride_p, int64_t stride_t, const int64_t* group, int64_t n_groups,
-                        double* stats, void* stream);
-/* r[p] = clamp(cov / sqrt(var_x var_y), -1, 1) from the statistics; r fp32 [n_parcels]; mean_out optional fp32 [1]. */
+                        const float* shift, double* stats, void* stream);
+/* shift[p] = pred[p * stride_p], shift[n_parcels + p] = target[p * stride_p]: the first sample of every parcel (exactly
+ * the column value for a constant column, so its shifted sums are exactly 0 and r = NaN like scipy.stats.pearsonr). */
+int tribe_pearson_pick_shift(const float* pred, const float* target, int64_t n_parcels, int64_t stride_p, float* shift, void* stream);
+/* In place: statistics taken about pivots shift_old -> the same statistics about shift_new (either may be NULL = 0), fp64. */
+int tribe_pearson_recenter(double* stats, int64_t n_groups, int64_t n_parcels, const float* shift_old, const float* shift_new, void* stream);
+/* r[p] = clamp(cov / sqrt(var_x var_y), -1, 1) from the statistics (NaN for a constant column or NaN input, like
+ * scipy / torchmetrics; n = 1 gives NaN where scipy raises); r fp32 [n_parcels]; mean_out optional fp32 [1]. */
 int tribe_pearson_finalize(const double* stats, int64_t n_parcels, float* r, float* mean_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -310,12 +320,13 @@ int tribe_xgpu_barrier(const TribeXgpuPeers* flags, int32_t rank, int32_t world,
 int tribe_point_loss_fwd_bwd(const float* pred, const float* target, float* loss_out, float* grad, int32_t kind, float param,
                              float grad_scale, int64_t n, double* partial, void* stream);
 /* PearsonLoss(dim=1) = reduce_p (1 - pcc_p), pcc_p = cov / (std_x std_y + 1e-8) over all rows of parcel p.
- * Forward: tribe_pearson_stats into a ZEROED stats block, then this finalize, which writes loss_out[0] and (optional)
+ * Forward: tribe_pearson_stats into a ZEROED stats block (with the pivots `shift`, or NULL), then this finalize, which writes loss_out[0] and (optional)
  * coef fp32 [4][n_parcels] = mean_x, mean_y, 1/D, cov*std_y/(D^2 std_x) for the backward pass.
  * Backward: grad[i] = -(upstream[0] * (reduction_mean ? 1/n_parcels : 1)) * (coef2[p] (y_i - coef1[p]) - coef3[p] (x_i - coef0[p]))
  * with p = (i / t_len) % n_parcels over contiguous (N, O) (t_len = 1) or (B, O, T) (t_len = T) tensors; upstream is a
  * device scalar (autograd's grad_output) or NULL for 1. */
-int tribe_pearson_loss_finalize(const double* stats, int64_t n_parcels, int32_t reduction_mean, float* coef, float* loss_out, void* stream);
+int tribe_pearson_loss_finalize(const double* stats, int64_t n_parcels, int32_t reduction_mean, const float* shift, float* coef,
+                                float* loss_out, void* stream);
 int tribe_pearson_loss_bwd(const float* pred, const float* target, const float* coef, const float* upstream, int32_t reduction_mean,
                            float* grad, int64_t n, int64_t n_parcels, int64_t t_len, void* stream);
 

@@ -49,11 +49,9 @@ for s in range(3):
     assert abs(got[str(s)] - want) < 1e-5, (s, got[str(s)], want)
 # ensemble: every rank is a member predicting the SAME windows
 member = (pred + 0.1 * (rank + 1) * torch.randn(pred.shape, generator=torch.Generator().manual_seed(10 + rank))).cuda()
-st = torch.zeros(1, 6, Onum, device="cuda", dtype=torch.float64)
 from algonauts2025_b200 import ops  # noqa: E402
 
-ops.pearson_stats(member, true.cuda(), st, layout="bdt")
-r_member = ops.pearson_finalize(st[0])[0]
+r_member = ops.pearson_r(member, true.cuda(), layout="bdt")[0]
 ens = parallel.ensemble_average(member, r_member, temperature=0.3)
 members = [torch.empty_like(member) for _ in range(world)]
 rs = [torch.empty_like(r_member) for _ in range(world)]

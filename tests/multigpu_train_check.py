@@ -92,7 +92,7 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
             continue
         sd, losses, tr, shadow, mom = train(p_drop, path, graphs, mine, contrastive=contrastive)
         same_on_all_ranks(torch.cat([v.flatten().float() for v in sd.values()]), f"{path} masters")
-        same_on_all_ranks(shadow.view(torch.int16), f"{path} bf16 shadow")
+        same_on_all_ranks(shadow.view(torch.uint8), f"{path} bf16 shadow")
         if graphs:
             assert tr._graphed.replays >= 1, f"{path}: graphs were not replayed"
         for k in sd:

@@ -444,3 +444,93 @@ def test_pearson_ragged_and_odd_parcel_counts():
         np.testing.assert_allclose(st[0], n)
         np.testing.assert_allclose(st[1], p.double().sum(0).numpy(), rtol=1e-6, atol=1e-5)
         np.testing.assert_allclose(st[5], (p.double() * t.double()).sum(0).numpy(), rtol=1e-6, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------- Pearson robustness
+@pytest.mark.parametrize("layout", ["bdt", "no"])
+def test_pearson_large_mean_constant_nan_and_tiny_n(layout):
+    """scipy.stats.pearsonr (main.py:474-476) centres before it multiplies.  The pivoted statistics must agree with it
+    to 1e-3 (north_star) when |mean| = 1e3 sigma, give NaN for constant columns and NaN inputs like scipy does, and
+    +-1 for two rows; raw fp32 moments (shift=None, the round-1 kernel) are shown to FAIL the large-mean case, which is
+    what the pivot is for."""
+    import scipy.stats
+
+    torch.manual_seed(21)
+    Bsz, D, T = 6, 64, 100
+    true = torch.randn(Bsz, D, T)
+    pred = 0.3 * true + torch.randn(Bsz, D, T)
+    true = true * 2.0 + 2000.0                      # mean = 1e3 sigma
+    pred = pred * 0.5 - 500.0
+    pred[:, 5] = 3.25                               # constant prediction column  -> scipy: NaN
+    true[:, 9] = -7.0                               # constant target column
+    pred[2, 11, 17] = float("nan")                  # NaN input                   -> NaN
+    pf, tf = O.flatten_bdt(pred).contiguous(), O.flatten_bdt(true).contiguous()
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # float64 scipy on the same fp32-quantised inputs = the exact answer; float32 scipy (what main.py runs) for 1e-3
+        ref = np.array([scipy.stats.pearsonr(tf[:, p].double().numpy(), pf[:, p].double().numpy())[0] for p in range(D)], dtype=np.float64)
+        ref32 = np.array([scipy.stats.pearsonr(tf[:, p].numpy(), pf[:, p].numpy())[0] for p in range(D)], dtype=np.float64)
+    if layout == "bdt":
+        a, b = pred.to(DEV), true.to(DEV)
+    else:
+        a, b = pf.to(DEV), tf.to(DEV)
+    r = ops.pearson_r(a, b, layout=layout)[0].cpu().numpy().astype(np.float64)
+    nan_ref = np.isnan(ref)
+    assert set(np.nonzero(nan_ref)[0]) == {5, 9, 11}
+    assert np.array_equal(np.isnan(r), nan_ref), (np.nonzero(np.isnan(r))[0], np.nonzero(nan_ref)[0])
+    assert float(np.abs(r[~nan_ref] - ref[~nan_ref]).max()) < 1e-5
+    assert float(np.abs(r[~nan_ref] - ref32[~nan_ref]).max()) < 1e-3
+    # the unpivoted moments lose the variance at this mean / sigma ratio
+    raw = torch.zeros(1, 6, D, device=DEV, dtype=torch.float64)
+    ops.pearson_stats(a, b, raw, layout=layout)
+    r_raw = ops.pearson_finalize(raw[0])[0].cpu().numpy()
+    ok = ~nan_ref & ~np.isnan(r_raw)
+    assert (~np.isnan(r_raw[~nan_ref])).sum() == 0 or float(np.abs(r_raw[ok] - ref[ok]).max()) > 1e-3
+    # streamed in three chunks with ONE pivot set + re-centred to pivot 0 (what the cross-rank merge does)
+    shift = torch.empty(2, D, device=DEV, dtype=torch.float32)
+    st = torch.zeros(1, 6, D, device=DEV, dtype=torch.float64)
+    ops.pearson_pick_shift(a, b, shift, layout=layout)
+    n0 = a.shape[0]
+    for lo, hi in ((0, n0 // 3), (n0 // 3, n0 // 2), (n0 // 2, n0)):
+        ops.pearson_stats(a[lo:hi].contiguous(), b[lo:hi].contiguous(), st, layout=layout, shift=shift)
+    r_s = ops.pearson_finalize(st[0])[0].cpu().numpy()
+    assert float(np.nanmax(np.abs(r_s - r))) < 1e-6
+    ops.pearson_recenter(st, shift, None)
+    want_sx = pf.double().sum(0).numpy()
+    got = st[0].cpu().numpy()
+    keep = ~nan_ref
+    np.testing.assert_allclose(got[1][keep], want_sx[keep], rtol=1e-9)
+    r_c = ops.pearson_finalize(st[0])[0].cpu().numpy()
+    assert float(np.nanmax(np.abs(r_c[keep] - ref[keep]))) < 1e-4
+    # two rows: r = +-1 exactly like scipy; one row: NaN (scipy raises)
+    two_p, two_t = torch.tensor([[1000.5, -3.0], [1001.5, -4.0]]), torch.tensor([[7.0, 2.0], [9.0, 5.0]])
+    r2 = ops.pearson_r(two_p.to(DEV), two_t.to(DEV), layout="no")[0].cpu().numpy()
+    np.testing.assert_allclose(r2, [1.0, -1.0], atol=1e-6)
+    r1 = ops.pearson_r(two_p[:1].contiguous().to(DEV), two_t[:1].contiguous().to(DEV), layout="no")[0].cpu().numpy()
+    assert np.isnan(r1).all()
+
+
+def test_pearson_metric_classes_use_pivots():
+    from algonauts2025_b200.metrics import GroupedMetric, MultidimPearsonCorrCoef
+
+    torch.manual_seed(22)
+    true = torch.randn(8, 40, 100) + 3000.0
+    pred = 0.4 * (true - 3000.0) + torch.randn(8, 40, 100) + 100.0
+    ref = O.pearson_columns_f64(O.flatten_bdt(pred).numpy(), O.flatten_bdt(true).numpy())
+    m = MultidimPearsonCorrCoef(num_outputs=40)
+    for lo in range(0, 8, 3):
+        m.update_bdt(pred[lo:lo + 3].to(DEV), true[lo:lo + 3].to(DEV))
+    assert abs(float(m.compute()) - float(ref.mean())) < 1e-5
+    assert float(np.abs(m.per_output().cpu().numpy() - ref).max()) < 1e-5
+    m.reset()
+    m.update(O.flatten_bdt(pred).contiguous().to(DEV), O.flatten_bdt(true).contiguous().to(DEV))
+    assert abs(float(m.compute()) - float(ref.mean())) < 1e-5
+    subj = torch.arange(8) % 2
+    gm = GroupedMetric("MultidimPearsonCorrCoef", {"num_outputs": 40})
+    gm.update_bdt(pred.to(DEV), true.to(DEV), groups=subj.to(DEV))
+    got = gm.compute()
+    for s in (0, 1):
+        want = O.pearson_columns_f64(O.flatten_bdt(pred[subj == s]).numpy(), O.flatten_bdt(true[subj == s]).numpy()).mean()
+        assert abs(got[str(s)] - want) < 1e-5

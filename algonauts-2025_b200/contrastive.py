@@ -31,6 +31,9 @@ class _HeadFn(torch.autograd.Function):
             x = x.unsqueeze(1)
         B, T = x.shape[0], x.shape[-1]
         M, K, H = B * T, lin.in_features, lin.out_features
+        k_in = x.shape[2] if model.config.layer_aggregation == "mean" else x.shape[1] * x.shape[2]
+        if k_in != K:
+            raise TribeError(f"contrastive head '{modality}': feature width {k_in} does not match in_features {K}")
         feat = torch.empty(M, K, device=eng.device, dtype=torch.bfloat16)
         ops.ingest_features(x, feat, 0, model.config.layer_aggregation == "mean")
         out = torch.empty(M, H, device=eng.device, dtype=torch.float32)

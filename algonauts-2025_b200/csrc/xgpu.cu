@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tribe_b200.h"
 #include "tribe_internal.h"
@@ -182,9 +183,66 @@ __global__ void __launch_bounds__(128, 6) sharded_adam_kernel(const ShardedAdamK
   }
 }
 
+// Micro-benchmark of the pieces (tools/xgpu_probe.py): mode 0 = multimem.ld_reduce only, 1 = peer loads only (world
+// peers), 2 = local p/m/v stream only (6 x 16 B loads + 6 stores), 3 = multimem.st bf16 only, 4 = ld_reduce with UNROLL 4.
+__global__ void __launch_bounds__(128, 6) xgpu_probe_kernel(const ShardedAdamK a, int mode, float* sink) {
+  const int64_t nv = a.n >> 3;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float acc = 0.f;
+  if (mode == 4) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += 4 * stride) {
+      float4 g[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t e = (i + u * stride < nv ? i + u * stride : i) << 3;
+        g[2 * u] = xg_ld_reduce(a.g_mc + e), g[2 * u + 1] = xg_ld_reduce(a.g_mc + e + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += g[u].x + g[u].y + g[u].z + g[u].w;
+    }
+  } else {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+      const int64_t e = i << 3;
+      if (mode == 0) {
+        const float4 g0 = xg_ld_reduce(a.g_mc + e), g1 = xg_ld_reduce(a.g_mc + e + 4);
+        acc += g0.x + g0.y + g0.z + g0.w + g1.x + g1.y + g1.z + g1.w;
+      } else if (mode == 1) {
+        for (int r = 0; r < a.world; ++r) {
+          const float* gp = reinterpret_cast<const float*>(a.g_peer.ptr[r]) + e;
+          const float4 g0 = xg_ld_peer(gp), g1 = xg_ld_peer(gp + 4);
+          acc += g0.x + g0.y + g0.z + g0.w + g1.x + g1.y + g1.z + g1.w;
+        }
+      } else if (mode == 2) {
+        float4 p0 = __ldcs(reinterpret_cast<const float4*>(a.p + e)), p1 = __ldcs(reinterpret_cast<const float4*>(a.p + e + 4));
+        float4 m0 = __ldcs(reinterpret_cast<const float4*>(a.m + e)), m1 = __ldcs(reinterpret_cast<const float4*>(a.m + e + 4));
+        float4 v0 = __ldcs(reinterpret_cast<const float4*>(a.v + e)), v1 = __ldcs(reinterpret_cast<const float4*>(a.v + e + 4));
+        p0.x += m0.x * v0.x, p1.x += m1.x * v1.x;
+        __stcs(reinterpret_cast<float4*>(a.p + e), p0), __stcs(reinterpret_cast<float4*>(a.p + e + 4), p1);
+        __stcs(reinterpret_cast<float4*>(a.m + e), m0), __stcs(reinterpret_cast<float4*>(a.m + e + 4), m1);
+        __stcs(reinterpret_cast<float4*>(a.v + e), v0), __stcs(reinterpret_cast<float4*>(a.v + e + 4), v1);
+      } else if (mode == 3) {
+        xg_mc_store(a.s_mc + e, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      }
+    }
+  }
+  if (acc == 123.456f) sink[0] = acc;
+}
+
 }  // namespace tribe
 
 using namespace tribe;
+
+extern "C" int tribe_xgpu_probe(const TribeShardedAdam* a, int32_t mode, int32_t blocks, float* sink, void* stream) {
+  if (!a || !sink || a->n <= 0 || (a->n & 7)) return set_error(TRIBE_EINVAL, "xgpu_probe: bad arguments");
+  ShardedAdamK k;
+  k.p = a->param, k.m = a->m, k.v = a->v;
+  k.g_mc = a->grad_mc, k.s_mc = reinterpret_cast<uint16_t*>(a->shadow_mc), k.p_mc = a->param_mc;
+  k.g_peer = a->grad_peer, k.s_peer = a->shadow_peer, k.p_peer = a->param_peer;
+  k.n = a->n, k.world = a->world, k.rank = a->rank, k.bcast = 0, k.inv_world = 1.f, k.hyper = a->hyper;
+  xgpu_probe_kernel<<<blocks > 0 ? blocks : 148, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(k, mode, sink);
+  TRIBE_CHECK_LAUNCH("xgpu_probe");
+  return TRIBE_OK;
+}
 
 extern "C" int tribe_xgpu_barrier(const TribeXgpuPeers* flags, int32_t rank, int32_t world, int32_t slot, uint32_t* err_flag, double timeout_s,
                                   void* stream) {
@@ -225,6 +283,18 @@ extern "C" int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream) 
   k.hyper = a->hyper;
   const int blocks = grid_for(a->n / 8, 128, a->max_blocks > 0 ? a->max_blocks : 148);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // the kernel has to share SMs with the persistent GEMM CTAs (~222 KB of dynamic shared memory each): ask for the same
+  // L1 / shared-memory split so that an SM does not have to drain before it can host both
+  static const bool carveout_set = [] {
+    const char* e = getenv("TRIBE_XGPU_CARVEOUT");
+    const int pct = e ? atoi(e) : 100;
+    if (pct >= 0) {
+      cudaFuncSetAttribute(sharded_adam_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(sharded_adam_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    return true;
+  }();
+  (void)carveout_set;
   if (mc)
     sharded_adam_kernel<true><<<blocks, 128, 0, s>>>(k);
   else

@@ -192,6 +192,13 @@ class Plan:
         self.x_input = False    # transformer_forward entry: encoder input given as a tensor
         self.training = False
 
+    def __del__(self):
+        # a grad-enabled forward whose backward never runs (main.py:349 warm-up call, a skipped loss, an exception):
+        # the workspace returns to the pool when autograd drops the graph that holds this plan
+        ws = self.__dict__.get("ws")
+        if ws is not None:
+            ws.in_use = False
+
 
 class Engine:
     def __init__(self, model):
@@ -228,6 +235,7 @@ class Engine:
             b.data = b.data.to(self.device)
         self.proj_in = {mod: lin.in_features for mod, lin in m.projectors.items()}
         self._ws_pool.clear()
+        self._rope.clear()  # the rotary table lives on the device too
 
     def _check_flat(self):
         if self.flat is None or not self.flat.intact():
@@ -243,12 +251,17 @@ class Engine:
             self._rope[T] = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().to(self.device)
         return self._rope[T]
 
+    MAX_WORKSPACES_PER_SHAPE = 4  # a contrastive train step holds two; anything beyond is a leak, not a need
+
     def _workspace(self, B, T):
         pool = self._ws_pool.setdefault((B, T), [])
         for ws in pool:
             if not ws.in_use:
                 ws.in_use = True
                 return ws
+        if len(pool) >= self.MAX_WORKSPACES_PER_SHAPE:
+            raise TribeError(f"{len(pool)} activation workspaces of shape (B={B}, T={T}) are held by forward passes whose backward never ran "
+                             "(outputs with an autograd graph are still referenced); drop them or call under torch.no_grad()")
         ws = Workspace(self, B, T)
         ws.in_use = True
         pool.append(ws)
@@ -271,9 +284,44 @@ class Engine:
         return self.flat.params[name]
 
     # ------------------------------------------------------------------------------------------------ forward
+    def _validate_batch(self, batch_data):
+        """Every modality must be (B, L, D, T) / (B, D, T) with L*D (or D for layer_aggregation="mean") equal to its
+        projector's in_features and the same (B, T) as the others; the reference fails in its matmul, the kernels would
+        read or write out of bounds instead."""
+        m = self.model
+        mean = m.config.layer_aggregation == "mean"
+        ref = None
+        for mod in m.feature_dims:
+            if mod not in batch_data or mod not in self.proj_in:
+                continue
+            x = batch_data[mod]
+            if x.dim() not in (3, 4):
+                raise TribeError(f"modality '{mod}': expected (B, L, D, T) or (B, D, T), got {tuple(x.shape)}")
+            L, D = (1, x.shape[1]) if x.dim() == 3 else (x.shape[1], x.shape[2])
+            k = D if mean else L * D
+            if k != self.proj_in[mod]:
+                raise TribeError(f"modality '{mod}': feature width {k} (L={L}, D={D}) does not match the projector's in_features {self.proj_in[mod]}")
+            bt = (x.shape[0], x.shape[-1])
+            if ref is None:
+                ref = (mod, bt)
+            elif bt != ref[1]:
+                raise TribeError(f"modality '{mod}' has (B, T) = {bt} but '{ref[0]}' has {ref[1]}")
+        if ref is None:
+            raise TribeError("batch holds none of the model's modalities")
+        return ref[1]
+
     def forward(self, plan: Plan, batch_data, x_in=None):
         self._check_flat()
         self.flat.refresh_bf16()
+        if not plan.x_input:
+            self._validate_batch(batch_data)
+        try:
+            return self._forward(plan, batch_data, x_in)
+        except BaseException:
+            self.release(plan)
+            raise
+
+    def _forward(self, plan: Plan, batch_data, x_in=None):
         m, H, heads, dh, F = self.model, self.hidden, self.heads, self.dh, self.ff
         cfg = m.config
         if plan.x_input:
@@ -408,6 +456,9 @@ class Engine:
         parameter that did not take part — the projector of a dropped modality, model.py:158-159 — keeps ``grad is
         None`` exactly like the reference's autograd) and returns d(loss)/d(encoder input) when asked."""
         fl, m, ws = self.flat, self.model, plan.ws
+        if ws is None:
+            raise TribeError("backward through this forward pass ran already: its activations were released "
+                             "(backward(retain_graph=True) followed by a second backward is not supported)")
         H, heads, dh, F = self.hidden, self.heads, self.dh, self.ff
         B, T, M, Tp = ws.B, ws.T, ws.M, ws.Tp
         BH = B * heads

@@ -61,6 +61,54 @@ class _Fn(torch.autograd.Function):
         return None, dx, None, None, None
 
 
+class _SubjectLayersFn(torch.autograd.Function):
+    """Stand-alone ``SubjectLayers.forward`` with its backward on the same tcgen05 GEMMs the engine uses for the readout."""
+
+    @staticmethod
+    def forward(ctx, x, weights, bias, subj):
+        B, C, T = x.shape
+        N, _, D = weights.shape
+        dev = x.device
+        xt = torch.empty(B * T, C, device=dev, dtype=torch.bfloat16)
+        ops.ingest_features(x.detach().unsqueeze(1), xt, 0, False)  # (B, C, T) -> bf16 (B*T, C)
+        w16 = weights.detach().to(torch.bfloat16).contiguous()
+        out = torch.empty(B, D, T, device=dev, dtype=torch.float32)
+        x_op = ops.Operand(xt, inner=C, rows=T, row_stride=C, batch=B, batch_stride=T * C)
+        w_op = ops.Operand(w16, inner=D, rows=C, row_stride=D, batch=N, batch_stride=C * D, mn_major=True, gather=subj)
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        ops.gemm(x_op, w_op, out, T, D, C, ldd=T, batch=B, d_zo=D * T, transposed=True, bias=b32, bias_gathered=b32 is not None,
+                 bias_z_stride=D)
+        ctx.save_for_backward(xt, w16, subj)
+        ctx.dims, ctx.has_bias = (B, C, T, N, D), bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xt, w16, subj = ctx.saved_tensors
+        B, C, T, N, D = ctx.dims
+        dev = grad_out.device
+        dyT = torch.empty(B, T, D, device=dev, dtype=torch.bfloat16)
+        ops.transpose_cast_bot(grad_out.contiguous().float(), dyT)
+        dx = dW = dB = None
+        if ctx.needs_input_grad[0]:
+            # dx[b] (C, T) = W[s_b] (C, D) dy[b] (D, T): per sample (T, D) x (C, D)^T, stored transposed
+            dx = torch.empty(B, C, T, device=dev, dtype=torch.float32)
+            dy_op = ops.Operand(dyT, inner=D, rows=T, row_stride=D, batch=B, batch_stride=T * D)
+            w_op = ops.Operand(w16, inner=D, rows=C, row_stride=D, batch=N, batch_stride=C * D, gather=subj)
+            ops.gemm(dy_op, w_op, dx, T, C, D, ldd=T, batch=B, d_zo=C * T, transposed=True)
+        if ctx.needs_input_grad[1]:
+            # dW[s] (C, D) = sum_{b: s_b = s} x[b] (C, T) dy[b]^T (T, D): subject-keyed K loop, no per-sample (B, C, D) tensor
+            dW = torch.empty(N, C, D, device=dev, dtype=torch.float32)
+            xa = ops.Operand(xt, inner=C, rows=T, row_stride=C, batch=B, batch_stride=T * C, mn_major=True)
+            dyb = ops.Operand(dyT, inner=D, rows=T, row_stride=D, batch=B, batch_stride=T * D, mn_major=True)
+            ops.gemm(xa, dyb, dW.view(N * C, D), C, D, T, ldd=D, batch=N, d_zo=C * D, kgroup=subj)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dB = torch.empty(N, D, device=dev, dtype=torch.float32)
+            ops.zero_(dB)
+            ops.subject_bias_grad(dyT, subj, dB, B, T, D, N)
+        return dx, dW, dB, None
+
+
 class SubjectLayers(nn.Module):
     """Per-subject linear readout (common.py:14-71).  ``forward(x (B, C, T), subjects (B, 1))`` runs the
     subject-index-gathered grouped GEMM; inside ``FmriEncoder`` the engine calls the same GEMM on pooled tokens."""
@@ -88,23 +136,18 @@ class SubjectLayers(nn.Module):
         self.average_subjects = average_subjects
 
     def forward(self, x: torch.Tensor, subjects: torch.Tensor) -> torch.Tensor:
+        """common.py:45-67 stand-alone: ``einsum("bct,bcd->bdt", x, weights[subjects]) + bias[subjects]``, differentiable
+        w.r.t. ``x``, ``weights`` and ``bias`` (gathered dgrad GEMM, subject-keyed grouped wgrad, bias reduction)."""
         if not x.is_cuda:
             raise TribeError("SubjectLayers needs CUDA tensors (no CPU fallback)")
-        B, C, T = x.shape
-        N, C2, D = self.weights.shape
+        if x.dim() != 3 or x.shape[1] != self.weights.shape[1]:
+            raise TribeError(f"SubjectLayers expects x (B, {self.weights.shape[1]}, T), got {tuple(x.shape)}")
+        if subjects.numel() != x.shape[0]:
+            raise TribeError(f"SubjectLayers: {subjects.numel()} subject ids for a batch of {x.shape[0]}")
+        N = self.weights.shape[0]
         assert subjects.max() < N, "Subject index higher than number of subjects used to initialize the weights."
-        dev = x.device
-        xt = torch.empty(B * T, C, device=dev, dtype=torch.bfloat16)
-        ops.ingest_features(x.detach().unsqueeze(1), xt, 0, False)  # (B, C, T) -> bf16 (B*T, C)
-        w16 = self.weights.detach().to(dev).to(torch.bfloat16)
-        out = torch.empty(B, D, T, device=dev, dtype=torch.float32)
-        subj = subjects.flatten().to(dev, torch.int64).contiguous()
-        x_op = ops.Operand(xt, inner=C, rows=T, row_stride=C, batch=B, batch_stride=T * C)
-        w_op = ops.Operand(w16, inner=D, rows=C, row_stride=D, batch=N, batch_stride=C * D, mn_major=True, gather=subj)
-        bias = self.bias.detach().to(dev).float() if self.bias is not None else None
-        ops.gemm(x_op, w_op, out, T, D, C, ldd=T, batch=B, d_zo=D * T, transposed=True, bias=bias, bias_gathered=bias is not None,
-                 bias_z_stride=D)
-        return out
+        subj = subjects.flatten().to(x.device, torch.int64).contiguous()
+        return _SubjectLayersFn.apply(x, self.weights.to(x.device), self.bias.to(x.device) if self.bias is not None else None, subj)
 
     def __repr__(self):
         S, C, D = self.weights.shape
@@ -292,8 +335,9 @@ class FmriEncoder(nn.Module):
             self.__dict__["_subject_event"] = None
             assert bad == 0, self._MSG
 
-    def _subjects(self, batch):
-        subject_id = batch.data.get("subject_id", None)
+    def _subjects(self, batch, subject_id=None):
+        if subject_id is None:
+            subject_id = batch.data.get("subject_id", None) if batch is not None else None
         if subject_id is None:
             return None
         self._engine._check_flat()
@@ -330,7 +374,7 @@ class FmriEncoder(nn.Module):
         # and running that node during a CUDA-graph capture would tie the capture to uncaptured work on that stream.
         return torch.empty(0, device=self._engine.device, requires_grad=True)
 
-    def _run(self, batch, *, mode, pool=True, x_in=None):
+    def _run(self, batch, *, mode, pool=True, x_in=None, subject_id=None):
         eng = self._engine
         eng._check_flat()
         plan = Plan()
@@ -344,6 +388,12 @@ class FmriEncoder(nn.Module):
         else:
             plan.x_input = True
             data = None
+            if hasattr(self, "subject_embed"):
+                if subject_id is None:
+                    raise TribeError("transformer_forward: subject_embedding=True needs subject_id (model.py:171-172)")
+                plan.subjects = self._subjects(None, subject_id)
+                if plan.subjects.numel() != x_in.shape[0]:
+                    raise TribeError(f"transformer_forward: {plan.subjects.numel()} subject ids for a batch of {x_in.shape[0]}")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             return _Fn.apply(self._anchor(), x_in, eng, plan, data)
@@ -363,8 +413,7 @@ class FmriEncoder(nn.Module):
         eng.flat.refresh_bf16()
         dropped = self._draw_dropout()
         self.last_dropped = list(dropped)
-        ref = next(batch.data[k] for k in batch.data if k in self.feature_dims)
-        B, T = ref.shape[0], ref.shape[-1]
+        B, T = eng._validate_batch(batch.data)
         M, H = B * T, self.hidden
         mods = list(self.feature_dims.keys())
         cat = self.config.feature_aggregation == "cat"
@@ -386,16 +435,17 @@ class FmriEncoder(nn.Module):
             first = False
         return out.view(B, T, H)
 
-    def _encode_tensor(self, x, add_pos=True):
+    def _encode_tensor(self, x, add_pos=True, subject_id=None):
         if not add_pos:
             raise TribeError("calling .encoder(x) directly is not supported; use transformer_forward")
-        return self._run(None, mode="latents", x_in=x)
+        if x.dim() != 3 or x.shape[-1] != self.hidden:
+            raise TribeError(f"transformer_forward expects (B, T, {self.hidden}), got {tuple(x.shape)}")
+        return self._run(None, mode="latents", x_in=x, subject_id=subject_id)
 
     def transformer_forward(self, x, subject_id=None):
-        """model.py:167-174: ``x + time_pos_embed[:, :T]`` (+ subject embedding) -> encoder."""
-        if hasattr(self, "subject_embed"):
-            raise TribeError("transformer_forward with subject_embedding=True: call forward(batch) instead")
-        return self._encode_tensor(x, add_pos=True)
+        """model.py:167-174: ``x + time_pos_embed[:, :T]`` (+ ``subject_embed(subject_id)`` broadcast over T when the
+        model was built with ``subject_embedding=True``) -> encoder.  Differentiable w.r.t. ``x`` and every parameter."""
+        return self._encode_tensor(x, add_pos=True, subject_id=subject_id)
 
     # --- Contrastive alignment helpers (model.py:177-241) -------------------------------------------------------------
     def get_brain_latents(self, batch: SegmentData) -> torch.Tensor:

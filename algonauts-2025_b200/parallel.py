@@ -232,6 +232,13 @@ class ShardedStep:
         """The fused reduce -> Adam -> multicast kernel on [lo, hi) of the flat layout (a range this rank owns)."""
         from . import _lib
 
+        a = self.kernel_args(lo, hi, bcast, hyper_ptr)
+        st = self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().tribe_sharded_adam_step(self._ctypes.byref(a), st), "tribe_sharded_adam_step")
+
+    def kernel_args(self, lo: int, hi: int, bcast: bool, hyper_ptr: int):
+        from . import _lib
+
         fl = self.flat
         a = _lib.TribeShardedAdam()
         a.param, a.m, a.v = fl.flat.data_ptr() + 4 * lo, fl.adam_m.data_ptr() + 4 * lo, fl.adam_v.data_ptr() + 4 * lo
@@ -245,8 +252,7 @@ class ShardedStep:
             a.shadow_peer.ptr[r] = self._peers["bf16"][r] + 2 * lo
             a.param_peer.ptr[r] = self._peers["flat"][r] + 4 * lo
         a.n, a.world, a.rank, a.bcast_master, a.max_blocks = hi - lo, self.world, self.rank, int(bcast), self.max_blocks
-        st = self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.load().tribe_sharded_adam_step(self._ctypes.byref(a), st), "tribe_sharded_adam_step")
+        return a
 
     # -------------------------------------------------------------------------------------------- step protocol
     def begin_step(self, backward_passes: int | None = None, head_passes: int | None = None):

@@ -309,6 +309,9 @@ typedef struct TribeShardedAdam {
   int32_t world, rank, bcast_master, max_blocks;
 } TribeShardedAdam;
 int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream);
+/* Micro-benchmark of the pieces of the kernel above (tools/xgpu_probe.py; not used by the product path): mode 0 =
+ * multimem.ld_reduce only, 1 = peer loads only, 2 = local param/m/v stream only, 3 = multimem.st only, 4 = ld_reduce x4. */
+int tribe_xgpu_probe(const TribeShardedAdam* a, int32_t mode, int32_t blocks, float* sink, void* stream);
 int tribe_xgpu_barrier(const TribeXgpuPeers* flags, int32_t rank, int32_t world, int32_t slot, uint32_t* err_flag, double timeout_s,
                        void* stream);
 

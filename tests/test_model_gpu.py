@@ -343,3 +343,55 @@ def test_config1_single_subject_short_clips_match_oracle(subject_embedding):
     assert rel_l2(got, want) <= 3e-2
     with torch.no_grad():
         assert_pred_close(model(batch, pool_outputs=False), oracle(as_oracle_batch(batch), pool_outputs=False))
+
+
+# ----------------------------------------------------------------------------------------------- API holes closed in round 2
+def test_transformer_forward_with_subject_embedding_and_gradients():
+    """model.py:167-174 with ``subject_embedding=True`` (the ensemble grid samples it, run_ensemble.py:31):
+    ``x + time_pos_embed[:, :T] + subject_embed(subject_id)`` -> encoder; forward and d/dx, d/d(subject_embed) vs oracle."""
+    model, oracle = small_pair(dict(subject_embedding=True))
+    torch.manual_seed(3)
+    x = torch.randn(3, 50, 384)
+    sid = torch.tensor([[2], [0], [2]])
+    model.train(), oracle.train()
+    xg = x.cuda().requires_grad_(True)
+    y = model.transformer_forward(xg, sid.cuda())
+    xo = x.clone().requires_grad_(True)
+    yo = oracle.transformer_forward(xo, sid)
+    assert_pred_close(y.detach(), yo.detach())
+    w = torch.randn_like(yo)
+    (y * w.cuda()).sum().backward()
+    (yo * w).sum().backward()
+    assert rel_l2(xg.grad, xo.grad) < 3e-2
+    assert rel_l2(model.subject_embed.weight.grad, oracle.subject_embed.weight.grad) < 3e-2
+    assert float(model.subject_embed.weight.grad[1].abs().max()) == 0.0  # subject 1 not in the batch
+    with pytest.raises(algonauts2025_b200.TribeError):
+        model.transformer_forward(xg)  # subject ids are required once the embedding exists
+
+
+def test_standalone_subject_layers_is_differentiable():
+    """common.py:45-67 imported on its own: output, d/dx, d/dweights (zero for absent subjects), d/dbias vs torch autograd
+    on the reference formula ``einsum("bct,bcd->bdt", x, W[subjects]) + bias[subjects]``."""
+    from algonauts2025_b200.model import SubjectLayers
+
+    torch.manual_seed(8)
+    B, C, T, D, S = 5, 128, 24, 200, 4
+    layer = SubjectLayers(C, D, S, bias=True).cuda()
+    subj = torch.tensor([[3], [0], [3], [1], [0]])
+    x = torch.randn(B, C, T)
+    xg = x.cuda().requires_grad_(True)
+    out = layer(xg, subj.cuda())
+    W = layer.weights.detach().cpu().clone().requires_grad_(True)
+    bias = layer.bias.detach().cpu().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.einsum("bct,bcd->bdt", xr, W.index_select(0, subj.flatten())) + bias.index_select(0, subj.flatten()).view(B, D, 1)
+    assert_pred_close(out.detach(), ref.detach())
+    g = torch.randn_like(ref)
+    (out * g.cuda()).sum().backward()
+    (ref * g).sum().backward()
+    assert rel_l2(xg.grad, xr.grad) < 2e-2
+    assert rel_l2(layer.weights.grad, W.grad) < 2e-2
+    assert float(layer.weights.grad[2].abs().max()) == 0.0
+    torch.testing.assert_close(layer.bias.grad.cpu(), bias.grad, rtol=2e-2, atol=2e-2)
+    with pytest.raises(AssertionError):
+        layer(xg, torch.tensor([[4], [0], [0], [0], [0]]).cuda())

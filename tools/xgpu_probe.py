@@ -81,6 +81,79 @@ for mc in ([True, False] if sh.multicast else [False]):
         log(f"{'multicast' if mc else 'peer-ptr '} blocks {blocks:4d}: {ms:7.3f} ms for {n_own / 1e6:.1f} M owned params  "
             f"local HBM {24 * n_own / ms / 1e6:7.1f} GB/s  reduced-in {4 * n_own / ms / 1e6:6.1f} GB/s  peer-read total {4 * n_own * (world - 1) / ms / 1e6:6.1f} GB/s")
 sh.check()
+
+# ---- pieces of the kernel, one at a time (which one is the ceiling?)
+import ctypes  # noqa: E402
+from algonauts2025_b200 import _lib, ops  # noqa: E402
+
+lib = _lib.load()
+sink = torch.zeros(4, device="cuda")
+sh.multicast = True
+big_lo, big_hi = [(x, y) for x, y, b in sh.pieces(lo, hi) if not b][0]
+args = sh.kernel_args(big_lo, big_hi, False, hyper.data_ptr())
+n_big = big_hi - big_lo
+names = {0: "multimem.ld_reduce only", 1: "peer loads only", 2: "local p/m/v stream only", 3: "multimem.st bf16 only", 4: "ld_reduce, 4 groups/thread"}
+for mode in (0, 4, 1, 2, 3):
+    for blocks in (148, 592, 1184):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(2):
+            lib.tribe_xgpu_probe(ctypes.byref(args), mode, blocks, ctypes.c_void_p(sink.data_ptr()), st)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(5):
+            lib.tribe_xgpu_probe(ctypes.byref(args), mode, blocks, ctypes.c_void_p(sink.data_ptr()), st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        per = {0: 4, 4: 4, 1: 4 * world, 2: 24, 3: 2}[mode]
+        log(f"piece [{names[mode]:28s}] blocks {blocks:4d}: {ms:7.3f} ms  {per * n_big / ms / 1e6:8.1f} GB/s ({per} B/param)")
+sh.check()
+
+# ---- interference with the persistent tcgen05 GEMM (FF1 shape): GEMM loop alone vs beside the step-tail kernel
+M, N, K = 4768, 12288, 3072
+xa = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+wb = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+side = torch.cuda.Stream()
+
+
+def gemm_loop(n):
+    for _ in range(n):
+        ops.gemm(ops.kmajor(xa), ops.kmajor(wb), out, M, N, K, ldd=N)
+
+
+gemm_loop(5)
+torch.cuda.synchronize()
+dist.barrier()
+e0.record()
+gemm_loop(30)
+e1.record()
+torch.cuda.synchronize()
+alone = e0.elapsed_time(e1) / 30
+log(f"GEMM {M}x{N}x{K} alone: {alone * 1e3:.1f} us = {2 * M * N * K / alone / 1e9:.0f} TFLOP/s (carveout env {os.environ.get('TRIBE_XGPU_CARVEOUT', 'default=100')})")
+for mc in (True, False):
+    sh.multicast = mc
+    for blocks in (16, 32, 74, 148):
+        sh.max_blocks = blocks
+        torch.cuda.synchronize()
+        dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        side.wait_stream(torch.cuda.current_stream())
+        e0.record()
+        with torch.cuda.stream(side):
+            s0.record()
+            for _ in range(3):
+                for x, y, b in sh.pieces(lo, hi):
+                    sh.launch(x, y, b, hyper.data_ptr())
+            s1.record()
+        gemm_loop(30)
+        e1.record()
+        torch.cuda.synchronize()
+        g = e0.elapsed_time(e1) / 30
+        log(f"GEMM beside {'multicast' if mc else 'peer-ptr '} tail x3 blocks {blocks:4d}: GEMM {g * 1e3:7.1f} us ({g / alone:4.2f}x), "
+            f"tail kernels {s0.elapsed_time(s1) / 3:6.3f} ms each, GEMM loop {g * 30:.2f} ms")
+sh.check()
 # correctness of one launch against torch on the gathered gradients
 sh.multicast = all(int(sh.handles[k].multicast_ptr) != 0 for k in ("grad", "bf16", "flat"))
 sh.max_blocks = 0

@@ -165,6 +165,8 @@ _SIGS = {
     "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
     "tribe_adam_hyper": [c_vp, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_vp],
     "tribe_sharded_adam_step": [ctypes.POINTER(TribeShardedAdam), c_vp],
+    "tribe_memcpy_async": [c_vp, c_vp, c_i64, c_vp],
+    "tribe_debug_spin": [c_i32, c_i32, c_f64, c_i32, c_vp, c_vp],
     "tribe_xgpu_probe": [ctypes.POINTER(TribeShardedAdam), c_i32, c_i32, c_vp, c_vp],
     "tribe_xgpu_barrier": [ctypes.POINTER(TribeXgpuPeers), c_i32, c_i32, c_i32, c_vp, c_f64, c_vp],
     "tribe_point_loss_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp, c_vp],

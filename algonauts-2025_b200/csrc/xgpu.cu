@@ -1,19 +1,23 @@
-// Data-parallel step tail in ONE kernel per gradient bucket (sm_100a + NVLink 5 / NVSwitch):
+// Data-parallel step tail in ONE kernel per owned range (sm_100a + NVLink 5 / NVSwitch):
 //
-//   in-switch gradient reduction (multimem.ld_reduce over the NVLS multicast mapping of every rank's flat fp32 gradient
-//   buffer)  ->  fused Adam on the slice of the bucket THIS rank owns  ->  multicast of the updated bf16 shadow weights
-//   (multimem.st: one store lands in every rank's copy).
+//   gradient reduction over ranks  ->  fused Adam on the slice of the bucket THIS rank owns  ->  multicast of the updated
+//   bf16 shadow weights (multimem.st: one store lands in every rank's copy).
+//
+// The reduction reads either (a) `world` staged copies — every rank's copy engines PUSH its slice of a finished bucket
+// into the owner's staging buffer over NVLink while the backward pass continues (tribe_memcpy_async: no SM involved), the
+// kernel sums them in rank order from local HBM; (b) the NVLS multicast mapping (multimem.ld_reduce, in-switch sum); or
+// (c) the peers' buffers through peer-mapped pointers.
 //
 // It replaces the reference's DDP gradient all-reduce + replicated optimizer step (Lightning DDP,
-// algonauts2025/main.py:388-394; Adam recipe algonauts2025/grids/defaults.py:126-141): per step a rank pulls 4 B per OWNED
-// parameter out of the switch (instead of all-reducing 4 B per parameter both ways), touches the optimizer state of
-// 1/N of the model, and receives 2 B per parameter of shadow weights.  The kernel has no shared memory and is built for
-// <= 88 registers x 128 threads so that one CTA is co-resident with the persistent tcgen05 GEMM CTA of an SM (320 threads x
-// 168 registers, ~222 KB smem): the backward GEMMs of the earlier layers keep all 148 SMs while the tail of a finished
-// layer streams beside them.
+// algonauts2025/main.py:388-394; Adam recipe algonauts2025/grids/defaults.py:126-141): per step a rank receives 4 B per
+// OWNED parameter from every peer (instead of all-reducing 4 B per parameter both ways), touches the optimizer state of
+// 1/N of the model, and receives 2 B per parameter of shadow weights.
 //
-// Without multicast support (no NVSwitch / fabric) the same kernel reads the N peer copies over peer-mapped pointers
-// in rank order and stores the shadow to every peer (P2P variant, template MC = false).
+// Measured on 2 x B200 (profiles/r02_xgpu_probe*.log, r02_coresidency.log): multimem.ld_reduce.v4.f32 tops out at
+// ~166 GB/s of reduced data per GPU and multimem.st at ~340 GB/s whatever the parallelism; peer loads reach ~330 GB/s;
+// and ANY foreign CTA that stays resident on an SM (even 32 threads) keeps the persistent 2-CTA tcgen05 GEMM off that
+// SM, whose static tile schedule then pays a second wave (1.5x per GEMM).  Hence the default: gradients travel by copy
+// engine during the backward pass, and this kernel runs after it, at HBM speed, with the device to itself.
 //
 // Cross-rank ordering uses xgpu_barrier_kernel: flag words in a symmetric buffer, one slot per (bucket, source rank),
 // CAS flip-flop (0 -> 1 by the signaller with release.sys, 1 -> 0 by the waiter with acquire.sys), so no epoch numbers
@@ -126,7 +130,10 @@ __device__ __forceinline__ void xg_adam_one(float& p, float g, float& m, float& 
   p = p - step_size * (m / denom);
 }
 
-template <bool MC>
+// GMC: gradients through multimem.ld_reduce (in-switch sum) vs a table of `world` addresses summed in rank order (peer
+// mappings, or LOCAL staging buffers the peers' copy engines filled during the backward pass).  OMC: outputs through
+// multimem.st vs per-peer stores.
+template <bool GMC, bool OMC>
 __global__ void __launch_bounds__(128, 6) sharded_adam_kernel(const ShardedAdamK a) {
   const float beta1 = a.hyper[0], beta2 = a.hyper[1], step_size = a.hyper[2], inv_bc2_sqrt = a.hyper[3], eps = a.hyper[4], wd = a.hyper[5];
   const int64_t nv = a.n >> 3;  // groups of 8 parameters: 2 x 16 B of gradient, one 16 B shadow store
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(128, 6) sharded_adam_kernel(const ShardedAdamK
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
     const int64_t e = i << 3;
     float4 g0, g1;
-    if (MC) {
+    if (GMC) {
       g0 = xg_ld_reduce(a.g_mc + e);
       g1 = xg_ld_reduce(a.g_mc + e + 4);
     } else {
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(128, 6) sharded_adam_kernel(const ShardedAdamK
     __stcs(reinterpret_cast<float4*>(a.m + e), m0), __stcs(reinterpret_cast<float4*>(a.m + e + 4), m1);
     __stcs(reinterpret_cast<float4*>(a.v + e), v0), __stcs(reinterpret_cast<float4*>(a.v + e + 4), v1);
     const uint32_t s0 = xg_pack2(p0.x, p0.y), s1 = xg_pack2(p0.z, p0.w), s2 = xg_pack2(p1.x, p1.y), s3 = xg_pack2(p1.z, p1.w);
-    if (MC) {
+    if (OMC) {
       xg_mc_store(a.s_mc + e, s0, s1, s2, s3);
       if (a.bcast) {  // parameters the kernels read as fp32 (biases, norm gains, residual scales, positional embedding)
         xg_mc_store(a.p_mc + e, __float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), __float_as_uint(p0.w));
@@ -228,9 +235,26 @@ __global__ void __launch_bounds__(128, 6) xgpu_probe_kernel(const ShardedAdamK a
   if (acc == 123.456f) sink[0] = acc;
 }
 
+// occupies `blocks` CTAs of `threads` threads for `ns` nanoseconds (tools/coresidency_probe.py: can a small CTA share an
+// SM with the persistent tcgen05 GEMM CTA?)
+__global__ void xgpu_spin_kernel(uint64_t ns, uint32_t* sink) {
+  const uint64_t t0 = xg_now();
+  while (xg_now() - t0 < ns) {
+  }
+  if (ns == 1) sink[0] = 1;
+}
+
 }  // namespace tribe
 
 using namespace tribe;
+
+extern "C" int tribe_debug_spin(int32_t blocks, int32_t threads, double seconds, int32_t carveout_pct, uint32_t* sink, void* stream) {
+  if (blocks <= 0 || threads <= 0 || threads > 1024 || !sink) return set_error(TRIBE_EINVAL, "debug_spin: bad arguments");
+  if (carveout_pct >= 0) cudaFuncSetAttribute(xgpu_spin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+  xgpu_spin_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<uint64_t>(seconds * 1e9), sink);
+  TRIBE_CHECK_LAUNCH("debug_spin");
+  return TRIBE_OK;
+}
 
 extern "C" int tribe_xgpu_probe(const TribeShardedAdam* a, int32_t mode, int32_t blocks, float* sink, void* stream) {
   if (!a || !sink || a->n <= 0 || (a->n & 7)) return set_error(TRIBE_EINVAL, "xgpu_probe: bad arguments");
@@ -260,17 +284,21 @@ extern "C" int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream) 
   if (!a || !a->param || !a->m || !a->v || !a->hyper || a->n <= 0 || (a->n & 7) || a->world < 1 || a->world > TRIBE_XGPU_MAX_WORLD ||
       a->rank < 0 || a->rank >= a->world)
     return set_error(TRIBE_EINVAL, "sharded_adam: bad arguments (n must be a positive multiple of 8)");
-  const bool mc = a->grad_mc != nullptr;
+  const bool gmc = a->grad_mc != nullptr, omc = a->shadow_mc != nullptr;
   uintptr_t al = reinterpret_cast<uintptr_t>(a->param) | reinterpret_cast<uintptr_t>(a->m) | reinterpret_cast<uintptr_t>(a->v);
-  if (mc) {
-    if (!a->shadow_mc || (a->bcast_master && !a->param_mc)) return set_error(TRIBE_EINVAL, "sharded_adam: multicast pointers missing");
+  if (gmc && !omc) return set_error(TRIBE_EINVAL, "sharded_adam: multicast gradients need multicast outputs");
+  if (omc) {
+    if (a->bcast_master && !a->param_mc) return set_error(TRIBE_EINVAL, "sharded_adam: multicast pointers missing");
     al |= reinterpret_cast<uintptr_t>(a->grad_mc) | reinterpret_cast<uintptr_t>(a->shadow_mc) | reinterpret_cast<uintptr_t>(a->param_mc);
-  } else {
-    for (int r = 0; r < a->world; ++r) {
-      if (!a->grad_peer.ptr[r] || !a->shadow_peer.ptr[r] || (a->bcast_master && !a->param_peer.ptr[r]))
-        return set_error(TRIBE_EINVAL, "sharded_adam: peer pointers missing");
-      al |= reinterpret_cast<uintptr_t>(a->grad_peer.ptr[r]) | reinterpret_cast<uintptr_t>(a->shadow_peer.ptr[r]) |
-            reinterpret_cast<uintptr_t>(a->param_peer.ptr[r]);
+  }
+  for (int r = 0; r < a->world; ++r) {
+    if (!gmc) {
+      if (!a->grad_peer.ptr[r]) return set_error(TRIBE_EINVAL, "sharded_adam: gradient pointers missing");
+      al |= reinterpret_cast<uintptr_t>(a->grad_peer.ptr[r]);
+    }
+    if (!omc) {
+      if (!a->shadow_peer.ptr[r] || (a->bcast_master && !a->param_peer.ptr[r])) return set_error(TRIBE_EINVAL, "sharded_adam: peer pointers missing");
+      al |= reinterpret_cast<uintptr_t>(a->shadow_peer.ptr[r]) | reinterpret_cast<uintptr_t>(a->param_peer.ptr[r]);
     }
   }
   if (al & 15) return set_error(TRIBE_EINVAL, "sharded_adam: every range must be 16-byte aligned");
@@ -281,24 +309,25 @@ extern "C" int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream) 
   k.n = a->n, k.world = a->world, k.rank = a->rank, k.bcast = a->bcast_master;
   k.inv_world = 1.0f / static_cast<float>(a->world);
   k.hyper = a->hyper;
-  const int blocks = grid_for(a->n / 8, 128, a->max_blocks > 0 ? a->max_blocks : 148);
+  // the kernel runs AFTER the backward pass with the device to itself (a CTA that stays on an SM keeps the persistent
+  // 2-CTA GEMM off that SM and its static tile schedule then pays a second wave: profiles/r02_coresidency.log)
+  const int blocks = grid_for(a->n / 8, 128, a->max_blocks > 0 ? a->max_blocks : 148 * 6);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // the kernel has to share SMs with the persistent GEMM CTAs (~222 KB of dynamic shared memory each): ask for the same
-  // L1 / shared-memory split so that an SM does not have to drain before it can host both
-  static const bool carveout_set = [] {
-    const char* e = getenv("TRIBE_XGPU_CARVEOUT");
-    const int pct = e ? atoi(e) : 100;
-    if (pct >= 0) {
-      cudaFuncSetAttribute(sharded_adam_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      cudaFuncSetAttribute(sharded_adam_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
-    return true;
-  }();
-  (void)carveout_set;
-  if (mc)
-    sharded_adam_kernel<true><<<blocks, 128, 0, s>>>(k);
+  if (gmc)
+    sharded_adam_kernel<true, true><<<blocks, 128, 0, s>>>(k);
+  else if (omc)
+    sharded_adam_kernel<false, true><<<blocks, 128, 0, s>>>(k);
   else
-    sharded_adam_kernel<false><<<blocks, 128, 0, s>>>(k);
+    sharded_adam_kernel<false, false><<<blocks, 128, 0, s>>>(k);
   TRIBE_CHECK_LAUNCH("sharded_adam");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream) {
+  if (!dst || !src || n_bytes < 0) return set_error(TRIBE_EINVAL, "memcpy_async: bad arguments");
+  if (n_bytes == 0) return TRIBE_OK;
+  // copy-engine transfer (no SM): local -> peer-mapped symmetric memory over NVLink, or device-local
+  cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(n_bytes), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_cuda_error(e, "memcpy_async");
   return TRIBE_OK;
 }

@@ -245,7 +245,7 @@ class TribeAdam(torch.optim.Adam):
             a, b = max(run["lo"], own_lo), min(run["hi"], own_hi)
             if b > a:
                 for x, y, bcast in sh.pieces(a, b):
-                    sh.launch(x, y, bcast, hyper)
+                    sh.launch(idx, x, y, bcast, hyper)
         self._early = (getattr(self, "_early", None) or []) + [tuple(lo_hi)]
 
     def state_dict(self):

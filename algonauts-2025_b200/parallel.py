@@ -131,28 +131,32 @@ class ShardedStep:
     """Data-parallel step tail on NVLink 5 / NVSwitch with OUR kernel instead of NCCL all-reduce + replicated Adam
     (reference: Lightning DDP + ``torch.optim.Adam`` on every rank, algonauts2025/main.py:388-394).
 
-    The flat gradient buffer, the bf16 shadow and the fp32 masters are re-homed into symmetric memory
-    (``torch.distributed._symmetric_memory``: same allocation on every rank, peer-mapped, NVLS multicast mapping when the
-    fabric has one).  Every bucket of the flat layout (0 = head, 1..depth = encoder layers) is statically cut into
-    ``world`` contiguous slices; when ``engine.backward`` reports a bucket complete, a side stream runs
+    Every bucket of the flat layout (0 = head, 1..depth = encoder layers) is statically cut into ``world`` contiguous
+    slices.  The bf16 shadow, the fp32 masters, a gradient staging buffer and a block of flag words live in symmetric
+    memory (``torch.distributed._symmetric_memory``: same allocation on every rank, peer-mapped, NVLS multicast mapping
+    when the fabric has one).  ``mode``:
 
-        cross-rank barrier (all ranks finished writing the bucket)  ->  ``tribe_sharded_adam_step`` on the owned slice:
-        ``multimem.ld_reduce`` (in-switch sum of all ranks' gradients) -> Adam -> ``multimem.st`` of the bf16 shadow
-        (and of the fp32 value for parameters the kernels read as fp32) into every rank's copy,
+    ``"staged"`` (default)  when ``engine.backward`` reports a bucket complete, this rank's COPY ENGINES push the slice each
+        peer owns into that peer's staging buffer (``tribe_memcpy_async``; no SM, no barrier — the slot is free since the
+        previous step's closing barrier) while the backward pass of the earlier layers keeps every SM.  After the
+        backward: one cross-rank barrier, then ``tribe_sharded_adam_step`` on the owned slices — sum of the ``world``
+        staged copies in rank order from local HBM -> Adam -> ``multimem.st`` of the bf16 shadow (and of the fp32 value of
+        parameters the kernels read as fp32) into every rank's copy — and a closing barrier.
+    ``"nvls"``   nothing moves during the backward; the same kernel reduces through ``multimem.ld_reduce`` (in-switch).
+    ``"p2p"``    the same kernel reads the peers' gradient buffers through peer-mapped pointers and stores to every peer
+        (no multicast needed).
 
-    beside the backward GEMMs of the earlier layers; ``finish_step`` closes with one more barrier and joins the stream.
-    No NCCL call is part of the step, so whole steps are captured in CUDA graphs for N > 1 as well.
+    No NCCL call is part of the step, so whole steps are captured in CUDA graphs for N > 1 as well.  Adam moments exist
+    only on the owner of a slice, and the fp32 master of weight matrices is current only there; ``gather_masters()`` /
+    ``gather_optimizer_state()`` (collective, lazy — ``state_dict()`` calls them) complete them.  The mean is the sum
+    times 1/N; every rank receives the SAME bits for every parameter by construction."""
 
-    Consequences: Adam moments exist only on the owner of a slice, and the fp32 master of weight matrices is current
-    only there; ``gather_masters()`` / ``gather_optimizer_state()`` (collective, lazy — ``state_dict()`` calls them)
-    complete them.  Reduction order: one in-switch add per element (NVLS) or rank order 0..N-1 (peer-load variant); the
-    mean is the sum times 1/N.  Every rank receives the SAME bits for every parameter by construction.
-    """
+    SLOT_REDUCE, SLOT_DONE = 1, 2
 
-    FINAL_SLOT = 40
-
-    def __init__(self, model, optimizer, group=None, max_blocks: int = 0, use_multicast: bool | None = None, timeout_s: float = 30.0):
+    def __init__(self, model, optimizer, group=None, max_blocks: int = 0, mode: str | None = None, use_multicast: bool | None = None,
+                 timeout_s: float = 30.0):
         import ctypes
+        import os
 
         import torch.distributed._symmetric_memory as symm
 
@@ -169,26 +173,46 @@ class ShardedStep:
             raise _lib.TribeError("ShardedStep needs a TribeAdam optimizer (TribeAdam.adopt)")
         self.group = group if group is not None else dist.group.WORLD
         self.max_blocks, self.timeout_s = max_blocks, timeout_s
-        dev = flat.device
-        flat.rehome(lambda n, dtype: symm.empty(n, dtype=dtype, device=dev))
-        self.flags = symm.empty(_lib.XGPU_SLOTS * _lib.XGPU_MAX_WORLD, dtype=torch.int32, device=dev)
-        self.flags.zero_()
-        torch.cuda.synchronize(dev)
-        self.handles = {k: symm.rendezvous(t, self.group) for k, t in (("grad", flat.grad), ("bf16", flat.bf16), ("flat", flat.flat), ("flags", self.flags))}
-        mc = all(int(self.handles[k].multicast_ptr) != 0 for k in ("grad", "bf16", "flat"))
-        self.multicast = mc if use_multicast is None else (bool(use_multicast) and mc)
-        self.err = torch.zeros(1, device=dev, dtype=torch.int32)
-        self._peers = {k: [int(x) for x in h.buffer_ptrs] for k, h in self.handles.items()}
-        self._flag_peers = _lib.TribeXgpuPeers()
-        for r in range(self.world):
-            self._flag_peers.ptr[r] = self._peers["flags"][r]
         self._ctypes = ctypes
+        dev = flat.device
         # static ownership: bucket b = [s, e) -> rank r owns [s + r * c, min(e, s + (r + 1) * c)), c a multiple of 8 elements
         self.owned = []
         for s, e in flat.bucket_ranges:
             c = -(-(e - s) // self.world)
             c = (c + 7) // 8 * 8
             self.owned.append([(min(e, s + r * c), min(e, s + (r + 1) * c)) for r in range(self.world)])
+        # staging layout at owner r: [source rank][bucket-major concatenation of r's owned slices]
+        self.prefix = [[0] * len(self.owned) for _ in range(self.world)]
+        totals = []
+        for r in range(self.world):
+            off = 0
+            for bi, owners in enumerate(self.owned):
+                self.prefix[r][bi] = off
+                off += owners[r][1] - owners[r][0]
+            totals.append(off)
+        self.cap = (max(totals) + 63) // 64 * 64
+        flat.rehome(lambda n, dtype: symm.empty(n, dtype=dtype, device=dev))
+        self.flags = symm.empty(_lib.XGPU_SLOTS * _lib.XGPU_MAX_WORLD, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.stage = symm.empty(self.world * self.cap, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        self.handles = {k: symm.rendezvous(t, self.group)
+                        for k, t in (("grad", flat.grad), ("bf16", flat.bf16), ("flat", flat.flat), ("flags", self.flags), ("stage", self.stage))}
+        self.has_multicast = all(int(self.handles[k].multicast_ptr) != 0 for k in ("grad", "bf16", "flat"))
+        mode = mode or os.environ.get("TRIBE_DP_MODE") or "staged"
+        if use_multicast is False and mode == "nvls":
+            mode = "p2p"
+        if mode not in ("staged", "nvls", "p2p"):
+            raise _lib.TribeError(f"unknown ShardedStep mode {mode!r}")
+        if mode == "nvls" and not self.has_multicast:
+            mode = "p2p"
+        self.mode = mode
+        self.out_multicast = self.has_multicast and mode != "p2p" and use_multicast is not False
+        self.err = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._peers = {k: [int(x) for x in h.buffer_ptrs] for k, h in self.handles.items()}
+        self._flag_peers = _lib.TribeXgpuPeers()
+        for r in range(self.world):
+            self._flag_peers.ptr[r] = self._peers["flags"][r]
         # maximal flat ranges of parameters the kernels read as fp32
         self.bcast = []
         for n in sorted(flat.offsets, key=flat.offsets.get):
@@ -201,11 +225,22 @@ class ShardedStep:
                     self.bcast.append([lo, hi])
         self.stream = torch.cuda.Stream(dev)
         self.counts, self.passes, self.head_passes = {}, 1, 0
+        self.ready = []
         self.masters_stale = self.state_stale = False
         self.engine.comm = self
         flat.sharded = self
         optimizer._tribe_sharded = self
         dist.barrier(group=self.group)
+
+    @property
+    def multicast(self) -> bool:
+        return self.mode == "nvls" or self.out_multicast
+
+    def describe(self) -> str:
+        grads = {"staged": "copy-engine pushes of every finished bucket's slices into the owners' staging buffers during the backward pass",
+                 "nvls": "NVLS multimem.ld_reduce (in-switch sum)", "p2p": "peer-pointer loads"}[self.mode]
+        out = "multimem.st multicast" if self.out_multicast else "per-peer stores"
+        return f"{grads} -> rank-sharded fused Adam -> bf16 shadow {out}, one kernel per owned range after the backward (csrc/xgpu.cu), no NCCL in the step"
 
     # -------------------------------------------------------------------------------------------- kernel plumbing
     def barrier(self, slot: int) -> None:
@@ -228,31 +263,52 @@ class ShardedStep:
             out.append((a, b, any(x <= a and b <= y for x, y in self.bcast)))
         return out
 
-    def launch(self, lo: int, hi: int, bcast: bool, hyper_ptr: int) -> None:
-        """The fused reduce -> Adam -> multicast kernel on [lo, hi) of the flat layout (a range this rank owns)."""
+    def push_bucket(self, idx: int) -> None:
+        """Copy-engine pushes of bucket ``idx``: the slice rank r owns goes to r's staging area for source ``self.rank``."""
         from . import _lib
 
-        a = self.kernel_args(lo, hi, bcast, hyper_ptr)
+        lib, fl = _lib.load(), self.flat
         st = self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.load().tribe_sharded_adam_step(self._ctypes.byref(a), st), "tribe_sharded_adam_step")
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world  # stagger the destinations so that the ranks do not all hit the same peer first
+            lo, hi = self.owned[idx][r]
+            if hi > lo:
+                dst = self._peers["stage"][r] + 4 * (self.rank * self.cap + self.prefix[r][idx])
+                _lib.check(lib.tribe_memcpy_async(self._ctypes.c_void_p(dst), self._ctypes.c_void_p(fl.grad.data_ptr() + 4 * lo), 4 * (hi - lo), st),
+                           "tribe_memcpy_async")
 
-    def kernel_args(self, lo: int, hi: int, bcast: bool, hyper_ptr: int):
+    def kernel_args(self, idx: int, lo: int, hi: int, bcast: bool, hyper_ptr: int):
+        """Arguments of the fused kernel for [lo, hi) (inside this rank's slice of bucket ``idx``)."""
         from . import _lib
 
         fl = self.flat
         a = _lib.TribeShardedAdam()
         a.param, a.m, a.v = fl.flat.data_ptr() + 4 * lo, fl.adam_m.data_ptr() + 4 * lo, fl.adam_v.data_ptr() + 4 * lo
         a.hyper = hyper_ptr
-        if self.multicast:
+        if self.mode == "nvls":
             a.grad_mc = int(self.handles["grad"].multicast_ptr) + 4 * lo
+        if self.out_multicast:
             a.shadow_mc = int(self.handles["bf16"].multicast_ptr) + 2 * lo
             a.param_mc = int(self.handles["flat"].multicast_ptr) + 4 * lo
+        own_lo = self.owned[idx][self.rank][0]
         for r in range(self.world):
-            a.grad_peer.ptr[r] = self._peers["grad"][r] + 4 * lo
+            if self.mode == "staged":
+                a.grad_peer.ptr[r] = (fl.grad.data_ptr() + 4 * lo if r == self.rank else
+                                      self.stage.data_ptr() + 4 * (r * self.cap + self.prefix[self.rank][idx] + (lo - own_lo)))
+            else:
+                a.grad_peer.ptr[r] = self._peers["grad"][r] + 4 * lo
             a.shadow_peer.ptr[r] = self._peers["bf16"][r] + 2 * lo
             a.param_peer.ptr[r] = self._peers["flat"][r] + 4 * lo
         a.n, a.world, a.rank, a.bcast_master, a.max_blocks = hi - lo, self.world, self.rank, int(bcast), self.max_blocks
         return a
+
+    def launch(self, idx: int, lo: int, hi: int, bcast: bool, hyper_ptr: int) -> None:
+        """The fused reduce -> Adam -> multicast kernel on [lo, hi) of the flat layout (a range this rank owns)."""
+        from . import _lib
+
+        a = self.kernel_args(idx, lo, hi, bcast, hyper_ptr)
+        st = self._ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().tribe_sharded_adam_step(self._ctypes.byref(a), st), "tribe_sharded_adam_step")
 
     # -------------------------------------------------------------------------------------------- step protocol
     def begin_step(self, backward_passes: int | None = None, head_passes: int | None = None):
@@ -260,25 +316,31 @@ class ShardedStep:
         contrastive = bool(getattr(cfg, "contrastive_enabled", False))
         self.passes = backward_passes if backward_passes is not None else (2 if contrastive else 1)
         self.head_passes = head_passes if head_passes is not None else (len(getattr(self.model, "contrastive_heads", ())) if contrastive else 0)
-        self.counts = {}
+        self.counts, self.ready = {}, []
 
     def bucket_ready(self, idx: int):
         self.counts[idx] = self.counts.get(idx, 0) + 1
         if self.counts[idx] < self.passes + (self.head_passes if idx == 0 else 0):
             return
-        main = torch.cuda.current_stream()
-        self.stream.wait_stream(main)  # this rank's contributions to the bucket are final
-        with torch.cuda.stream(self.stream):
-            self.barrier(idx)          # ... and so are every other rank's
-            self.optimizer.step_bucket_sharded(idx)
-        self.masters_stale = self.state_stale = True
+        self.ready.append(idx)
+        if self.mode == "staged":
+            self.stream.wait_stream(torch.cuda.current_stream())  # this rank's contributions to the bucket are final
+            with torch.cuda.stream(self.stream):
+                self.push_bucket(idx)
 
     def finish_step(self):
-        """All ranks have read every gradient and written every shadow slice: the next forward may start and the next
-        backward may overwrite the gradient buffer."""
-        with torch.cuda.stream(self.stream):
-            self.barrier(self.FINAL_SLOT)
-        torch.cuda.current_stream().wait_stream(self.stream)
+        """After the backward pass: every rank's gradients are in place (barrier), the owned slices are reduced, stepped and
+        multicast, and a closing barrier says that all ranks have read every gradient and written every shadow slice —
+        the next forward may start and the next backward may overwrite the gradient / staging buffers."""
+        main = torch.cuda.current_stream()
+        if self.mode == "staged":
+            main.wait_stream(self.stream)      # this rank's pushes have landed
+        self.barrier(self.SLOT_REDUCE)         # ... and so have everyone else's
+        for idx in self.ready:
+            self.optimizer.step_bucket_sharded(idx)
+        self.barrier(self.SLOT_DONE)
+        if self.ready:
+            self.masters_stale = self.state_stale = True
 
     def check(self) -> None:
         """Raise if a cross-rank wait timed out (synchronises the device)."""
@@ -299,22 +361,20 @@ class ShardedStep:
     def gather_masters(self) -> None:
         """Every rank receives the owners' fp32 masters (collective; called by ``state_dict()`` and before a re-cast)."""
         if self.masters_stale:
-            torch.cuda.current_stream().wait_stream(self.stream)
             self._gather([self.flat.flat])
             self.masters_stale = False
 
     def gather_optimizer_state(self) -> None:
         """Every rank receives the owners' Adam moments (collective; called by ``TribeAdam.state_dict()``)."""
         if self.state_stale and getattr(self.flat, "adam_m", None) is not None:
-            torch.cuda.current_stream().wait_stream(self.stream)
             self._gather([self.flat.adam_m, self.flat.adam_v])
             self.state_stale = False
 
 
 def data_parallel(model, optimizer, group=None, prefer: str = "nvlink", **kw):
-    """The gradient-synchronisation object for ``trainer.MiniTrainer(grad_sync=...)``: ``ShardedStep`` (our NVLink kernel,
-    rank-sharded Adam) when symmetric memory can be set up on every rank, else ``GradAllReduce`` (NCCL all-reduce +
-    replicated Adam).  The decision is collective."""
+    """The gradient-synchronisation object for ``trainer.MiniTrainer(grad_sync=...)``: ``ShardedStep`` (copy-engine gradient
+    pushes + our fused reduce / Adam / multicast kernel, rank-sharded optimizer) when symmetric memory can be set up on
+    every rank, else ``GradAllReduce`` (NCCL all-reduce + replicated Adam).  The decision is collective."""
     rank, ws = world()
     if ws == 1:
         return None

@@ -320,14 +320,14 @@ def run_ours(args):
     # the reference recipe (Adam lr 1e-4 + OneCycleLR per step); the stock torch.optim.Adam instance is adopted by the
     # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
     opt, sched = default_optimizer(model.parameters(), total_steps=4 * (K + W) + 16, model=None if args.stock_adam else model)
-    # N > 1: our NVLink step tail (in-switch gradient reduction -> rank-sharded Adam -> bf16 shadow multicast, one kernel
-    # per bucket, parallel.ShardedStep); --dp allreduce selects the NCCL all-reduce + replicated Adam path
+    # N > 1: our NVLink step tail (copy-engine gradient pushes during the backward -> one fused reduce / rank-sharded Adam /
+    # bf16-shadow-multicast kernel per owned range, parallel.ShardedStep); --dp allreduce = NCCL all-reduce + replicated Adam
     sync = None
     if world > 1:
         if args.dp == "allreduce" or args.stock_adam:
             sync = parallel.GradAllReduce(model, gemm_sms_during_comm=args.comm_gemm_sms)
         else:
-            sync = parallel.data_parallel(model, opt, max_blocks=args.dp_blocks, use_multicast=None if args.dp == "nvlink" else False)
+            sync = parallel.data_parallel(model, opt, max_blocks=args.dp_blocks, mode=args.dp)
     sharded = isinstance(sync, parallel.ShardedStep)
     # whole-step CUDA graphs; NCCL all-reduces inside a step are only captured on request, our own step tail always is
     use_graphs = not args.eager and not args.stock_adam and (world == 1 or args.graph_comm or sharded)
@@ -451,8 +451,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
                            "gradient_path": ("none (1 GPU)" if world == 1 else
-                                             (("NVLS multimem.ld_reduce" if sync.multicast else "peer-pointer loads") + " -> rank-sharded fused Adam -> bf16 shadow multicast, one kernel per bucket (csrc/xgpu.cu), no NCCL in the step")
-                                             if sharded else "NCCL all-reduce (fp32, 9 buckets) + replicated fused Adam"),
+                                             sync.describe() if sharded else "NCCL all-reduce (fp32, 9 buckets) + replicated fused Adam"),
                            "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel)") + " + OneCycleLR, fp32 master weights",
                            "optimizer_overlap": overlap, "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
                            "last_loss": last, "host_enqueue_ms_per_step": cpu_enqueue_ms,
@@ -585,8 +584,10 @@ def main():
     ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying whole-step CUDA graphs")
     ap.add_argument("--graph-comm", action="store_true", help="N > 1: capture the steps including their NCCL all-reduces (default: eager steps)")
-    ap.add_argument("--dp", default="nvlink", choices=["nvlink", "p2p", "allreduce"], help="N > 1 gradient path: our NVLS kernel (default), its peer-pointer variant, or NCCL all-reduce")
-    ap.add_argument("--dp-blocks", type=int, default=0, help="N > 1: CTAs of the sharded step-tail kernel (0 = 148)")
+    ap.add_argument("--dp", default="staged", choices=["staged", "nvls", "p2p", "allreduce"],
+                    help="N > 1 gradient path: copy-engine pushes + our fused reduce/Adam/multicast kernel (default), the same kernel reducing "
+                         "through NVLS multimem.ld_reduce or peer pointers, or NCCL all-reduce + replicated Adam")
+    ap.add_argument("--dp-blocks", type=int, default=0, help="N > 1: CTAs of the sharded step-tail kernel (0 = 6 per SM)")
     ap.add_argument("--comm-gemm-sms", type=int, default=0, help="N > 1: SMs the backward GEMMs use while gradient all-reduces are in flight (0 = all)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump all thread stacks and exit if the run takes longer than this many seconds (0 = off)")
     ap.add_argument("--overlap", action="store_true", help="run each layer's Adam step behind the backward (parallel.StepOverlap) instead of after it")

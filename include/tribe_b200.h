@@ -274,14 +274,16 @@ int tribe_adam_hyper(float* hyper_dev, double lr, double beta1, double beta2, do
  *
  * tribe_sharded_adam_step: ONE kernel for the [lo, lo + n) range THIS rank owns —
  *   g = (sum over ranks of grad[i]) / world   multimem.ld_reduce.add.f32 on grad_mc (in-switch reduction), or, when
- *                                             grad_mc == NULL, loads from grad_peer[0..world) summed in rank order;
+ *                                             grad_mc == NULL, loads from grad_peer[0..world) summed in rank order
+ *                                             (peer mappings, or local staging buffers filled by tribe_memcpy_async);
  *   Adam on the local param / m / v (same arithmetic as tribe_adam_step_dev, scalars from the device block `hyper`);
- *   bf16(param) -> every rank's shadow         multimem.st on shadow_mc, or stores to shadow_peer[r];
+ *   bf16(param) -> every rank's shadow         multimem.st on shadow_mc, or (shadow_mc == NULL) stores to shadow_peer[r];
  *   bcast_master != 0: the fp32 param too      (parameters the kernels read as fp32: biases, gains, residual scales,
  *                                              positional embedding) — param_mc / param_peer.
  * All pointers already include the offset `lo`; n is a multiple of 8 and every pointer 16-byte aligned.  m / v (and the
  * fp32 master of ranges without bcast_master) are only current on the owner (gathered on demand for checkpoints).
- * max_blocks bounds the grid (default 148: one 128-thread CTA per SM, co-resident with the persistent GEMM CTAs).
+ * max_blocks bounds the grid (default 888 = 6 CTAs of 128 threads per SM: the kernel runs after the backward pass with
+ * the device to itself — a resident foreign CTA keeps the persistent 2-CTA GEMM off its SM, profiles/r02_coresidency.log).
  *
  * tribe_xgpu_barrier: all `world` ranks meet at `slot` (< TRIBE_XGPU_SLOTS).  flags->ptr[r] = rank r's flag block
  * (TRIBE_XGPU_SLOTS * TRIBE_XGPU_MAX_WORLD zero-initialised uint32 words of symmetric memory) as mapped into THIS
@@ -309,8 +311,14 @@ typedef struct TribeShardedAdam {
   int32_t world, rank, bcast_master, max_blocks;
 } TribeShardedAdam;
 int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream);
+/* Copy-engine transfer dst <- src (device pointers of this process: local memory or peer-mapped symmetric memory).  The
+ * data-parallel step PUSHES each finished gradient bucket's slices into their owners' staging buffers with it while the
+ * backward pass keeps every SM (grad_peer[] of tribe_sharded_adam_step then points at the LOCAL staged copies). */
+int tribe_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream);
 /* Micro-benchmark of the pieces of the kernel above (tools/xgpu_probe.py; not used by the product path): mode 0 =
  * multimem.ld_reduce only, 1 = peer loads only, 2 = local param/m/v stream only, 3 = multimem.st only, 4 = ld_reduce x4. */
+/* Debug: `blocks` CTAs of `threads` threads spin for `seconds` (tools/coresidency_probe.py). */
+int tribe_debug_spin(int32_t blocks, int32_t threads, double seconds, int32_t carveout_pct, uint32_t* sink, void* stream);
 int tribe_xgpu_probe(const TribeShardedAdam* a, int32_t mode, int32_t blocks, float* sink, void* stream);
 int tribe_xgpu_barrier(const TribeXgpuPeers* flags, int32_t rank, int32_t world, int32_t slot, uint32_t* err_flag, double timeout_s,
                        void* stream);

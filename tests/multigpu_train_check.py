@@ -2,8 +2,10 @@
 tests/test_multigpu_gpu.py).  Every rank trains on its own windows.  Paths compared:
 
   allreduce   parallel.GradAllReduce: bucketed NCCL all-reduce (mean) + replicated fused Adam
-  nvlink      parallel.ShardedStep: our fused kernel (in-switch multimem.ld_reduce -> rank-sharded Adam -> multimem.st of
-              the bf16 shadow), eager and replayed as whole-step CUDA graphs
+  staged      parallel.ShardedStep: copy-engine pushes of every finished bucket's slices to their owners during the backward,
+              then our fused kernel (sum of the staged copies -> rank-sharded Adam -> multimem.st of the bf16 shadow),
+              eager and replayed as whole-step CUDA graphs
+  nvls        the same kernel reducing through multimem.ld_reduce (in-switch sum)
   p2p         the same kernel's peer-pointer variant (no multicast)
 
 After a few Adam steps (a) all ranks hold bit-identical weights (fp32 masters after the lazy gather AND the bf16 shadow
@@ -55,9 +57,9 @@ def train(p_drop, path, graphs, batches, steps=6, contrastive=False):
     elif path == "allreduce":
         gs = parallel.GradAllReduce(model)
     else:
-        gs = parallel.ShardedStep(model, opt, use_multicast=(path == "nvlink"))
-        if path == "nvlink" and not gs.multicast and rank == 0:
-            print("note: no multicast mapping on this box — 'nvlink' runs the peer-pointer variant", flush=True)
+        gs = parallel.ShardedStep(model, opt, mode=path)
+        if gs.mode != path and rank == 0:
+            print(f"note: no multicast mapping on this box — '{path}' runs as '{gs.mode}'", flush=True)
     tr = MiniTrainer(module, opt, sched, grad_sync=gs, use_graphs=graphs, graph_collectives=True)
     losses = [tr.train_step(batches[i % len(batches)]).clone() for i in range(steps)]
     torch.cuda.synchronize()
@@ -87,7 +89,7 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
         for k in base_sd:
             d = float((base_sd[k].float() - ref_sd[k].float()).abs().max())
             assert d <= 2e-3 + 2e-2 * float(ref_sd[k].float().abs().max()), (k, d)
-    for path, graphs in (("nvlink", False), ("nvlink", True), ("p2p", True), ("allreduce", True)):
+    for path, graphs in (("staged", False), ("staged", True), ("nvls", True), ("p2p", True), ("allreduce", True)):
         if contrastive and path == "allreduce":
             continue
         sd, losses, tr, shadow, mom = train(p_drop, path, graphs, mine, contrastive=contrastive)

@@ -60,26 +60,45 @@ log(f"xgpu barrier: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per barrier kernel")
 lo, hi = sh.owned[1][rank]
 hyper = torch.tensor([0.9, 0.999, 1e-4, 1.0, 1e-8, 0.0, 0, 0], device="cuda")
 n_own = hi - lo
-for mc in ([True, False] if sh.multicast else [False]):
-    sh.multicast = mc
-    for blocks in (16, 32, 74, 148, 296, 592):
+
+
+def set_mode(mode):
+    sh.mode = mode
+    sh.out_multicast = sh.has_multicast and mode != "p2p"
+
+
+for mode in (["staged", "nvls", "p2p"] if sh.has_multicast else ["staged", "p2p"]):
+    set_mode(mode)
+    for blocks in (148, 444, 888):
         sh.max_blocks = blocks
         for _ in range(2):
             sh.barrier(2)
             for x, y, b in sh.pieces(lo, hi):
-                sh.launch(x, y, b, hyper.data_ptr())
+                sh.launch(1, x, y, b, hyper.data_ptr())
         torch.cuda.synchronize()
         dist.barrier()
         e0.record()
         reps = 5
         for _ in range(reps):
             for x, y, b in sh.pieces(lo, hi):
-                sh.launch(x, y, b, hyper.data_ptr())
+                sh.launch(1, x, y, b, hyper.data_ptr())
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        log(f"{'multicast' if mc else 'peer-ptr '} blocks {blocks:4d}: {ms:7.3f} ms for {n_own / 1e6:.1f} M owned params  "
-            f"local HBM {24 * n_own / ms / 1e6:7.1f} GB/s  reduced-in {4 * n_own / ms / 1e6:6.1f} GB/s  peer-read total {4 * n_own * (world - 1) / ms / 1e6:6.1f} GB/s")
+        log(f"{mode:6s} blocks {blocks:4d}: {ms:7.3f} ms for {n_own / 1e6:.1f} M owned params  local HBM {(26 + (4 * world if mode == 'staged' else 0)) * n_own / ms / 1e6:7.1f} GB/s")
+# copy-engine push of one bucket
+for _ in range(2):
+    sh.push_bucket(1)
+torch.cuda.synchronize()
+dist.barrier()
+e0.record()
+for _ in range(5):
+    sh.push_bucket(1)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+sent = 4 * sum(b - a for r, (a, b) in enumerate(sh.owned[1]) if r != rank)
+log(f"copy-engine push of one layer bucket: {ms:7.3f} ms for {sent / 1e6:.0f} MB -> {sent / ms / 1e6:.0f} GB/s out of this GPU")
 sh.check()
 
 # ---- pieces of the kernel, one at a time (which one is the ceiling?)
@@ -88,9 +107,9 @@ from algonauts2025_b200 import _lib, ops  # noqa: E402
 
 lib = _lib.load()
 sink = torch.zeros(4, device="cuda")
-sh.multicast = True
 big_lo, big_hi = [(x, y) for x, y, b in sh.pieces(lo, hi) if not b][0]
-args = sh.kernel_args(big_lo, big_hi, False, hyper.data_ptr())
+set_mode("nvls")
+args = sh.kernel_args(1, big_lo, big_hi, False, hyper.data_ptr())
 n_big = big_hi - big_lo
 names = {0: "multimem.ld_reduce only", 1: "peer loads only", 2: "local p/m/v stream only", 3: "multimem.st bf16 only", 4: "ld_reduce, 4 groups/thread"}
 for mode in (0, 4, 1, 2, 3):
@@ -133,8 +152,8 @@ torch.cuda.synchronize()
 alone = e0.elapsed_time(e1) / 30
 log(f"GEMM {M}x{N}x{K} alone: {alone * 1e3:.1f} us = {2 * M * N * K / alone / 1e9:.0f} TFLOP/s (carveout env {os.environ.get('TRIBE_XGPU_CARVEOUT', 'default=100')})")
 for mc in (True, False):
-    sh.multicast = mc
-    for blocks in (16, 32, 74, 148):
+    set_mode("nvls" if mc else "p2p")
+    for blocks in (16, 148):
         sh.max_blocks = blocks
         torch.cuda.synchronize()
         dist.barrier()
@@ -145,7 +164,7 @@ for mc in (True, False):
             s0.record()
             for _ in range(3):
                 for x, y, b in sh.pieces(lo, hi):
-                    sh.launch(x, y, b, hyper.data_ptr())
+                    sh.launch(1, x, y, b, hyper.data_ptr())
             s1.record()
         gemm_loop(30)
         e1.record()
@@ -153,34 +172,50 @@ for mc in (True, False):
         g = e0.elapsed_time(e1) / 30
         log(f"GEMM beside {'multicast' if mc else 'peer-ptr '} tail x3 blocks {blocks:4d}: GEMM {g * 1e3:7.1f} us ({g / alone:4.2f}x), "
             f"tail kernels {s0.elapsed_time(s1) / 3:6.3f} ms each, GEMM loop {g * 30:.2f} ms")
-sh.check()
-# correctness of one launch against torch on the gathered gradients
-sh.multicast = all(int(sh.handles[k].multicast_ptr) != 0 for k in ("grad", "bf16", "flat"))
-sh.max_blocks = 0
-fl.grad.normal_()
-fl.adam_m.zero_(), fl.adam_v.zero_()
 torch.cuda.synchronize()
 dist.barrier()
-gs = [torch.empty_like(fl.grad[lo:hi]) for _ in range(world)]
-mine = fl.grad[lo:hi].clone()
-allg = [torch.empty(fl.total, device="cuda") for _ in range(world)]
-dist.all_gather(allg, fl.grad.clone())
-gmean = sum(a[lo:hi] for a in allg) / world
-p_before = fl.flat[lo:hi].clone()
-sh.barrier(3)
-for x, y, b in sh.pieces(lo, hi):
-    sh.launch(x, y, b, hyper.data_ptr())
-sh.barrier(4)
+side.wait_stream(torch.cuda.current_stream())
+s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+with torch.cuda.stream(side):
+    s0.record()
+    for _ in range(8):
+        sh.push_bucket(1)
+    s1.record()
+gemm_loop(30)
+e1.record()
 torch.cuda.synchronize()
-m = gmean * (1 - 0.9)
-v = (1 - 0.999) * gmean * gmean
-want = p_before - 1e-4 * (m / (v.sqrt() * 1.0 + 1e-8))
-err = float((fl.flat[lo:hi] - want).abs().max())
-shadow_all = [torch.empty(fl.total, device="cuda", dtype=torch.bfloat16) for _ in range(world)]
-dist.all_gather(shadow_all, fl.bf16.clone())
-ok_shadow = all(torch.equal(s, shadow_all[0]) for s in shadow_all)
-own_ok = torch.equal(fl.bf16[lo:hi], fl.flat[lo:hi].to(torch.bfloat16))
-print(f"rank {rank}: adam max err {err:.2e}; shadow equal on all ranks {ok_shadow}; shadow == bf16(master) on owned slice {own_ok}", flush=True)
+g = e0.elapsed_time(e1) / 30
+log(f"GEMM beside 8 copy-engine bucket pushes: GEMM {g * 1e3:7.1f} us ({g / alone:4.2f}x), pushes {s0.elapsed_time(s1) / 8:6.3f} ms each")
 sh.check()
+# correctness of one launch of every mode against torch on the gathered gradients
+for mode in (["staged", "nvls", "p2p"] if sh.has_multicast else ["staged", "p2p"]):
+    set_mode(mode)
+    sh.max_blocks = 0
+    fl.grad.normal_()
+    fl.adam_m.zero_(), fl.adam_v.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+    allg = [torch.empty(fl.total, device="cuda") for _ in range(world)]
+    dist.all_gather(allg, fl.grad.clone())
+    gmean = sum(a[lo:hi] for a in allg) / world
+    p_before = fl.flat[lo:hi].clone()
+    if mode == "staged":
+        sh.push_bucket(1)
+    sh.barrier(3)
+    for x, y, b in sh.pieces(lo, hi):
+        sh.launch(1, x, y, b, hyper.data_ptr())
+    sh.barrier(4)
+    torch.cuda.synchronize()
+    m = gmean * (1 - 0.9)
+    v = (1 - 0.999) * gmean * gmean
+    want = p_before - 1e-4 * (m / (v.sqrt() * 1.0 + 1e-8))
+    err = float((fl.flat[lo:hi] - want).abs().max())
+    shadow_all = [torch.empty(fl.total, device="cuda", dtype=torch.bfloat16) for _ in range(world)]
+    dist.all_gather(shadow_all, fl.bf16.clone())
+    ok_shadow = all(torch.equal(s_, shadow_all[0]) for s_ in shadow_all)
+    own_ok = torch.equal(fl.bf16[lo:hi], fl.flat[lo:hi].to(torch.bfloat16))
+    print(f"rank {rank} mode {mode}: adam max err {err:.2e}; shadow equal on all ranks {ok_shadow}; shadow == bf16(master) on owned slice {own_ok}", flush=True)
+    sh.check()
 dist.barrier()
 os._exit(0)

@@ -484,13 +484,24 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         barrier()
-        if use_graphs:
+        if use_graphs and not sharded:
             # CUDA graphs that captured NCCL collectives keep the communicator busy: destroy_process_group() blocks on
             # them (seen on 2 x B200).  The result is printed and every rank has passed the barrier — leave directly.
             sys.stdout.flush()
             sys.stderr.flush()
             os._exit(0)
-        dist.destroy_process_group()
+        # our own step tail puts no NCCL work into the graphs: a normal teardown (bounded, in case a communicator is stuck)
+        done = threading.Event()
+
+        def _teardown():
+            dist.destroy_process_group()
+            done.set()
+
+        threading.Thread(target=_teardown, daemon=True).start()
+        if not done.wait(30.0):
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def run_ensemble(args):

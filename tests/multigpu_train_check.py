@@ -84,6 +84,14 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
     base_sd, base_losses, _, base_shadow, base_mom = train(p_drop, "allreduce", False, mine, contrastive=contrastive)
     flat = torch.cat([v.flatten().float() for v in base_sd.values()])
     same_on_all_ranks(flat, "allreduce masters")
+    # noise floor: the SAME path run twice (atomically accumulated small gradients + Adam's normalisation of tiny gradients)
+    again_sd, again_losses, _, _, again_mom = train(p_drop, "allreduce", False, mine, contrastive=contrastive)
+
+    def deviation(a_sd, b_sd):
+        return max(float((a_sd[k].float() - b_sd[k].float()).abs().max()) / (1e-3 + float(b_sd[k].float().abs().max())) for k in a_sd)
+
+    floor = deviation(again_sd, base_sd)
+    floor_mom = float((again_mom - base_mom).abs().max()) / float(base_mom.abs().max())
     if p_drop == 0.0:
         ref_sd, _, _, _, _ = train(0.0, "single", False, everyone)
         for k in base_sd:
@@ -99,18 +107,16 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
             assert tr._graphed.replays >= 1, f"{path}: graphs were not replayed"
         # separate runs differ by the run-to-run noise of the atomically accumulated small gradients (norm gains, residual
         # scales, positional embedding): compare against the all-reduce run like test_graphed_gpu compares graph vs eager
-        worst = 0.0
-        for k in sd:
-            d = float((sd[k].float() - base_sd[k].float()).abs().max())
-            worst = max(worst, d / (1e-3 + float(base_sd[k].float().abs().max())))
-            assert d <= 1e-4 + 2e-3 * float(base_sd[k].float().abs().max()), (path, graphs, k, d)
+        worst = deviation(sd, base_sd)
+        assert worst <= 4.0 * floor + 2e-3, (path, graphs, worst, floor)
         same_on_all_ranks(mom, f"{path} gathered Adam moments")
-        assert float((mom - base_mom).abs().max()) <= 1e-6 + 1e-2 * float(base_mom.abs().max()), (path, "Adam moments")
-        assert float((losses - base_losses).abs().max()) <= 2e-3 * float(base_losses.abs().max()), (path, losses, base_losses)
+        dev_mom = float((mom - base_mom).abs().max()) / float(base_mom.abs().max())
+        assert dev_mom <= 4.0 * floor_mom + 1e-3, (path, "Adam moments", dev_mom, floor_mom)
+        assert float((losses - base_losses).abs().max()) <= 4.0 * float((again_losses - base_losses).abs().max()) + 2e-3 * float(base_losses.abs().max())
         dist.barrier()
         if rank == 0:
             print(f"dp train check p_drop={p_drop} contrastive={contrastive} path={path} graphs={graphs}: ranks bit-identical, "
-                  f"max relative deviation from the all-reduce run {worst:.1e}", flush=True)
+                  f"relative deviation from the all-reduce run {worst:.1e} (two all-reduce runs differ by {floor:.1e}), Adam moments {dev_mom:.1e} ({floor_mom:.1e})", flush=True)
 if rank == 0:
     print("multi-GPU data-parallel training OK", flush=True)
 sys.stdout.flush()

@@ -203,13 +203,14 @@ for mode in (["staged", "nvls", "p2p"] if sh.has_multicast else ["staged", "p2p"
     if mode == "staged":
         sh.push_bucket(1)
     sh.barrier(3)
+    hyper_eps1 = torch.tensor([0.9, 0.999, 1e-4, 1.0, 1.0, 0.0, 0, 0], device="cuda")  # eps = 1: the update depends on the gradient SCALE (mean, not sum)
     for x, y, b in sh.pieces(lo, hi):
-        sh.launch(1, x, y, b, hyper.data_ptr())
+        sh.launch(1, x, y, b, hyper_eps1.data_ptr())
     sh.barrier(4)
     torch.cuda.synchronize()
     m = gmean * (1 - 0.9)
     v = (1 - 0.999) * gmean * gmean
-    want = p_before - 1e-4 * (m / (v.sqrt() * 1.0 + 1e-8))
+    want = p_before - 1e-4 * (m / (v.sqrt() * 1.0 + 1.0))
     err = float((fl.flat[lo:hi] - want).abs().max())
     shadow_all = [torch.empty(fl.total, device="cuda", dtype=torch.bfloat16) for _ in range(world)]
     dist.all_gather(shadow_all, fl.bf16.clone())

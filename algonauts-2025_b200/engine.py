@@ -191,6 +191,7 @@ class Plan:
         self.mode = "predict"   # "predict": readout output; "latents": final-norm output (B, T, H)
         self.x_input = False    # transformer_forward entry: encoder input given as a tensor
         self.training = False
+        self.out = None         # optional preallocated (B, O, T') fp32 output (evaluation sweeps write predictions in place)
 
     def __del__(self):
         # a grad-enabled forward whose backward never runs (main.py:349 warm-up call, a skipped loss, an exception):
@@ -421,7 +422,11 @@ class Engine:
             ops.token_pool_fwd(ws.xnf, xp, B, T, Tq, H)
         else:
             Tq, xp = T, ws.xnf
-        out = torch.empty(B, O, Tq, device=self.device, dtype=torch.float32)
+        out = plan.out
+        if out is None:
+            out = torch.empty(B, O, Tq, device=self.device, dtype=torch.float32)
+        elif tuple(out.shape) != (B, O, Tq) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise TribeError(f"forward(out=...): expected contiguous float32 {(B, O, Tq)} on {self.device}, got {tuple(out.shape)} {out.dtype}")
         w16 = self._w16("predictor.weights")
         x_op = ops.Operand(xp, inner=H, rows=Tq, row_stride=H, batch=B, batch_stride=Tq * H)
         w_op = ops.Operand(w16, inner=O, rows=H, row_stride=O, batch=S, batch_stride=H * O, mn_major=True, gather=subj)

@@ -162,7 +162,7 @@ class GroupedMetric(nn.Module):
 
 @torch.no_grad()
 def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice: slice | None = None, distributed: str | None = "auto",
-                             n_outputs: int | None = None) -> np.ndarray:
+                             n_outputs: int | None = None, n_windows: int | None = None, timings: dict | None = None) -> np.ndarray:
     """``Experiment.compute_multidim_pearson`` (main.py:459-477): eval-mode batched predict, then per-parcel Pearson r
     over all (window, TR) rows.  Predictions never leave the device; the 1000-iteration scipy loop becomes one
     statistics kernel per batch + one finalize.  ``parcel_slice`` restricts the statistics to a shard of parcels.
@@ -170,19 +170,42 @@ def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice
     Rank-aware: under ``torch.distributed`` (world size > 1) every rank passes ITS shard of the windows and every rank
     receives r over ALL ranks' windows.  ``distributed="stats"`` (what "auto" selects) all-reduces the fp64 sufficient
     statistics (6 x O doubles); ``"parcels"`` keeps the predictions, re-lays them to parcel shards with one all-to-all
-    and reduces 1000/G parcels per rank (BASELINE config 5, ``parallel.sharded_pearson``); ``None`` = local windows only."""
+    and reduces 1000/G parcels per rank (BASELINE config 5, ``parallel.sharded_pearson``); ``None`` = local windows only.
+    ``n_windows`` (optional, "parcels" mode): this rank's window count — predictions are then written in place into one
+    preallocated buffer by the readout GEMM.  ``timings`` (optional dict) receives CUDA-event pairs per stage."""
     model.eval()
     ws = _world_size()
     mode = ("stats" if ws > 1 else None) if distributed == "auto" else distributed
-    if ws == 1:
+    if ws == 1 and mode == "stats":
         mode = None
     stats = shift = None
-    kept_p, kept_t = [], []
+    kept_p, kept_t, buf_p, buf_t, filled = [], [], None, None, 0
+
+    def stamp(name, first=None):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            timings.setdefault(name, []).append(e)
+
+    stamp("predict")
     for batch in loader:
-        y_pred = model(batch)
-        y_true = batch.data["fmri"].to(y_pred.device, torch.float32)
+        y_true = batch.data["fmri"]
         if y_true.ndim == 4:
             y_true = y_true.squeeze(-1)
+        if mode == "parcels" and n_windows is not None and parcel_slice is None and hasattr(model, "_engine"):
+            bsz = y_true.shape[0]
+            if buf_p is None:
+                dev = model._engine.device if model._engine.device is not None else torch.device("cuda", torch.cuda.current_device())
+                buf_p = torch.empty(n_windows, *y_true.shape[1:], device=dev, dtype=torch.float32)
+                buf_t = torch.empty_like(buf_p)
+            if filled + bsz > n_windows:
+                raise TribeError(f"compute_multidim_pearson: more windows than n_windows={n_windows}")
+            model(batch, out=buf_p[filled: filled + bsz])
+            ops.copy_(buf_t[filled: filled + bsz], y_true.to(buf_t.device, torch.float32).contiguous())
+            filled += bsz
+            continue
+        y_pred = model(batch)
+        y_true = y_true.to(y_pred.device, torch.float32)
         if parcel_slice is not None:
             y_pred, y_true = y_pred[:, parcel_slice], y_true.contiguous()[:, parcel_slice]  # read in place by the kernel
         if mode == "parcels":
@@ -193,10 +216,15 @@ def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice
             shift = torch.empty(2, y_pred.shape[1], device=y_pred.device, dtype=torch.float32)
             ops.pearson_pick_shift(y_pred.float(), y_true, shift, layout="bdt")
         ops.pearson_stats(y_pred.float(), y_true, stats, layout="bdt", shift=shift)
+    stamp("predict")
     if mode == "parcels":
         from . import parallel
 
-        r = parallel.sharded_pearson(torch.cat(kept_p), torch.cat(kept_t))
+        if buf_p is not None:
+            p_all, t_all = buf_p[:filled], buf_t[:filled]
+        else:
+            p_all, t_all = torch.cat(kept_p), torch.cat(kept_t)
+        r = parallel.sharded_pearson(p_all, t_all, timings=timings)
         return r.cpu().numpy().astype(np.float32)
     if stats is None:  # a rank without windows still has to take part in the reduction
         if mode != "stats":
@@ -207,9 +235,11 @@ def compute_multidim_pearson(model: nn.Module, loader: tp.Iterable, parcel_slice
         if parcel_slice is not None:
             o = len(range(*parcel_slice.indices(o)))
         stats = torch.zeros(1, 6, o, device=torch.device("cuda", torch.cuda.current_device()), dtype=torch.float64)
+    stamp("pearson")
     if mode == "stats":
         stats = _merged_stats(stats, shift)
     r, _ = ops.pearson_finalize(stats[0])
+    stamp("pearson")
     return r.cpu().numpy().astype(np.float32)
 
 

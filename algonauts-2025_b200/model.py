@@ -368,16 +368,34 @@ class FmriEncoder(nn.Module):
             self.flush_subject_check()
         return subj
 
+    # Gradients are written by hand into the flat buffer (engine.backward): the parameters' AccumulateGrad nodes never run,
+    # so torch DistributedDataParallel's reducer hooks never fire — wrapping this module in DDP (Lightning strategy "ddp*",
+    # main.py:388-394) would silently train every rank on its local gradient.  Data-parallel training goes through
+    # parallel.data_parallel(model, optimizer) (BrainModule.configure_optimizers installs it); a training forward in a
+    # multi-rank job without it raises unless the replica is declared independent (ensemble members).
+    independent_replica = False
+
+    def _check_gradient_sync(self) -> None:
+        if not self.training or self._engine.comm is not None or self.independent_replica:
+            return
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise TribeError("training forward in a multi-rank job without gradient synchronisation: torch DDP hooks never fire for this "
+                             "module (gradients are written directly into the flat buffer). Use parallel.data_parallel(model, optimizer) "
+                             "(BrainModule.configure_optimizers does) or set model.independent_replica = True for ensemble members.")
+
     def _anchor(self):
         # What makes the output of ``_Fn`` require grad.  A FRESH leaf per call (not a parameter): autograd caches a
         # leaf's AccumulateGrad node together with the stream it was created on for as long as any old graph is alive,
         # and running that node during a CUDA-graph capture would tie the capture to uncaptured work on that stream.
         return torch.empty(0, device=self._engine.device, requires_grad=True)
 
-    def _run(self, batch, *, mode, pool=True, x_in=None, subject_id=None):
+    def _run(self, batch, *, mode, pool=True, x_in=None, subject_id=None, out=None):
         eng = self._engine
         eng._check_flat()
         plan = Plan()
+        plan.out = out
         plan.mode, plan.pool, plan.t_out = mode, pool, self.pooler.output_size
         plan.training = self.training
         if x_in is None:
@@ -396,13 +414,18 @@ class FmriEncoder(nn.Module):
                     raise TribeError(f"transformer_forward: {plan.subjects.numel()} subject ids for a batch of {x_in.shape[0]}")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
+            self._check_gradient_sync()
             return _Fn.apply(self._anchor(), x_in, eng, plan, data)
         out = eng.forward(plan, data, x_in)
         eng.release(plan)
         return out
 
-    def forward(self, batch: SegmentData, pool_outputs: bool = True) -> torch.Tensor:
-        return self._run(batch, mode="predict", pool=pool_outputs)
+    def forward(self, batch: SegmentData, pool_outputs: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
+        """model.py:113-123.  ``out`` (extension): a preallocated (B, n_outputs, T') fp32 CUDA tensor the readout GEMM writes
+        into — evaluation sweeps collect predictions without a copy (no-grad calls only)."""
+        if out is not None and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise TribeError("forward(out=...) is for inference: call it under torch.no_grad()")
+        return self._run(batch, mode="predict", pool=pool_outputs, out=out)
 
     def aggregate_features(self, batch):
         """model.py:125-165 (projector outputs, concatenated / summed; dropped modalities zeroed), (B, T, H) fp32.

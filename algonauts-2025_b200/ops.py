@@ -481,6 +481,14 @@ def zero_(t) -> None:
         _run("tribe_memset_zero", _ptr(t), t.numel() * t.element_size(), _stream())
 
 
+def copy_(dst, src) -> None:
+    """Stream-ordered copy-engine copy between contiguous CUDA tensors of equal byte size (cudaMemcpyAsync through the ABI)."""
+    if not (dst.is_cuda and src.is_cuda and dst.is_contiguous() and src.is_contiguous()) or dst.numel() * dst.element_size() != src.numel() * src.element_size():
+        raise TribeError("copy_: contiguous CUDA tensors of equal byte size required")
+    if dst.numel():
+        _run("tribe_memcpy_async", _ptr(dst), _ptr(src), dst.numel() * dst.element_size(), _stream())
+
+
 def scale_dev(src, scalar):
     """src * scalar with ``scalar`` a one-element CUDA tensor (no host read)."""
     _need(src, torch.float32, "scale src")

@@ -450,16 +450,30 @@ def gather_parcels(r_shard: torch.Tensor, n_parcels: int, group=None) -> torch.T
     return torch.cat([p[: b - a] for p, (a, b) in zip(parts, bounds)])
 
 
-def sharded_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=None) -> torch.Tensor:
+def sharded_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=None, timings: dict | None = None) -> torch.Tensor:
     """Per-parcel Pearson r over ALL ranks' rows, parcels sharded across ranks.  Inputs are this rank's (n_local, O)
-    row-major matrices or (n_windows_local, O, T) prediction tensors, fp32 CUDA -> (O,) fp32 on every rank."""
+    row-major matrices or (n_windows_local, O, T) prediction tensors, fp32 CUDA -> (O,) fp32 on every rank.
+    ``timings`` (optional dict) receives CUDA events around the exchange / statistics / gather stages."""
     from . import ops
 
+    def stamp(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            timings.setdefault(name, []).append(e)
+
     O = preds_local.shape[1]
+    stamp("exchange")
     p_shard, _ = exchange_parcel_shards(preds_local, group)
     t_shard, _ = exchange_parcel_shards(trues_local, group)
+    stamp("exchange")
+    stamp("pearson")
     r, _ = ops.pearson_r(p_shard.contiguous(), t_shard.contiguous(), layout="no" if p_shard.dim() == 2 else "bdt")
-    return gather_parcels(r, O, group)
+    stamp("pearson")
+    stamp("gather")
+    out = gather_parcels(r, O, group)
+    stamp("gather")
+    return out
 
 
 def allreduced_pearson(preds_local: torch.Tensor, trues_local: torch.Tensor, group=None) -> torch.Tensor:

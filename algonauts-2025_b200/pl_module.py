@@ -59,6 +59,16 @@ class _FlattenFn(torch.autograd.Function):
         return ops.transpose_last2(g.contiguous().float().view(b, t, d))
 
 
+def _is_torchmetrics(metric) -> bool:
+    """Lightning's ``self.log(name, metric_object)`` accepts ``torchmetrics.Metric`` instances only (it computes / resets
+    them at epoch end); anything else must be logged by value."""
+    try:
+        import torchmetrics
+    except Exception:  # noqa: BLE001
+        return False
+    return isinstance(metric, torchmetrics.Metric)
+
+
 def _flatten_bdt(x: torch.Tensor) -> torch.Tensor:
     if x.is_cuda and x.dim() == 3:
         return _FlattenFn.apply(x)
@@ -79,6 +89,7 @@ class BrainModule(_Base):
         self.model, self.loss, self.metrics = model, loss, metrics
         self.optim_config, self.max_epochs = optim_config, max_epochs
         self.checkpoint_path, self.config = checkpoint_path, config
+        self._grad_sync = None  # parallel.data_parallel(...) installed by configure_optimizers in multi-rank jobs
 
     def forward(self, batch):
         return self.model(batch)
@@ -125,7 +136,10 @@ class BrainModule(_Base):
                 metric.update_bdt(pred, target)  # retrieval metrics fuse the time average into their kernels
             else:
                 metric.update(_flatten_bdt(pred), _flatten_bdt(target))
-            self.log(key, metric, **log_opts)
+            if _is_torchmetrics(metric):
+                self.log(key, metric, **log_opts)  # Lightning computes and resets it at epoch end
+            # our kernel-backed metric classes are plain modules: their VALUE is logged at epoch end
+            # (on_val_or_test_epoch_end) and they are reset at the start of the next epoch
 
     def _run_step(self, batch: SegmentData, batch_idx, step_name):
         pred = self.forward(batch)                                              # (B, D, T) on the device
@@ -147,7 +161,16 @@ class BrainModule(_Base):
 
     # ------------------------------------------------------------------------------------------------ Lightning hooks
     def training_step(self, batch: SegmentData, batch_idx):
+        if self._grad_sync is not None:
+            self._grad_sync.begin_step()
         return self._run_step(batch, batch_idx, step_name="train")[0]
+
+    def on_before_optimizer_step(self, optimizer, *args, **kwargs) -> None:
+        """Lightning calls this after ``loss.backward()`` and right before ``optimizer.step()``: the data-parallel step tail
+        (gradient reduction, rank-sharded Adam, shadow multicast — or the NCCL all-reduce fallback) closes here.  Under a
+        Lightning DDP strategy torch's own reducer sees no gradient (they are written by hand) and stays a no-op."""
+        if self._grad_sync is not None:
+            self._grad_sync.finish_step()
 
     def validation_step(self, batch: SegmentData, batch_idx):
         return self._run_step(batch, batch_idx, step_name="val")[1:]
@@ -157,8 +180,23 @@ class BrainModule(_Base):
 
     def on_val_or_test_epoch_end(self, step_name: str) -> None:
         for key, metric in self.metrics.items():
-            if key.startswith(step_name) and self.GROUPED_TAG in type(metric).__name__.lower():
+            if not key.startswith(step_name):
+                continue
+            if self.GROUPED_TAG in type(metric).__name__.lower():
                 self.log_dict({f"{key}/{group}": value for group, value in metric.compute().items()})
+            elif not _is_torchmetrics(metric):
+                self.log(key, metric.compute())  # epoch-level value (what on_epoch=True logging of a Metric object yields)
+
+    def _reset_metrics(self, step_name: str) -> None:
+        for key, metric in self.metrics.items():
+            if key.startswith(step_name) and not _is_torchmetrics(metric) and hasattr(metric, "reset"):
+                metric.reset()  # Lightning resets torchmetrics objects itself; plain modules would accumulate across epochs
+
+    def on_validation_epoch_start(self) -> None:
+        self._reset_metrics("val")
+
+    def on_test_epoch_start(self) -> None:
+        self._reset_metrics("test")
 
     def on_validation_epoch_end(self) -> None:
         self.on_val_or_test_epoch_end("val")
@@ -175,5 +213,15 @@ class BrainModule(_Base):
         # Adam(+bf16 shadow) kernel; any other optimizer is left untouched
         from .optim import TribeAdam
 
-        TribeAdam.adopt(built["optimizer"] if isinstance(built, dict) else built, self.model)
+        optimizer = built["optimizer"] if isinstance(built, dict) else built
+        TribeAdam.adopt(optimizer, self.model)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not getattr(self.model, "independent_replica", False) \
+                and hasattr(self.model, "_engine"):
+            from . import parallel
+
+            # multi-rank job (Lightning DDP, main.py:388-394): torch DDP cannot see this model's gradients — install our own
+            # gradient path (collective: every rank reaches configure_optimizers)
+            self._grad_sync = parallel.data_parallel(self.model, optimizer)
         return built

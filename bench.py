@@ -10,7 +10,11 @@ full TRIBE shape (text 2x3072, audio 2x1024, video 2x1408 feature stacks at T=29
 `roofline`: all tcgen05 GEMM launches of the timed steps, algorithmic FLOPs / summed CUDA-event time, against the
             measured sustained bf16 peak (MEASURED_PEAKS.json).
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference path (oracle/) on the host cores.
-Under torchrun (N > 1) every rank trains its own 16 windows and gradients are all-reduced over NCCL (weak scaling).
+Under torchrun (N > 1) every rank trains its own 16 windows (weak scaling); gradients travel by copy engine over NVLink
+into their owner's staging buffer during the backward pass and one fused kernel per owned range reduces them, runs the
+rank-sharded Adam and multicasts the bf16 shadow weights (parallel.ShardedStep, csrc/xgpu.cu) — no NCCL in the step.
+Extra keys of the same JSON line (each with its own timing, BASELINE.json configs 4 and 5 and the reference's default
+recipe): `contrastive_on`, `ensemble` (N > 1), `eval_predict`, `eval_sweep`, `pearson_eval`.
 """
 from __future__ import annotations
 
@@ -279,9 +283,10 @@ def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with
                    "unit": "parcel-TRs/s", "h2d_bytes_per_step": 8 * n_e2e * (hi - lo) * EVAL_TRS, "d2h_bytes_per_step": 4 * (hi - lo),
                    "sample": f"{n_e2e} windows per rank from pinned host arrays via metrics.pearson_from_host"},
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                        # dram__bytes_read+write of one launch at this exact shape on 1 GPU, ncu --set full
-                        # (profiles/r01_ncu_full_summary_v2.txt): 2051.0 MB read + 4.4 MB written for 2048 MB of operands
-                        "traffic": 2.0554e9 if world == 1 else None, "algorithmic_bytes": shard_bytes,
+                        # dram__bytes_read+write of one launch at this exact shape on 1 GPU from an ncu --set full capture, with its
+                        # provenance (profiles/ncu_reference.json); NOT measured by this run
+                        "traffic": ncu_reference().get("pearson_bdt_dram_bytes", {}).get("value") if world == 1 else None,
+                        "traffic_source": ncu_reference().get("pearson_bdt_dram_bytes", {}).get("source"), "algorithmic_bytes": shard_bytes,
                         "kernel": "pearson_bdt_kernel<4>", "peak_source": peaks["src"] + " copy bandwidth", "bytes_per_parcel_tr": 8}}
     if with_cpu:
         out["cpu_baseline"] = cpu_pearson_baseline()
@@ -289,15 +294,275 @@ def pearson_eval_leg(rank: int, world: int, steps: int, warmup: int, peaks, with
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def ncu_reference():
+    """ncu-derived context numbers with their provenance (profiles/ncu_reference.json); never measured by this run."""
+    path = os.path.join(ROOT, "profiles", "ncu_reference.json")
+    try:
+        return json.load(open(path))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def _barrier(world):
     import torch.distributed as dist
 
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(values, world):
+    import torch.distributed as dist
+
+    t = torch.tensor(values, device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
+def train_leg(args, rank, world, local, *, contrastive: bool, dp: str, seed: int, steps: int, warmup: int, roofline: bool, e2e: bool,
+              clocks: ClockSampler | None = None, keep_model: bool = False):
+    """One training configuration: build the model (+ optimizer, data-parallel step tail, whole-step graphs), W warm-up
+    steps, K timed steps on device-resident batches, K steps end to end from pinned host batches, and (``roofline``) K
+    instrumented steps with a CUDA-event pair around every tcgen05 GEMM launch."""
     import algonauts2025_b200
     from algonauts2025_b200 import ops, parallel
     from algonauts2025_b200.model import FmriEncoderConfig
     from algonauts2025_b200.pl_module import BrainModule
     from algonauts2025_b200.segment import DevicePrefetcher, synthetic_batch
     from algonauts2025_b200.trainer import MiniTrainer, default_optimizer
+
+    B, K, W = args.batch, steps, warmup
+    torch.manual_seed(seed)  # DP: identical seeds on every rank -> identical weights and dropout masks (main.py:492-495)
+    cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3, feature_aggregation="cat", layer_aggregation="cat", contrastive_enabled=contrastive)
+    model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
+    model.independent_replica = dp == "none"  # ensemble members train without gradient exchange on purpose
+    module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=15)
+    # the reference recipe (Adam lr 1e-4 + OneCycleLR per step); the stock torch.optim.Adam instance is adopted by the
+    # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
+    opt, sched = default_optimizer(model.parameters(), total_steps=4 * (K + W) + 16, model=None if args.stock_adam else model)
+    # N > 1: our NVLink step tail (copy-engine gradient pushes during the backward -> one fused reduce / rank-sharded Adam /
+    # bf16-shadow-multicast kernel per owned range, parallel.ShardedStep); --dp allreduce = NCCL all-reduce + replicated Adam
+    sync = None
+    if world > 1 and dp != "none":
+        if dp == "allreduce" or args.stock_adam:
+            sync = parallel.GradAllReduce(model, gemm_sms_during_comm=args.comm_gemm_sms)
+        else:
+            sync = parallel.data_parallel(model, opt, max_blocks=args.dp_blocks, mode=dp)
+    sharded = isinstance(sync, parallel.ShardedStep)
+    # whole-step CUDA graphs; NCCL all-reduces inside a step are only captured on request, our own step tail always is
+    use_graphs = not args.eager and not args.stock_adam and (sync is None or args.graph_comm or sharded)
+    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=args.graph_comm or sharded,
+                          overlap_optimizer=args.overlap and not args.stock_adam)
+
+    # two distinct host batches (pinned) alternate through the two persistent device slots of a DevicePrefetcher;
+    # 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
+    data_seed = 1234 + (17 * rank if dp != "none" else 0)  # ensemble members see the same data stream (run_ensemble.py)
+    host = [synthetic_batch(batch_size=B, seed=data_seed + i, pin=True) for i in range(2)]
+    prefetch = DevicePrefetcher(())
+    dev = prefetch.resident(host)
+    h2d = sum(v.numel() * v.element_size() for v in host[0].data.values())
+
+    for i in range(W):
+        trainer.eager_step(dev[i % 2])
+    _barrier(world)
+    n_graphs = 0
+    if use_graphs:
+        # steady state of a long run: every modality-dropout variant of the step has been captured (captures execute
+        # nothing; weights, optimizer state and RNG streams are untouched)
+        n_graphs = trainer._graphed.warm(dev)
+        for i in range(2):
+            trainer.train_step(dev[i % 2])
+        _barrier(world)
+
+    # ---- timed region 1: device-resident inputs
+    launches0 = algonauts2025_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(world)
+    e0.record()
+    t_cpu = time.perf_counter()
+    for i in range(K):
+        trainer.train_step(dev[i % 2])
+    cpu_enqueue_ms = 1e3 * (time.perf_counter() - t_cpu) / K  # host time to enqueue one step (no sync inside the loop)
+    e1.record()
+    _barrier(world)
+    t_end = time.perf_counter()
+    launches = algonauts2025_b200.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop(t_cpu, t_end) if clocks is not None else None
+
+    # ---- timed region 2: end to end through the public API from pinned host memory
+    ms_e2e, last = float("nan"), float("nan")
+    if e2e:
+        _barrier(world)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        # public-API loop a user writes: pinned host batches -> DevicePrefetcher (H2D of batch i+1 overlaps step i) -> train_step
+        # every step's loss is read back to pinned host memory inside the timed region (asynchronously, like a logger that
+        # consumes it later; a blocking .item() per step would only measure Python launch latency after each sync)
+        loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
+        for i, batch in enumerate(prefetch.feed(host[j % 2] for j in range(K))):
+            loss_host[i].copy_(trainer.train_step(batch), non_blocking=True)
+        f1.record()
+        _barrier(world)
+        ms_e2e = f0.elapsed_time(f1)
+        last = float(loss_host[-1])
+        assert all(math.isfinite(float(x)) for x in loss_host), "non-finite loss in the end-to-end loop"
+
+    # ---- roofline pass: K more steps with a CUDA-event pair around every tcgen05 GEMM launch.  With graphs the pairs
+    # are captured as event-record nodes of an instrumented copy of the (no-modality-dropped) step graph and read back
+    # after each replay, so the GEMMs are timed inside a GPU-bound step exactly like in the timed region.
+    gemm_ms, gemm_flops, ms_instr = 0.0, 0.0, float("nan")
+    if roofline:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if use_graphs:
+            entries = []
+            for j in range(2):
+                ops.GEMM_LOG = []
+                entry = trainer._graphed._capture(dev[j], [[] for _ in range(2 if contrastive else 1)])
+                entries.append((entry, ops.GEMM_LOG))
+                ops.GEMM_LOG = None
+            _barrier(world)
+            g0.record()
+            for i in range(K):
+                entry, log = entries[i % 2]
+                trainer._graphed._replay(entry)
+                torch.cuda.synchronize()
+                gemm_ms += sum(a.elapsed_time(b) for a, b, _ in log)
+                gemm_flops += sum(f for _, _, f in log)
+            g1.record()
+        else:
+            ops.GEMM_LOG = []
+            g0.record()
+            for i in range(K):
+                trainer.eager_step(dev[i % 2])
+            g1.record()
+            _barrier(world)
+            gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.GEMM_LOG)
+            gemm_flops = sum(f for _, _, f in ops.GEMM_LOG)
+            ops.GEMM_LOG = None
+        _barrier(world)
+        ms_instr = g0.elapsed_time(g1)
+    if sharded:
+        sync.check()  # no cross-rank wait of the step tail timed out
+
+    ms, ms_e2e, gemm_ms, ms_instr = _max_over_ranks([ms, ms_e2e if e2e else 0.0, gemm_ms, ms_instr if roofline else 0.0], world)
+    peaks = measured_peaks()
+    n_models = world
+    out = {"value": n_models * B * K / (ms / 1e3), "ms_per_step": ms / K, "steps": K, "warmup": W, "contrastive": contrastive,
+           "gpu_launches": launches, "host_enqueue_ms_per_step": cpu_enqueue_ms, "last_loss": last, "h2d": h2d,
+           "cuda_graphs": {"enabled": use_graphs, "variants_captured": n_graphs, "replays": trainer._graphed.replays if use_graphs else 0},
+           "gradient_path": ("none (1 GPU)" if world == 1 else "none (independent ensemble members)" if dp == "none" else
+                             sync.describe() if sharded else "NCCL all-reduce (fp32, 9 buckets) + replicated fused Adam"),
+           "clocks": clk}
+    if e2e:
+        out["e2e"] = {"value": n_models * B * K / (ms_e2e / 1e3), "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+    step_tflops = algorithmic_flops_per_window(contrastive) * B * K / (ms / 1e3) / 1e12
+    out["whole_step_tflops"], out["whole_step_frac"] = step_tflops, step_tflops / peaks["tflops"]
+    if roofline:
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        ref = ncu_reference()
+        out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                           # context from ncu captures, with provenance (profiles/ncu_reference.json); NOT measured by this run
+                           "traffic": (ref.get("train_step_gemm_dram_bytes", {}).get("value") if not contrastive else None),
+                           "traffic_unit": "dram bytes per train step, all GEMM launches", "traffic_source": ref.get("train_step_gemm_dram_bytes", {}).get("source"),
+                           "tensor_pipe_active_pct_ncu": ref.get("tensor_pipe_active_pct", {}).get("value"),
+                           "tensor_pipe_source": ref.get("tensor_pipe_active_pct", {}).get("source"),
+                           "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (all tcgen05 GEMM launches of the timed steps)",
+                           "peak_source": peaks["src"] + " sustained bf16", "gemm_share_of_step": gemm_ms / (ms_instr if ms_instr else ms),
+                           "measured_in": ("K replays of an instrumented step graph (event-record nodes around every GEMM launch)" if use_graphs
+                                           else "the K eager steps, CUDA-event pair per GEMM launch"), "instrumented_ms_per_step": ms_instr / K,
+                           "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peaks["tflops"]}
+    del trainer, opt, sched, module, dev, prefetch
+    if sharded:
+        model._engine.comm = None
+    if not keep_model:
+        del model
+        model = None
+    torch.cuda.empty_cache()
+    return out, model
+
+
+def ensemble_eval_leg(model, rank, world, B):
+    """BASELINE config 4, evaluation half (average_submissions.py:107-125): every member predicts the same windows, its
+    per-parcel validation r weights its predictions, one all-reduce forms the ensemble prediction, the Pearson kernel
+    scores it."""
+    from algonauts2025_b200 import ops, parallel
+    from algonauts2025_b200.segment import synthetic_batch
+
+    model.eval()
+    shared = [synthetic_batch(batch_size=B, seed=999 + i) for i in range(4)]
+    shared = [type(b)(data={k: v.cuda() for k, v in b.data.items()}, segments=b.segments) for b in shared]
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        model(shared[0])
+        _barrier(world)
+        f0.record()
+        preds = torch.empty(4 * B, 1000, 100, device="cuda")
+        for i, b in enumerate(shared):
+            model(b, out=preds[i * B:(i + 1) * B])                              # this member's predictions, written in place
+        trues = torch.cat([b.data["fmri"] for b in shared])
+        r_member = ops.pearson_r(preds, trues, layout="bdt")[0]                # (O,) per-parcel r of this member
+        ens = parallel.ensemble_average(preds, r_member, temperature=0.3)      # weighted all-reduce (reference weighting)
+        r_ens, mean_ens = ops.pearson_r(ens.contiguous(), trues, layout="bdt", want_mean=True)
+        f1.record()
+    _barrier(world)
+    (ms_eval,) = _max_over_ranks([f0.elapsed_time(f1)], world)
+    model.train()
+    return {"windows": 4 * B, "members": world, "ms": ms_eval, "windows_per_s": 4 * B / (ms_eval / 1e3), "mean_r_member0": float(r_member.mean()),
+            "mean_r_ensemble": float(mean_ens[0]), "collective": "weighted all-reduce (NCCL) of the members' predictions inside the timed region",
+            "weights": "softmax(r / 0.3) over the voxel axis per member (average_submissions.py:108-109)"}
+
+
+def eval_sweep_leg(model, rank, world, n_windows: int = EVAL_WINDOWS, batch: int = 64):
+    """BASELINE config 5 end to end: every rank predicts ITS shard of the held-out windows from pinned host batches
+    (H2D inside the timed region), one all-to-all re-lays (window shard x all parcels) into (all windows x parcel shard),
+    every rank reduces 1000/G parcels with the Pearson kernel, r is gathered and read back — the public call
+    ``metrics.compute_multidim_pearson(model, loader, distributed="parcels")`` (main.py:459-477)."""
+    from algonauts2025_b200 import metrics
+    from algonauts2025_b200.segment import DevicePrefetcher, synthetic_batch
+
+    per_rank = n_windows // world
+    n_batches = max(1, per_rank // batch)
+    per_rank = n_batches * batch
+    host = [synthetic_batch(batch_size=batch, seed=4321 + 31 * rank + i, pin=True) for i in range(2)]
+    prefetch = DevicePrefetcher(())
+    model.eval()
+    metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(2)), distributed="parcels", n_windows=2 * batch)  # warm-up
+    _barrier(world)
+    timings = {}
+    t0 = time.perf_counter()
+    r = metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(n_batches)), distributed="parcels",
+                                         n_windows=per_rank, timings=timings)
+    wall = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    assert r.shape == (EVAL_PARCELS,) and np_isfinite(r)
+    stage = {k: v[0].elapsed_time(v[-1]) for k, v in timings.items() if len(v) >= 2}
+    vals = _max_over_ranks([wall] + [stage.get(k, 0.0) for k in ("predict", "exchange", "pearson", "gather")], world)
+    wall, stage_ms = vals[0], dict(zip(("predict", "exchange", "pearson", "gather"), vals[1:]))
+    model.train()
+    total = per_rank * world
+    h2d = sum(v.numel() * v.element_size() for v in host[0].data.values())
+    return {"metric": "eval sweep (predict -> parcel all-to-all -> sharded Pearson -> gather) windows/s", "value": total / wall, "unit": "windows/s",
+            "parcel_trs_per_s": total * EVAL_PARCELS * EVAL_TRS / wall, "windows": total, "windows_per_gpu": per_rank, "batch_per_gpu": batch,
+            "wall_s": wall, "stage_ms_max_over_ranks": stage_ms, "mean_r": float(r.mean()),
+            "e2e": {"value": total / wall, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * EVAL_PARCELS,
+                    "api": 'metrics.compute_multidim_pearson(model, DevicePrefetcher(pinned host batches), distributed="parcels") -> r[1000] on host'},
+            "exchange_bytes_per_gpu": 2 * 4 * per_rank * EVAL_TRS * (EVAL_PARCELS - EVAL_PARCELS // world) if world > 1 else 0,
+            "collectives": ("NCCL all-to-all of predictions + targets, all-gather of r — inside the timed region" if world > 1 else "none (1 GPU)")}
+
+
+def np_isfinite(a):
+    import numpy as np
+
+    return bool(np.isfinite(a).all())
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import algonauts2025_b200
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -306,6 +571,7 @@ def run_ours(args):
     algonauts2025_b200.load()
     B, K, W = args.batch, args.steps, args.warmup
     contrastive = bool(args.contrastive)
+    extras = not args.headline_only
 
     # The Pearson-eval leg is an independent metric of a bandwidth kernel "timed alone": it runs FIRST, before the train legs
     # put the board under its power cap (tools/pearson_variance_probe.py: 6.1-6.3 TB/s on a cool chip, 5.5 TB/s right after
@@ -313,178 +579,70 @@ def run_ours(args):
     pe = pearson_eval_leg(rank, world, max(K, 5), W, measured_peaks(), world == 1 and not args.no_cpu_baseline) if not args.no_pearson else None
     torch.cuda.empty_cache()
 
-    torch.manual_seed(33)  # identical seeds on every rank -> identical weights and dropout masks (main.py:492-495)
-    cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3, feature_aggregation="cat", layer_aggregation="cat", contrastive_enabled=contrastive)
-    model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
-    module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=15)
-    # the reference recipe (Adam lr 1e-4 + OneCycleLR per step); the stock torch.optim.Adam instance is adopted by the
-    # fused Adam + bf16-shadow kernel exactly as BrainModule.configure_optimizers does (--stock-adam keeps torch's)
-    opt, sched = default_optimizer(model.parameters(), total_steps=4 * (K + W) + 16, model=None if args.stock_adam else model)
-    # N > 1: our NVLink step tail (copy-engine gradient pushes during the backward -> one fused reduce / rank-sharded Adam /
-    # bf16-shadow-multicast kernel per owned range, parallel.ShardedStep); --dp allreduce = NCCL all-reduce + replicated Adam
-    sync = None
-    if world > 1:
-        if args.dp == "allreduce" or args.stock_adam:
-            sync = parallel.GradAllReduce(model, gemm_sms_during_comm=args.comm_gemm_sms)
-        else:
-            sync = parallel.data_parallel(model, opt, max_blocks=args.dp_blocks, mode=args.dp)
-    sharded = isinstance(sync, parallel.ShardedStep)
-    # whole-step CUDA graphs; NCCL all-reduces inside a step are only captured on request, our own step tail always is
-    use_graphs = not args.eager and not args.stock_adam and (world == 1 or args.graph_comm or sharded)
-    # measured on B200 (profiles/r01_adam_overlap_ab.txt): the step is power-capped, so moving Adam's 28 GB of HBM
-    # traffic beside the GEMMs lowers their clocks by as much as it saves — off by default
-    overlap = args.overlap and not args.stock_adam
-    trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=args.graph_comm,
-                          overlap_optimizer=overlap)
-
-    # two distinct host batches (pinned) alternate through the two persistent device slots of a DevicePrefetcher;
-    # 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
-    host = [synthetic_batch(batch_size=B, seed=1234 + 17 * rank + i, pin=True) for i in range(2)]
-    prefetch = DevicePrefetcher(())
-    dev = prefetch.resident(host)
-    h2d = sum(v.numel() * v.element_size() for v in host[0].data.values())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     clocks = ClockSampler(local)
     clocks.start()  # nvidia-smi needs a few hundred ms to deliver its first sample: start ahead of the timed region
-    for i in range(W):
-        trainer.eager_step(dev[i % 2])
-    barrier()
-    n_graphs = 0
-    if use_graphs:
-        # steady state of a long run: every modality-dropout variant of the step has been captured (captures execute
-        # nothing; weights, optimizer state and RNG streams are untouched)
-        n_graphs = trainer._graphed.warm(dev)
-        for i in range(2):
-            trainer.train_step(dev[i % 2])
-        barrier()
-
-    # ---- timed region 1: device-resident inputs
-    launches0 = algonauts2025_b200.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    t_cpu = time.perf_counter()
-    for i in range(K):
-        trainer.train_step(dev[i % 2])
-    cpu_enqueue_ms = 1e3 * (time.perf_counter() - t_cpu) / K  # host time to enqueue one step (no sync inside the loop)
-    e1.record()
-    barrier()
-    t_end = time.perf_counter()
-    launches = algonauts2025_b200.launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-
-    # ---- timed region 2: end to end through the public API from pinned host memory
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    last = 0.0
-    # public-API loop a user writes: pinned host batches -> DevicePrefetcher (H2D of batch i+1 overlaps step i) -> train_step
-    # every step's loss is read back to pinned host memory inside the timed region (asynchronously, like a logger that
-    # consumes it later; a blocking .item() per step would only measure Python launch latency after each sync)
-    loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
-    for i, batch in enumerate(prefetch.feed(host[j % 2] for j in range(K))):
-        loss_host[i].copy_(trainer.train_step(batch), non_blocking=True)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    clk = clocks.stop(t_cpu, t_end)
-
-    # ---- roofline pass: K more steps with a CUDA-event pair around every tcgen05 GEMM launch.  With graphs the pairs
-    # are captured as event-record nodes of an instrumented copy of the (no-modality-dropped) step graph and read back
-    # after each replay, so the GEMMs are timed inside a GPU-bound step exactly like in the timed region.
-    gemm_ms, gemm_flops = 0.0, 0.0
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if use_graphs:
-        entries = []
-        for j in range(2):
-            ops.GEMM_LOG = []
-            entry = trainer._graphed._capture(dev[j], [[] for _ in range(2 if contrastive else 1)])
-            entries.append((entry, ops.GEMM_LOG))
-            ops.GEMM_LOG = None
-        barrier()
-        g0.record()
-        for i in range(K):
-            entry, log = entries[i % 2]
-            trainer._graphed._replay(entry)
-            torch.cuda.synchronize()
-            gemm_ms += sum(a.elapsed_time(b) for a, b, _ in log)
-            gemm_flops += sum(f for _, _, f in log)
-        g1.record()
-    else:
-        ops.GEMM_LOG = []
-        g0.record()
-        for i in range(K):
-            trainer.eager_step(dev[i % 2])
-        g1.record()
-        barrier()
-        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.GEMM_LOG)
-        gemm_flops = sum(f for _, _, f in ops.GEMM_LOG)
-        ops.GEMM_LOG = None
-    barrier()
-    ms_eager = g0.elapsed_time(g1)
-    last = float(loss_host[-1])
-    if sharded:
-        sync.check()  # no cross-rank wait of the step tail timed out
-    assert all(math.isfinite(float(x)) for x in loss_host), "non-finite loss in the end-to-end loop"
-
-    t = torch.tensor([ms, ms_e2e, gemm_ms, ms_eager], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, gemm_ms, ms_eager = (float(x) for x in t.cpu())
+    main_leg, model = train_leg(args, rank, world, local, contrastive=contrastive, dp=args.dp, seed=33, steps=K, warmup=W, roofline=True, e2e=True,
+                                clocks=clocks, keep_model=True)
+    line = None
     if rank == 0:
-        peaks = measured_peaks()
-        value = world * B * K / (ms / 1e3)
-        e2e = world * B * K / (ms_e2e / 1e3)
-        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-        step_tflops = algorithmic_flops_per_window(contrastive) * B * K / (ms / 1e3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(2, 1, REF_WINDOWS_PER_STEP, contrastive)  # bounded sample: ~20 s of host work (1.7 TFLOP per window-step)
             cpu = {"value": r["windows_per_s"], "unit": "windows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-        line = {"metric": "train windows/s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        line = {"metric": "train windows/s", "value": main_leg["value"], "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": main_leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
-                           "gradient_path": ("none (1 GPU)" if world == 1 else
-                                             sync.describe() if sharded else "NCCL all-reduce (fp32, 9 buckets) + replicated fused Adam"),
-                           "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel)") + " + OneCycleLR, fp32 master weights",
-                           "optimizer_overlap": overlap, "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
-                           "last_loss": last, "host_enqueue_ms_per_step": cpu_enqueue_ms,
-                           "cuda_graphs": {"enabled": use_graphs, "variants_captured": n_graphs, "replays": trainer._graphed.replays if use_graphs else 0}},
-                "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches,
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                             # dram bytes of ALL GEMM launches of one step (8 x the layer-0 fwd + layer-7 bwd captures of
-                             # profiles/r01_ncu_full_summary_v2.txt; tensor-bound kernels, so this is context, not the bound)
-                             "traffic": 27.65e9 if not contrastive else None, "traffic_unit": "dram bytes per train step, all GEMM launches",
-                             "tensor_pipe_active_pct_ncu": {"wgrad": "82-85", "ff1/qkv fwd": "72-80", "dgrad": "65-82", "out 3072^2": "44-67", "attention": "11-18"},
-                             "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (all tcgen05 GEMM launches of the timed steps)",
-                             "peak_source": peaks["src"] + " sustained bf16", "gemm_share_of_step": gemm_ms / ms if ms else None,
-                             "measured_in": ("K replays of an instrumented step graph (event-record nodes around every GEMM launch)" if use_graphs
-                                             else "the K eager steps, CUDA-event pair per GEMM launch"), "instrumented_ms_per_step": ms_eager / K,
-                             "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peaks["tflops"]},
-                "clocks": clk}
+                           "gradient_path": main_leg["gradient_path"],
+                           "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel" + (", rank-sharded" if world > 1 and args.dp not in ("allreduce", "none") else "") + ")") + " + OneCycleLR, fp32 master weights",
+                           "optimizer_overlap": bool(args.overlap), "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
+                           "last_loss": main_leg["last_loss"], "host_enqueue_ms_per_step": main_leg["host_enqueue_ms_per_step"],
+                           "cuda_graphs": main_leg["cuda_graphs"]},
+                "e2e": main_leg["e2e"], "gpu_launches": main_leg["gpu_launches"], "roofline": main_leg["roofline"], "clocks": main_leg["clocks"]}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    del trainer, opt, sched, module, dev
-    torch.cuda.empty_cache()
-    ev = eval_predict_leg(model, rank, world, max(K // 2, 4)) if not args.no_pearson else None
-    if rank == 0 and ev is not None:
-        line["eval_predict"] = ev
+
+    # ---- BASELINE config 5 (eval sweep) on the trained replica: batched predict + parcel-sharded Pearson
+    ev = sweep = None
+    if not args.no_pearson:
+        ev = eval_predict_leg(model, rank, world, max(K // 2, 4))
+        if extras:
+            sweep = eval_sweep_leg(model, rank, world)
     del model
     torch.cuda.empty_cache()
+
+    # ---- the reference's default recipe has the contrastive branch ON (defaults.py:102): second encoder pass + InfoNCE
+    con = ens = None
+    if extras and not contrastive:
+        con, _ = train_leg(args, rank, world, local, contrastive=True, dp=args.dp, seed=33, steps=max(K // 2, 5), warmup=max(W, 3), roofline=True, e2e=False)
+    # ---- BASELINE config 4 (run_ensemble): one independent member per GPU (own seed, no training collectives) + ensemble eval
+    if extras and world > 1:
+        ens, member = train_leg(args, rank, world, local, contrastive=False, dp="none", seed=1000 + rank, steps=max(K // 2, 5), warmup=max(W, 3),
+                                roofline=False, e2e=False, keep_model=True)
+        ens["ensemble_eval"] = ensemble_eval_leg(member, rank, world, B)
+        del member
+        torch.cuda.empty_cache()
+
     if rank == 0:
+        if ev is not None:
+            line["eval_predict"] = ev
+        if sweep is not None:
+            line["eval_sweep"] = sweep
         if pe is not None:
             line["pearson_eval"] = pe
+        if con is not None:
+            line["contrastive_on"] = {"metric": "train windows/s, contrastive branch on (reference default, defaults.py:102)", "value": con["value"], "unit": "windows/s",
+                                      "ms_per_step": con["ms_per_step"], "steps": con["steps"], "gpu_launches": con["gpu_launches"], "cuda_graphs": con["cuda_graphs"],
+                                      "gradient_path": con["gradient_path"], "roofline": con["roofline"]}
+        if ens is not None:
+            line["ensemble"] = {"metric": "ensemble train windows/s (BASELINE config 4: one member per GPU, no training collectives)", "value": ens["value"],
+                                "unit": "windows/s", "members": world, "ms_per_step": ens["ms_per_step"], "steps": ens["steps"], "scaling": "weak",
+                                "whole_step_frac": ens["whole_step_frac"], "gpu_launches": ens["gpu_launches"], "ensemble_eval": ens["ensemble_eval"]}
+        elif extras:
+            line["ensemble"] = {"skipped": "1 GPU: an ensemble of one member is the headline train step; run with --gpus >= 2"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        barrier()
-        if use_graphs and not sharded:
+        _barrier(world)
+        if args.graph_comm and args.dp == "allreduce":
             # CUDA graphs that captured NCCL collectives keep the communicator busy: destroy_process_group() blocks on
             # them (seen on 2 x B200).  The result is printed and every rank has passed the barrier — leave directly.
             sys.stdout.flush()
@@ -505,79 +663,25 @@ def run_ours(args):
 
 
 def run_ensemble(args):
-    """BASELINE.json config 4 (run_ensemble): one TRIBE member per GPU (own seed, no training collectives), then the
-    ensemble-averaged per-parcel Pearson evaluation on a shared held-out set (average_submissions.py:107-125):
-    every member predicts the same windows, its per-parcel validation r weights its predictions, one all-reduce
-    forms the ensemble prediction, the Pearson kernel scores it."""
+    """``--mode ensemble``: only the BASELINE config 4 legs (the default run reports them under the ``ensemble`` key)."""
     import torch.distributed as dist
 
     import algonauts2025_b200
-    from algonauts2025_b200 import ops, parallel
-    from algonauts2025_b200.model import FmriEncoderConfig
-    from algonauts2025_b200.pl_module import BrainModule
-    from algonauts2025_b200.segment import DevicePrefetcher, synthetic_batch
-    from algonauts2025_b200.trainer import MiniTrainer, default_optimizer
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     algonauts2025_b200.load()
-    B, K, W = args.batch, args.steps, args.warmup
-    torch.manual_seed(1000 + rank)  # run_ensemble.py:23 seed=None -> every member its own initialisation
-    cfg = FmriEncoderConfig(n_subjects=4, modality_dropout=0.3)
-    model = cfg.build(feature_dims=FEATURE_DIMS, n_outputs=1000, n_output_timesteps=100)
-    module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=15)
-    opt, sched = default_optimizer(model.parameters(), total_steps=2 * (K + W) + 16, model=model)
-    trainer = MiniTrainer(module, opt, sched, use_graphs=not args.eager)
-    host = [synthetic_batch(batch_size=B, seed=1234 + i, pin=True) for i in range(2)]  # same data stream for every member
-    dev = DevicePrefetcher(()).resident(host)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(W):
-        trainer.eager_step(dev[i % 2])
-    if trainer._graphed is not None:
-        trainer._graphed.warm(dev)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        trainer.train_step(dev[i % 2])
-    e1.record()
-    barrier()
-    ms_train = e0.elapsed_time(e1)
-    # ---- ensemble evaluation on a shared set of 4 x B windows
-    model.eval()
-    shared = [synthetic_batch(batch_size=B, seed=999 + i) for i in range(4)]
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    f0.record()
-    with torch.no_grad():
-        preds = torch.cat([model(b) for b in shared])                          # (4B, O, T') this member's predictions
-        trues = torch.cat([b.data["fmri"] for b in shared]).cuda()
-        r_member = ops.pearson_r(preds, trues, layout="bdt")[0]                # (O,) per-parcel r of this member
-        ens = parallel.ensemble_average(preds, r_member, temperature=0.3)      # weighted all-reduce (reference weighting)
-        r_ens, mean_ens = ops.pearson_r(ens.contiguous(), trues, layout="bdt", want_mean=True)
-    f1.record()
-    barrier()
-    ms_eval = f0.elapsed_time(f1)
-    t = torch.tensor([ms_train, ms_eval], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_train, ms_eval = (float(x) for x in t.cpu())
+    ens, member = train_leg(args, rank, world, local, contrastive=False, dp="none", seed=1000 + rank, steps=args.steps, warmup=args.warmup,
+                            roofline=False, e2e=False, keep_model=True)
+    ev = ensemble_eval_leg(member, rank, world, args.batch)
     if rank == 0:
-        print(json.dumps({"metric": "ensemble train windows/s (one member per GPU)", "value": world * B * K / (ms_train / 1e3), "unit": "windows/s",
-                          "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_train / K, "higher_is_better": True, "scaling": "weak",
+        print(json.dumps({"metric": "ensemble train windows/s (one member per GPU)", "value": ens["value"], "unit": "windows/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ens["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                           "config": {"workload": WORKLOAD, "members": world, "parallelism": f"ensemble x{world} (no training collectives)"},
-                          "ensemble_eval": {"windows": 4 * B, "ms": ms_eval, "windows_per_s": 4 * B / (ms_eval / 1e3),
-                                            "mean_r_member0": float(r_member.mean()), "mean_r_ensemble": float(mean_ens[0]),
-                                            "weights": "softmax(r / 0.3) over the voxel axis per member (average_submissions.py:108-109)"}}), flush=True)
+                          "gpu_launches": ens["gpu_launches"], "ensemble_eval": ev}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -592,10 +696,11 @@ def main():
     ap.add_argument("--contrastive", type=int, default=0)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pearson", action="store_true", help="skip the Pearson-eval leg (second headline metric)")
+    ap.add_argument("--no-pearson", action="store_true", help="skip the evaluation legs (Pearson kernel, eval predict, eval sweep)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the extra legs (contrastive-on, ensemble, eval sweep)")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying whole-step CUDA graphs")
     ap.add_argument("--graph-comm", action="store_true", help="N > 1: capture the steps including their NCCL all-reduces (default: eager steps)")
-    ap.add_argument("--dp", default="staged", choices=["staged", "nvls", "p2p", "allreduce"],
+    ap.add_argument("--dp", default="staged", choices=["staged", "nvls", "p2p", "allreduce", "none"],
                     help="N > 1 gradient path: copy-engine pushes + our fused reduce/Adam/multicast kernel (default), the same kernel reducing "
                          "through NVLS multimem.ld_reduce or peer pointers, or NCCL all-reduce + replicated Adam")
     ap.add_argument("--dp-blocks", type=int, default=0, help="N > 1: CTAs of the sharded step-tail kernel (0 = 6 per SM)")

@@ -50,6 +50,7 @@ def train(p_drop, path, graphs, batches, steps=6, contrastive=False):
     torch.manual_seed(7), np.random.seed(7)
     cfg = FmriEncoderConfig(n_subjects=3, modality_dropout=p_drop, contrastive_enabled=contrastive)
     model = FmriEncoder(DIMS, 200, 25, cfg, **SMALL)
+    model.independent_replica = path == "single"  # the single-process reference run deliberately has no gradient exchange
     module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=1)
     opt, sched = default_optimizer(model.parameters(), total_steps=steps + 2, lr=1e-3, model=model)
     if path == "single":
@@ -117,7 +118,45 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
         if rank == 0:
             print(f"dp train check p_drop={p_drop} contrastive={contrastive} path={path} graphs={graphs}: ranks bit-identical, "
                   f"relative deviation from the all-reduce run {worst:.1e} (two all-reduce runs differ by {floor:.1e}), Adam moments {dev_mom:.1e} ({floor_mom:.1e})", flush=True)
+
+# ---- the Lightning route: BrainModule.configure_optimizers installs the gradient path itself in a multi-rank job;
+# torch DDP around the module is a harmless no-op (its reducer never sees a gradient); a bare model fails loudly
+class _OptimConfig:  # stand-in for modeling_utils' optimizer config (optimizers/base.py:47-48, 84-96)
+    def copy(self):
+        return self
+
+    def build(self, params, total_steps):
+        return torch.optim.Adam(params, lr=1e-3)
+
+
+torch.manual_seed(7), np.random.seed(7)
+model = FmriEncoder(DIMS, 200, 25, FmriEncoderConfig(n_subjects=3, modality_dropout=0.0), **SMALL)
+module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=_OptimConfig(), metrics={}, max_epochs=1)
+model.train()
+try:
+    model(mine[0])
+    raise AssertionError("a training forward without gradient synchronisation must raise in a multi-rank job")
+except algonauts2025_b200.TribeError:
+    pass
+opt = module.configure_optimizers()
+assert module._grad_sync is not None, "configure_optimizers did not install the data-parallel gradient path"
+ddp = torch.nn.parallel.DistributedDataParallel(module, device_ids=[local], find_unused_parameters=True)  # what Lightning's strategy builds
+module.train()
+for i in range(4):  # Lightning's automatic optimisation order
+    opt.zero_grad(set_to_none=True)
+    loss = module.training_step(mine[i % 2], i)
+    loss.backward()
+    module.on_before_optimizer_step(opt)
+    opt.step()
+torch.cuda.synchronize()
+if hasattr(module._grad_sync, "check"):
+    module._grad_sync.check()
+sd = model.state_dict()
+same_on_all_ranks(torch.cat([v.flatten().float() for v in sd.values()]), "BrainModule-installed gradient path")
+same_on_all_ranks(model._engine.flat.bf16.view(torch.uint8), "BrainModule-installed gradient path, shadow")
+del ddp
 if rank == 0:
+    print(f"BrainModule.configure_optimizers route ({type(module._grad_sync).__name__}) under a DDP wrapper: ranks bit-identical", flush=True)
     print("multi-GPU data-parallel training OK", flush=True)
 sys.stdout.flush()
 os._exit(0)  # graphs that captured NCCL work keep the communicator busy at teardown

@@ -114,7 +114,8 @@ class TribeGemm(ctypes.Structure):
                 ("bias_z_stride", c_i64), ("res", c_vp), ("ld_res", c_i64), ("res_row_mod", c_i32), ("res_batched", c_i32), ("rscale", c_vp),
                 ("aux_in", c_vp), ("aux_out", c_vp), ("ld_aux", c_i64), ("rope", c_vp), ("rope_t", c_i32),
                 ("rope_dim", c_i32), ("head_dim", c_i32), ("rope_cols", c_i32), ("rope_sign", c_f32),
-                ("block_n", c_i32), ("splitk_ws", c_vp), ("splitk_ws_bytes", c_i64)]
+                ("block_n", c_i32), ("splitk_ws", c_vp), ("splitk_ws_bytes", c_i64),
+                ("adam_p", c_vp), ("adam_m", c_vp), ("adam_v", c_vp), ("adam_shadow", c_vp), ("adam_hyper", c_vp), ("adam_keep_grad", c_i32)]
 
 
 XGPU_MAX_WORLD, XGPU_SLOTS = 16, 64
@@ -164,6 +165,7 @@ _SIGS = {
     "tribe_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32, c_vp],
     "tribe_adam_step_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp],
     "tribe_adam_hyper": [c_vp, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_vp],
+    "tribe_adam_hyper_batch": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp],
     "tribe_sharded_adam_step": [ctypes.POINTER(TribeShardedAdam), c_vp],
     "tribe_memcpy_async": [c_vp, c_vp, c_i64, c_vp],
     "tribe_debug_spin": [c_i32, c_i32, c_f64, c_i32, c_vp, c_vp],

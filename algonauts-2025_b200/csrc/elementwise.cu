@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tribe_b200.h"
 #include "tribe_internal.h"
@@ -175,76 +176,106 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_warp_kernel(const float* __
 //   dx_in[c] = sqrt(dim) g rnorm (d_xn[c] - x_in[c] rnorm dot) + dy_out[c] * rs[c]
 //   d_rs[c] += dy_out[c] * x_in[c]        d_g += sqrt(dim) * dot
 // Each block walks a strided set of rows and keeps its d_rs column partials in registers (dim <= 4096).
+// Software-pipelined: while row A is reduced / finished, the loads of the block's next row B are already in flight
+// (two register sets, the row loop is unrolled by two), so every block has a row's worth of reads (30 KB at dim 3072)
+// outstanding at all times instead of only between a row's first load and its block reduction.
 template <int NV>
-__global__ void __launch_bounds__(256, NV <= 3 ? 3 : 2) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
-                                                           const float* __restrict__ x_in, const float* __restrict__ rnorm,
-                                                           const float* __restrict__ g, const float* __restrict__ rs,
-                                                           float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
-                                                           float* __restrict__ d_rs, float* __restrict__ d_g, int64_t rows, int dim) {
+struct SubRow {
+  float4 xc[NV], dyv[NV];
+  uint2 dnraw[NV];
+};
+
+template <int NV>
+__device__ __forceinline__ void sub_row_load(SubRow<NV>& r, const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
+                                             const float* __restrict__ x_in, int64_t row, int dim, int nvec) {
+  const float4* xr = reinterpret_cast<const float4*>(x_in + row * dim);
+  const float4* dyr = dy_out ? reinterpret_cast<const float4*>(dy_out + row * dim) : nullptr;
+  const uint2* dnr = d_xn ? reinterpret_cast<const uint2*>(d_xn + row * dim) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * 256;
+    if (v < nvec) {
+      r.xc[i] = __ldcs(xr + v);
+      if (dnr) r.dnraw[i] = __ldcs(dnr + v);
+      if (dyr) r.dyv[i] = __ldcs(dyr + v);
+    }
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void sub_row_finish(const SubRow<NV>& r, bool has_dn, bool has_dy, const float* __restrict__ rnorm,
+                                               const float* __restrict__ rs, float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
+                                               int64_t row, int dim, int nvec, float sqrt_dim, float gval, float4 (&rs_acc)[NV], float& dg_acc,
+                                               float* red) {
+  float4 dn[NV];
+  float dot = 0.f;
+  if (has_dn) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * 256;
+      if (v < nvec) {
+        const float2 a = unpack_bf16x2(r.dnraw[i].x), b = unpack_bf16x2(r.dnraw[i].y);
+        dn[i] = make_float4(a.x, a.y, b.x, b.y);
+        dot += dn[i].x * r.xc[i].x + dn[i].y * r.xc[i].y + dn[i].z * r.xc[i].z + dn[i].w * r.xc[i].w;
+      }
+    }
+  }
+  float coef = 0.f, rn = 0.f;
+  if (has_dn) {
+    rn = __ldg(rnorm + row);
+    dot = block_sum(dot, red) * rn;
+    coef = sqrt_dim * gval * rn;
+    dg_acc += dot;  // identical in every thread; thread 0 publishes
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * 256;
+    if (v < nvec) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_dn) {
+        const float k = rn * dot;
+        o.x = coef * (dn[i].x - r.xc[i].x * k), o.y = coef * (dn[i].y - r.xc[i].y * k);
+        o.z = coef * (dn[i].z - r.xc[i].z * k), o.w = coef * (dn[i].w - r.xc[i].w * k);
+      }
+      if (has_dy) {
+        const float4 dy = r.dyv[i];
+        float4 r4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (rs) r4 = __ldg(reinterpret_cast<const float4*>(rs) + v);
+        o.x += dy.x * r4.x, o.y += dy.y * r4.y, o.z += dy.z * r4.z, o.w += dy.w * r4.w;
+        rs_acc[i].x += dy.x * r.xc[i].x, rs_acc[i].y += dy.y * r.xc[i].y, rs_acc[i].z += dy.z * r.xc[i].z, rs_acc[i].w += dy.w * r.xc[i].w;
+      }
+      if (dx_in) __stcs(reinterpret_cast<float4*>(dx_in + row * dim) + v, o);
+      // the bf16 copy is the A operand of the next dgrad / wgrad GEMM: keep it cacheable
+      if (dx_in_bf16) reinterpret_cast<uint2*>(dx_in_bf16 + row * dim)[v] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __restrict__ dy_out, const __nv_bfloat16* __restrict__ d_xn,
+                                                              const float* __restrict__ x_in, const float* __restrict__ rnorm,
+                                                              const float* __restrict__ g, const float* __restrict__ rs,
+                                                              float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
+                                                              float* __restrict__ d_rs, float* __restrict__ d_g, int64_t rows, int dim) {
   __shared__ float red[32];
   const int nvec = dim >> 2;
   const float sqrt_dim = sqrtf(static_cast<float>(dim));
   const float gval = g ? __ldg(g) : 0.f;
+  const bool has_dn = d_xn != nullptr, has_dy = dy_out != nullptr;
   float4 rs_acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) rs_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float dg_acc = 0.f;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    const float4* xr = reinterpret_cast<const float4*>(x_in + row * dim);
-    const float4* dyr = dy_out ? reinterpret_cast<const float4*>(dy_out + row * dim) : nullptr;
-    const uint2* dnr = d_xn ? reinterpret_cast<const uint2*>(d_xn + row * dim) : nullptr;
-    // issue every global load of this row before the block reduction (memory-level parallelism)
-    float4 xc[NV], dn[NV], dyv[NV];
-    uint2 dnraw[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = threadIdx.x + i * 256;
-      if (v < nvec) {
-        xc[i] = __ldg(xr + v);
-        if (dnr) dnraw[i] = __ldg(dnr + v);
-        if (dyr) dyv[i] = __ldg(dyr + v);
-      }
-    }
-    float dot = 0.f;
-    if (dnr) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int v = threadIdx.x + i * 256;
-        if (v < nvec) {
-          const float2 a = unpack_bf16x2(dnraw[i].x), b = unpack_bf16x2(dnraw[i].y);
-          dn[i] = make_float4(a.x, a.y, b.x, b.y);
-          dot += dn[i].x * xc[i].x + dn[i].y * xc[i].y + dn[i].z * xc[i].z + dn[i].w * xc[i].w;
-        }
-      }
-    }
-    float coef = 0.f, rn = 0.f;
-    if (dnr) {
-      rn = __ldg(rnorm + row);
-      dot = block_sum(dot, red) * rn;
-      coef = sqrt_dim * gval * rn;
-      dg_acc += dot;  // identical in every thread; thread 0 publishes
-    }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = threadIdx.x + i * 256;
-      if (v < nvec) {
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (dnr) {
-          const float k = rn * dot;
-          o.x = coef * (dn[i].x - xc[i].x * k), o.y = coef * (dn[i].y - xc[i].y * k);
-          o.z = coef * (dn[i].z - xc[i].z * k), o.w = coef * (dn[i].w - xc[i].w * k);
-        }
-        if (dyr) {
-          const float4 dy = dyv[i];
-          float4 r4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (rs) r4 = __ldg(reinterpret_cast<const float4*>(rs) + v);
-          o.x += dy.x * r4.x, o.y += dy.y * r4.y, o.z += dy.z * r4.z, o.w += dy.w * r4.w;
-          rs_acc[i].x += dy.x * xc[i].x, rs_acc[i].y += dy.y * xc[i].y, rs_acc[i].z += dy.z * xc[i].z, rs_acc[i].w += dy.w * xc[i].w;
-        }
-        if (dx_in) reinterpret_cast<float4*>(dx_in + row * dim)[v] = o;
-        if (dx_in_bf16) reinterpret_cast<uint2*>(dx_in_bf16 + row * dim)[v] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      }
-    }
+  SubRow<NV> A, B;
+  int64_t row_a = blockIdx.x;
+  if (row_a < rows) sub_row_load<NV>(A, dy_out, d_xn, x_in, row_a, dim, nvec);
+  while (row_a < rows) {
+    const int64_t row_b = row_a + gridDim.x;
+    if (row_b < rows) sub_row_load<NV>(B, dy_out, d_xn, x_in, row_b, dim, nvec);
+    sub_row_finish<NV>(A, has_dn, has_dy, rnorm, rs, dx_in, dx_in_bf16, row_a, dim, nvec, sqrt_dim, gval, rs_acc, dg_acc, red);
+    row_a = row_b + gridDim.x;
+    if (row_a < rows) sub_row_load<NV>(A, dy_out, d_xn, x_in, row_a, dim, nvec);
+    if (row_b < rows) sub_row_finish<NV>(B, has_dn, has_dy, rnorm, rs, dx_in, dx_in_bf16, row_b, dim, nvec, sqrt_dim, gval, rs_acc, dg_acc, red);
   }
   if (d_rs) {
 #pragma unroll
@@ -388,6 +419,43 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, c
     const int64_t c = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
     if (c < cols) atomicAdd(out + c, s);
   }
+}
+
+// bf16 column sums with 16-byte loads: a thread owns 8 adjacent columns (strip = 256 columns per block), 8 row lanes per
+// block, 4 rows in flight per thread (64 B outstanding per thread instead of 32 B with the generic 4-column kernel).
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t rows,
+                                                            int64_t cols, int64_t ld, int64_t rows_per_block) {
+  __shared__ float red[8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 256 + tx * 8;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols) {  // host guarantees cols % 8 == 0
+    auto add = [&](const uint4& q) {
+      const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+      acc[0] += a.x, acc[1] += a.y, acc[2] += b.x, acc[3] += b.y, acc[4] += c.x, acc[5] += c.y, acc[6] += d.x, acc[7] += d.y;
+    };
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldcs(reinterpret_cast<const uint4*>(x + (r + 8 * u) * ld + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add(q[u]);
+    }
+    for (; r < r1; r += 8) add(__ldcs(reinterpret_cast<const uint4*>(x + r * ld + c0)));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  float s_ = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_ += red[k][threadIdx.x];
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (c < cols) atomicAdd(out + c, s_);
 }
 
 // ------------------------------------------------------------------------------------------------ casts / axpby
@@ -584,7 +652,12 @@ extern "C" int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, co
   if (!x_in || rows <= 0 || dim <= 0 || dim % 4 || dim > 4096) return set_error(TRIBE_EINVAL, "sublayer_bwd: bad arguments (dim % 4, dim <= 4096)");
   if (d_xn_bf16 && (!rnorm || !g)) return set_error(TRIBE_EINVAL, "sublayer_bwd: d_xn needs rnorm and g");
   const int nv = static_cast<int>((dim / 4 + 255) / 256);
-  const int grid = grid_for(rows, 2, 148 * (nv <= 3 ? 3 : 2));
+  static const int sub_bpsm = [] {
+    const char* e = getenv("TRIBE_SUBLAYER_BPSM");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 2;
+  }();
+  const int grid = grid_for(rows, 2, 148 * sub_bpsm);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dxn = reinterpret_cast<const __nv_bfloat16*>(d_xn_bf16);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_in_bf16);
@@ -636,6 +709,17 @@ extern "C" int tribe_colsum(const void* x, int32_t x_dtype, const void* y, int32
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * cols, s);
     if (e != cudaSuccess) return set_cuda_error(e, "colsum memset");
+  }
+  if (x_dtype == 2 && !y && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && cols >= 2048) {
+    const int64_t strips8 = (cols + 255) / 256;
+    int64_t chunks8 = (148 * 4 + strips8 - 1) / strips8;
+    if (chunks8 > (rows + 31) / 32) chunks8 = (rows + 31) / 32;
+    if (chunks8 < 1) chunks8 = 1;
+    const int64_t rpb8 = (rows + chunks8 - 1) / chunks8;
+    dim3 grid8(static_cast<unsigned>(strips8), static_cast<unsigned>((rows + rpb8 - 1) / rpb8));
+    colsum_bf16x8_kernel<<<grid8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ld, rpb8);
+    TRIBE_CHECK_LAUNCH("colsum");
+    return TRIBE_OK;
   }
   const int64_t strips = (cols + 127) / 128;
   int64_t chunks = (148 * 4 + strips - 1) / strips;

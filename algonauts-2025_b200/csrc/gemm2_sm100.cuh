@@ -62,20 +62,24 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-template <int BN>
+template <int BN, bool ADAM = false>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = 128 * BK * 2;        // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (220 * 1024) / STAGE_BYTES;
+  // the optimizer-carrying instance trades one ring stage for eight per-warp transpose buffers (adam_tile_coalesced)
+  static constexpr int EPI_STAGE_BYTES = ADAM ? 8 * kAdamStageFloats * 4 : 0;
+  static constexpr int STAGES_RAW = (220 * 1024 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// ADAM: the instance whose epilogue can carry the optimizer step (weight gradients; see adam_chunk) — a separate
+// instantiation so that every other launch keeps the leaner epilogue (148 registers, no spills).
+template <int BN, bool A_MN, bool B_MN, bool ADAM = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) gemm2_bf16_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, ADAM>;
   static_assert(BN == 128 || BN == 256, "2-CTA tiles: BN/2 must be a multiple of 64");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -206,16 +210,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
     const int row_in_half = q * 32 + lane;
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t leader_tempty1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+    float* adam_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES) + (warp - 2) * kAdamStageFloats;
+    // one finished 32-column chunk of this thread's row: optimizer step through the transpose buffer (weight gradients
+    // with an armed optimizer, full chunks) or the generic fused epilogue
+    auto finish_chunk = [&](float (&v)[32], int row, bool row_ok, int col0, long long zoff, const float* bias, int res_row, int pos,
+                            const uint4* pre_aux) {
+      if constexpr (ADAM) {
+        if (p.adam_p && p.vec_ok && col0 + 32 <= p.n) {  // warp-uniform
+          epilogue_math<true>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux);
+          adam_tile_coalesced(p, v, adam_stage, lane, row - lane, col0, zoff);
+          return;
+        }
+      }
+      epilogue_chunk<ADAM, false, ADAM>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux);
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     Work w;
     for (int it = 0; next_work(p, it, w, pair, npairs); ++it) {
       const TileCoord t = decode_tile(p, w.tile, BN, BM2);
+      const long long zoff = static_cast<long long>(t.zo) * p.d_zo + static_cast<long long>(t.zi) * p.d_zi;
+      if constexpr (ADAM) {
+        // The optimizer state of this tile (128 rows x BN columns of p, m, v = 3 x 128 KB per CTA) is requested into L2
+        // NOW, while the tile's MMAs are still running: 384 row segments of 1 KB, one or two bulk prefetches per epilogue
+        // thread.  The epilogue's state loads then are L2 hits instead of HBM round trips (it is latency-bound: each
+        // warp has 6 KB in flight per round).
+        if (p.adam_p && p.vec_ok) {
+          const int ncols = min(BN, p.n - t.n0);
+          const uint32_t bytes = static_cast<uint32_t>(ncols) * 4u;
+          for (int idx = (warp - 2) * 32 + lane; idx < 3 * 128; idx += kEpi2Threads) {
+            const int arr = idx >> 7, prow = t.m0 + static_cast<int>(rank) * 128 + (idx & 127);
+            if (prow < p.m && (bytes & 15u) == 0) {
+              const float* base = arr == 0 ? p.adam_p : (arr == 1 ? p.adam_m : p.adam_v);
+              const float* src = base + zoff + static_cast<long long>(prow) * p.ldd + t.n0;
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = t.m0 + static_cast<int>(rank) * 128 + row_in_half;
       const bool row_ok = row < p.m;
-      const long long zoff = static_cast<long long>(t.zo) * p.d_zo + static_cast<long long>(t.zi) * p.d_zi;
       const float* bias = p.bias;
       if (bias && p.bias_gathered) bias += static_cast<long long>(batch_coord(p.b_gather, t.z, p.b_zdiv)) * p.bias_z_stride;
       const int res_row = p.res_row_mod ? row % p.res_row_mod : row;
@@ -226,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
       if (!w.partial) {
         // GELU' epilogue (dgrad of FF2): the bf16 pre-activations of the NEXT chunk are requested before this chunk's
         // accumulator is read, one chunk ahead of their use
-        const bool pre = p.epilogue == TRIBE_EPI_GELU_BWD && p.vec_ok && row_ok;
+        const bool pre = !ADAM && p.epilogue == TRIBE_EPI_GELU_BWD && p.vec_ok && row_ok;  // (never a weight gradient)
         uint4 ax_cur[4], ax_nxt[4];
         auto ld_aux = [&](int c, uint4 (&a)[4]) {
           const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + static_cast<long long>(row) * p.ld_aux + t.n0 + c * 32);
@@ -246,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-          epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos, have ? ax_cur : nullptr);
+          finish_chunk(v, row, row_ok, col0, zoff, bias, res_row, pos, have ? ax_cur : nullptr);
 #pragma unroll
           for (int j = 0; j < 4; ++j) ax_cur[j] = ax_nxt[j];
         }
@@ -298,7 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-          epilogue_chunk(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
+          finish_chunk(v, row, row_ok, col0, zoff, bias, res_row, pos, nullptr);
         }
         epi2_bar_sync();
         if (warp == 2 && lane == 0) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "adam_math.cuh"
 #include "ptx_sm100.cuh"
 #include "tribe_b200.h"
 
@@ -50,6 +51,13 @@ struct alignas(64) GemmKParams {
   int full_tiles, tail_units, split, kb_per;
   float* ws;
   int* counters;
+  // optimizer step fused into the epilogue (weight gradients): same element offsets as D
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  __nv_bfloat16* adam_shadow;
+  const float* adam_hyper;
+  int adam_keep_grad;
 };
 
 template <int BN>
@@ -139,12 +147,68 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Adam step on 32 consecutive elements of one weight row whose finished gradient sits in registers (wgrad GEMMs):
+// 12 B read + 14 B written per parameter, all streaming (nothing is re-read before the next forward pass); the
+// gradient itself never has to reach memory.  A thread owns a whole 128-byte line of each state array per chunk.
+template <bool VEC = true>
+__device__ __forceinline__ void adam_chunk(const GemmKParams& p, const float (&g)[32], long long off, int nvalid, bool full) {
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.adam_hyper));
+  const float2 h1 = __ldg(reinterpret_cast<const float2*>(p.adam_hyper + 4));
+  const float beta1 = h0.x, beta2 = h0.y, step_size = h0.z, inv_bc2_sqrt = h0.w, eps = h1.x, wd = h1.y;
+  float* pp = p.adam_p + off;
+  float* pm = p.adam_m + off;
+  float* pv = p.adam_v + off;
+  __nv_bfloat16* ps = p.adam_shadow ? p.adam_shadow + off : nullptr;
+  if (VEC && full) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 P[4], M[4], V[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        P[j] = __ldcs(reinterpret_cast<const float4*>(pp) + half * 4 + j);
+        M[j] = __ldcs(reinterpret_cast<const float4*>(pm) + half * 4 + j);
+        V[j] = __ldcs(reinterpret_cast<const float4*>(pv) + half * 4 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = half * 16 + j * 4;
+        adam_one(P[j].x, g[c], M[j].x, V[j].x, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+        adam_one(P[j].y, g[c + 1], M[j].y, V[j].y, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+        adam_one(P[j].z, g[c + 2], M[j].z, V[j].z, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+        adam_one(P[j].w, g[c + 3], M[j].w, V[j].w, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+        __stcs(reinterpret_cast<float4*>(pp) + half * 4 + j, P[j]);
+        __stcs(reinterpret_cast<float4*>(pm) + half * 4 + j, M[j]);
+        __stcs(reinterpret_cast<float4*>(pv) + half * 4 + j, V[j]);
+      }
+      if (ps) {
+#pragma unroll
+        for (int j = 0; j < 4; j += 2)
+          __stcs(reinterpret_cast<uint4*>(ps) + half * 2 + (j >> 1),
+                 make_uint4(pack2(P[j].x, P[j].y), pack2(P[j].z, P[j].w), pack2(P[j + 1].x, P[j + 1].y), pack2(P[j + 1].z, P[j + 1].w)));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {  // fully unrolled: g[] must stay in registers
+      if (j < nvalid) {
+        float P = pp[j], M = pm[j], V = pv[j];
+        adam_one(P, g[j], M, V, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+        pp[j] = P, pm[j] = M, pv[j] = V;
+        if (ps) ps[j] = __float2bfloat16(P);
+      }
+    }
+  }
+}
+
 // Fused epilogue of 32 consecutive columns of one output row (v already scaled by alpha).
 // pre_aux (optional): the chunk's 32 bf16 aux_in values (GELU' operand) already loaded by the caller — issued BEFORE the
 // TMEM load so that the global-load latency is not exposed in the epilogue (ncu: 15 % of the dgrad-FF2 samples sat on the
 // first use of this load).
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
-                                               const float* bias, int res_row, int pos, const uint4* pre_aux = nullptr) {
+// Part 1: everything that changes the VALUES of the chunk (bias, activation, residual, rotary); aux_out side store of GELU.
+// LEAN: only what a weight-gradient GEMM can ask for (bias, RESIDUAL accumulation) is compiled in.
+template <bool LEAN = false>
+__device__ __forceinline__ void epilogue_math(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
+                                              const float* bias, int res_row, int pos, const uint4* pre_aux = nullptr) {
   const int nvalid = min(32, p.n - col0);
   const bool full = (nvalid == 32) && p.vec_ok;
 
@@ -162,7 +226,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[
     }
   }
 
-  if (p.epilogue == TRIBE_EPI_GELU) {
+  if (!LEAN && p.epilogue == TRIBE_EPI_GELU) {
     if (row_ok) {
       __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
       if (full) {
@@ -177,7 +241,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.epilogue == TRIBE_EPI_GELU_BWD) {
+  } else if (!LEAN && p.epilogue == TRIBE_EPI_GELU_BWD) {
     if (row_ok) {
       const __nv_bfloat16* ap = p.aux_in + static_cast<long long>(row) * p.ld_aux + col0;
       if (full) {
@@ -215,7 +279,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[
           if (j < nvalid) v[j] += __ldg(rp + j) * (p.rscale ? __ldg(p.rscale + col0 + j) : 1.0f);
       }
     }
-  } else if (p.epilogue == TRIBE_EPI_ROPE) {
+  } else if (!LEAN && p.epilogue == TRIBE_EPI_ROPE) {
     const int cih = col0 % p.head_dim;  // chunk-uniform: head_dim, rope_dim are multiples of 32
     if (col0 < p.rope_cols && cih < p.rope_dim) {
       const float2* tab = p.rope + static_cast<long long>(pos) * (p.rope_dim >> 1) + (cih >> 1);
@@ -232,7 +296,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[
     }
   }
 
+}
+
+// Part 2: where the chunk goes (optimizer step and / or the D store).
+// ADAM_VEC = false: the caller handles full chunks itself (adam_tile_coalesced) and only ragged ones arrive here.
+template <bool ADAM = true, bool ADAM_VEC = true>
+__device__ __forceinline__ void epilogue_store(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff) {
+  const int nvalid = min(32, p.n - col0);
+  const bool full = (nvalid == 32) && p.vec_ok;
   if (!row_ok) return;
+  if constexpr (ADAM) {
+    if (p.adam_p) {  // host side guarantees d_f32 && !d_transposed
+      adam_chunk<ADAM_VEC>(p, v, zoff + static_cast<long long>(row) * p.ldd + col0, nvalid, full);
+      if (!p.adam_keep_grad) return;
+    }
+  }
   if (p.d_transposed) {
     if (p.d_f32) {
       float* dp = reinterpret_cast<float*>(p.d) + zoff + static_cast<long long>(col0) * p.ldd + row;
@@ -265,6 +343,65 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <bool ADAM = true, bool ADAM_VEC = true, bool LEAN = false>
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
+                                               const float* bias, int res_row, int pos, const uint4* pre_aux = nullptr) {
+  epilogue_math<LEAN>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux);
+  epilogue_store<ADAM, ADAM_VEC>(p, v, row, row_ok, col0, zoff);
+}
+
+// Adam step on a warp's 32-row x 32-column gradient tile with COALESCED state traffic: the tile (thread = row after
+// tcgen05.ld) goes through a padded shared-memory buffer (36-float rows: conflict-free 16-byte writes by row and reads by
+// quarter-row), after which lane l owns columns 4*(l%8)..+3 of rows l/8, l/8 + 4, ...: every warp-wide access covers four
+// full 128-byte lines of p / m / v (row-per-thread accesses touch 32 lines for the same bytes and ran the fused step at
+// a third of the stand-alone kernel's bandwidth).  Four row groups (12 x 16-byte loads per lane) are in flight at once.
+constexpr int kAdamStageRow = 36;
+constexpr int kAdamStageFloats = 32 * kAdamStageRow;
+__device__ __forceinline__ void adam_tile_coalesced(const GemmKParams& p, const float (&g)[32], float* stage, int lane, int row0, int col0,
+                                                    long long zoff) {
+  __syncwarp();  // the previous chunk's reads of `stage` are complete
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * kAdamStageRow + 4 * j) = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+  __syncwarp();
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.adam_hyper));
+  const float2 h1 = __ldg(reinterpret_cast<const float2*>(p.adam_hyper + 4));
+  const float beta1 = h0.x, beta2 = h0.y, step_size = h0.z, inv_bc2_sqrt = h0.w, eps = h1.x, wd = h1.y;
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it0 = 0; it0 < 8; it0 += 4) {
+    float4 P[4], M[4], V[4];
+    long long off[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = (it0 + u) * 4 + sub;
+      ok[u] = row0 + r < p.m;
+      off[u] = zoff + static_cast<long long>(row0 + r) * p.ldd + col0 + c4;
+      if (ok[u]) {
+        P[u] = __ldcs(reinterpret_cast<const float4*>(p.adam_p + off[u]));
+        M[u] = __ldcs(reinterpret_cast<const float4*>(p.adam_m + off[u]));
+        V[u] = __ldcs(reinterpret_cast<const float4*>(p.adam_v + off[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const int r = (it0 + u) * 4 + sub;
+      const float4 G = *reinterpret_cast<const float4*>(stage + r * kAdamStageRow + c4);
+      adam_one(P[u].x, G.x, M[u].x, V[u].x, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+      adam_one(P[u].y, G.y, M[u].y, V[u].y, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+      adam_one(P[u].z, G.z, M[u].z, V[u].z, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+      adam_one(P[u].w, G.w, M[u].w, V[u].w, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
+      __stcs(reinterpret_cast<float4*>(p.adam_p + off[u]), P[u]);
+      __stcs(reinterpret_cast<float4*>(p.adam_m + off[u]), M[u]);
+      __stcs(reinterpret_cast<float4*>(p.adam_v + off[u]), V[u]);
+      if (p.adam_shadow) __stcs(reinterpret_cast<uint2*>(p.adam_shadow + off[u]), make_uint2(pack2(P[u].x, P[u].y), pack2(P[u].z, P[u].w)));
+      if (p.adam_keep_grad) __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.d) + off[u]), G);
     }
   }
 }

@@ -415,11 +415,11 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
   return TRIBE_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool ADAM = false>
 static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, ADAM>;
   static bool attr_set = false;
-  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, ADAM>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm2)");
@@ -437,6 +437,7 @@ static int dispatch_major2(const GemmKParams& kp, int grid, bool a_mn, bool b_mn
   if (!a_mn && !b_mn) return launch_gemm2<BN, false, false>(kp, grid, s);
   if (a_mn && !b_mn) return launch_gemm2<BN, true, false>(kp, grid, s);
   if (!a_mn && b_mn) return launch_gemm2<BN, false, true>(kp, grid, s);
+  if (kp.adam_p) return launch_gemm2<BN, true, true, true>(kp, grid, s);
   return launch_gemm2<BN, true, true>(kp, grid, s);
 }
 
@@ -502,7 +503,8 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
     const char* e = getenv("TRIBE_GEMM_2CTA");
     return e ? atoi(e) : 1;
   }();
-  const bool use2 = allow_2cta && bn == 256 && !g->kgroup && g->m >= 1024 && (num_sms() % 2 == 0);
+  bool use2 = allow_2cta && bn == 256 && !g->kgroup && g->m >= 1024 && (num_sms() % 2 == 0);
+  if (use2 && g->adam_p && !(a_mn && b_mn)) use2 = false;  // only the wgrad form (both operands MN-major) has a 2-CTA Adam instance
   int rc = encode_operand(g->a, a_mn ? BK : BM, &kp.tma);
   if (rc) return rc;
   rc = encode_operand(g->b, b_mn ? BK : (use2 ? bn / 2 : bn), &kp.tmb);
@@ -541,6 +543,16 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   if (g->aux_in) vec = vec && al16(g->aux_in) && (g->ld_aux * 2) % 16 == 0;
   if (g->aux_out) vec = vec && al16(g->aux_out) && (g->ld_aux * 2) % 16 == 0;
   if (g->rope && !al16(g->rope)) return set_error(TRIBE_EINVAL, "gemm: rope table must be 16-byte aligned");
+  if (g->adam_p) {
+    if (!g->adam_m || !g->adam_v || !g->adam_hyper) return set_error(TRIBE_EINVAL, "gemm: fused Adam needs adam_m, adam_v and adam_hyper");
+    if (!g->d_f32 || g->d_transposed) return set_error(TRIBE_EINVAL, "gemm: fused Adam needs a row-major fp32 output");
+    if (g->epilogue != TRIBE_EPI_STORE && g->epilogue != TRIBE_EPI_RESIDUAL)
+      return set_error(TRIBE_EINVAL, "gemm: fused Adam combines with the STORE and RESIDUAL (accumulate) epilogues only");
+    if (!al16(g->adam_hyper)) return set_error(TRIBE_EINVAL, "gemm: adam_hyper must be 16-byte aligned");
+    vec = vec && al16(g->adam_p) && al16(g->adam_m) && al16(g->adam_v) && al16(g->adam_shadow);
+    kp.adam_p = g->adam_p, kp.adam_m = g->adam_m, kp.adam_v = g->adam_v;
+    kp.adam_shadow = reinterpret_cast<__nv_bfloat16*>(g->adam_shadow), kp.adam_hyper = g->adam_hyper, kp.adam_keep_grad = g->adam_keep_grad;
+  }
   kp.vec_ok = vec ? 1 : 0;
 
   // ---- schedule: whole tiles round-robin; the ragged last wave is split along K when a workspace is provided

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "adam_math.cuh"
 #include "tribe_b200.h"
 #include "tribe_internal.h"
 
@@ -14,15 +15,6 @@ namespace tribe {
 __device__ __forceinline__ uint32_t opt_pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
-}
-
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float beta1, float beta2, float step_size, float inv_bc2_sqrt,
-                                         float eps, float wd) {
-  if (wd != 0.f) g = fmaf(wd, p, g);
-  m = m + (g - m) * (1.0f - beta1);           // exp_avg.lerp_(grad, 1 - beta1)
-  v = beta2 * v + (1.0f - beta2) * g * g;     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
-  p = p - step_size * (m / denom);
 }
 
 // hyper == nullptr: scalars come from the launch arguments; otherwise from 6 floats in device memory
@@ -60,6 +52,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 __global__ void set_floats_kernel(float* __restrict__ dst, int n, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
   const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
   if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
+}
+
+constexpr int kHyperBatch = 96;
+struct HyperBatch {
+  int32_t slot[kHyperBatch];
+  float val[kHyperBatch][6];
+};
+// one launch refreshes up to 96 hyper-parameter blocks (block i of `base` = 8 floats at base + 8 * slot[i])
+__global__ void set_hyper_batch_kernel(float* __restrict__ base, const __grid_constant__ HyperBatch hb, int n) {
+  const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+  if (i < n && j < 6) base[static_cast<int64_t>(hb.slot[i]) * 8 + j] = hb.val[i][j];
 }
 
 }  // namespace tribe
@@ -104,5 +107,30 @@ extern "C" int tribe_adam_hyper(float* hyper_dev, double lr, double beta1, doubl
                                                                         static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)),
                                                                         static_cast<float>(eps), static_cast<float>(weight_decay), 0.f, 0.f);
   TRIBE_CHECK_LAUNCH("adam_hyper");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_adam_hyper_batch(float* hyper_base, const int32_t* slots_host, const int64_t* steps_host, const double* lr_host,
+                                      const double* beta1_host, const double* beta2_host, const double* eps_host, const double* wd_host, int32_t n,
+                                      void* stream) {
+  using namespace tribe;
+  if (!hyper_base || n < 0 || (n > 0 && (!slots_host || !steps_host || !lr_host || !beta1_host || !beta2_host || !eps_host || !wd_host)))
+    return set_error(TRIBE_EINVAL, "adam_hyper_batch: bad arguments");
+  for (int32_t base = 0; base < n; base += kHyperBatch) {
+    const int cnt = n - base < kHyperBatch ? n - base : kHyperBatch;
+    HyperBatch hb;
+    for (int i = 0; i < cnt; ++i) {
+      const int q = base + i;
+      if (steps_host[q] <= 0 || slots_host[q] < 0) return set_error(TRIBE_EINVAL, "adam_hyper_batch: step must be >= 1 and slot >= 0");
+      const double bc1 = 1.0 - pow(beta1_host[q], static_cast<double>(steps_host[q]));
+      const double bc2 = 1.0 - pow(beta2_host[q], static_cast<double>(steps_host[q]));
+      hb.slot[i] = slots_host[q];
+      hb.val[i][0] = static_cast<float>(beta1_host[q]), hb.val[i][1] = static_cast<float>(beta2_host[q]);
+      hb.val[i][2] = static_cast<float>(lr_host[q] / bc1), hb.val[i][3] = static_cast<float>(1.0 / sqrt(bc2));
+      hb.val[i][4] = static_cast<float>(eps_host[q]), hb.val[i][5] = static_cast<float>(wd_host[q]);
+    }
+    set_hyper_batch_kernel<<<1, kHyperBatch * 8, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hyper_base, hb, cnt);
+    TRIBE_CHECK_LAUNCH("adam_hyper_batch");
+  }
   return TRIBE_OK;
 }

@@ -28,6 +28,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "adam_math.cuh"
 #include "tribe_b200.h"
 #include "tribe_internal.h"
 
@@ -119,15 +120,11 @@ __device__ __forceinline__ uint32_t xg_pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// identical arithmetic to adam_kernel (optim.cu): the single-GPU and the sharded step produce the same bits from the
-// same gradient
+// identical arithmetic to adam_kernel (optim.cu) — the shared adam_math.cuh: the single-GPU and the sharded step produce
+// the same bits from the same gradient
 __device__ __forceinline__ void xg_adam_one(float& p, float g, float& m, float& v, float beta1, float beta2, float step_size, float inv_bc2_sqrt,
                                             float eps, float wd) {
-  if (wd != 0.f) g = fmaf(wd, p, g);
-  m = m + (g - m) * (1.0f - beta1);
-  v = beta2 * v + (1.0f - beta2) * g * g;
-  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
-  p = p - step_size * (m / denom);
+  adam_one(p, g, m, v, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
 }
 
 // GMC: gradients through multimem.ld_reduce (in-switch sum) vs a table of `world` addresses summed in rank order (peer

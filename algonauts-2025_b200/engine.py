@@ -192,6 +192,12 @@ class Plan:
         self.x_input = False    # transformer_forward entry: encoder input given as a tensor
         self.training = False
         self.out = None         # optional preallocated (B, O, T') fp32 output (evaluation sweeps write predictions in place)
+        self.awaiting = None    # the Engine that counts this plan among its grad-enabled forwards awaiting a backward
+
+    def settle(self):
+        eng, self.awaiting = self.awaiting, None
+        if eng is not None:
+            eng._grad_plans -= 1
 
     def __del__(self):
         # a grad-enabled forward whose backward never runs (main.py:349 warm-up call, a skipped loss, an exception):
@@ -199,6 +205,8 @@ class Plan:
         ws = self.__dict__.get("ws")
         if ws is not None:
             ws.in_use = False
+        if self.__dict__.get("awaiting") is not None:
+            self.settle()
 
 
 class Engine:
@@ -216,6 +224,10 @@ class Engine:
         self._rope = {}
         self.proj_in = {}
         self.comm = None  # set by parallel.GradAllReduce for data-parallel training
+        # optimizer-in-backward (optim.TribeAdam.arm_fused_backward): the LAST backward pass of a step applies the Adam
+        # update of every GEMM weight inside its wgrad epilogue
+        self.fused_opt = None
+        self._grad_plans = 0  # grad-enabled forward passes whose backward has not run yet
 
     # ------------------------------------------------------------------------------------------------ parameters
     def materialize(self, device):
@@ -449,12 +461,18 @@ class Engine:
             raise TribeError(f"parameter {name} carries a foreign .grad tensor; use zero_grad(set_to_none=True)")
         return g
 
-    def _wgrad(self, a_op, b_op, name, m_, n_, k_, acc, out=None, **kw):
-        g = out if out is not None else self.flat.gview(name)
+    def _wgrad(self, a_op, b_op, name, m_, n_, k_, acc, out=None, fused=None, **kw):
+        """Weight gradient of ``name`` (or of the adjacent parameters ``name`` lists, written through ``out``).  With
+        ``fused`` (the armed optimizer, last backward pass of the step) the Adam update of those parameters happens in the
+        GEMM epilogue: the gradient is not stored, ``p.grad`` stays None and ``optimizer.step()`` skips them."""
+        names = [name] if isinstance(name, str) else list(name)
+        g = out if out is not None else self.flat.gview(names[0])
+        adam = fused.fused_wgrad_args(names) if fused is not None else None
         if acc:
-            ops.gemm(a_op, b_op, g, m_, n_, k_, ldd=n_, epilogue=ops.EPI_RESIDUAL, res=g, ld_res=n_, res_batched=True, **kw)
+            ops.gemm(a_op, b_op, g, m_, n_, k_, ldd=n_, epilogue=ops.EPI_RESIDUAL, res=g, ld_res=n_, res_batched=True, adam=adam, **kw)
         else:
-            ops.gemm(a_op, b_op, g, m_, n_, k_, ldd=n_, **kw)
+            ops.gemm(a_op, b_op, g, m_, n_, k_, ldd=n_, adam=adam, **kw)
+        return adam is not None
 
     def backward(self, plan: Plan, grad_out: torch.Tensor, want_dx_in=False):
         """Writes parameter gradients straight into the flat gradient buffer (``p.grad`` become views of it; a
@@ -470,11 +488,23 @@ class Engine:
         fl.ensure_grad()
         touched = []
         acc = {}
+        last_pass = self._grad_plans <= 1  # no other grad-enabled forward is still waiting for its backward
+        plan.settle()
+        fo = self.fused_opt if (last_pass and self.comm is None and plan.training) else None
 
         def tgt(name):
             g = self._grad_target(name, acc)
             touched.append(name)
             return g
+
+        def wgrad(a_op, b_op, name, m_, n_, k_, **kw):
+            names = [name] if isinstance(name, str) else list(name)
+            for n in names:
+                tgt(n)
+            if self._wgrad(a_op, b_op, names, m_, n_, k_, acc[names[0]], fused=fo, **kw):
+                for n in names:  # updated in the epilogue: no gradient to publish (optimizer.step() skips grad-less parameters)
+                    touched.remove(n)
+                    fl.params[n].grad = None
 
         def publish():
             # hand the finished gradients to autograd's view of the parameters (p.grad = view of the flat buffer);
@@ -508,11 +538,10 @@ class Engine:
             w_op = ops.Operand(w16, inner=O, rows=H, row_stride=O, batch=S, batch_stride=H * O, gather=plan.subjects)
             ops.gemm(dy_op, w_op, d_xp, Tq, H, O, ldd=H, batch=B, d_zo=Tq * H)
             # grouped wgrad: dW[s] (H, O) = sum_{b: s_b = s} xp[b]^T dy[b]
-            gW = tgt("predictor.weights")
             xa = ops.Operand(xp, inner=H, rows=Tq, row_stride=H, batch=B, batch_stride=Tq * H, mn_major=True)
             dyb = ops.Operand(dyT, inner=O, rows=Tq, row_stride=O, batch=B, batch_stride=Tq * O, mn_major=True)
-            self._wgrad(xa, dyb, "predictor.weights", H, O, Tq, acc["predictor.weights"], out=gW.view(S * H, O), batch=S, d_zo=H * O,
-                        kgroup=plan.subjects)
+            wgrad(xa, dyb, "predictor.weights", H, O, Tq, out=fl.gview("predictor.weights").view(S * H, O), batch=S, d_zo=H * O,
+                  kgroup=plan.subjects)
             if m.predictor.bias is not None:
                 gB = tgt("predictor.bias")
                 if not acc["predictor.bias"]:
@@ -545,13 +574,11 @@ class Engine:
             w2, w1 = self._w16(f"{f}.1.ff.2.weight"), self._w16(f"{f}.1.ff.0.0.weight")
             # d_hpre = (dx @ W2) * gelu'(hpre)          W2 (H, F): MN-major B (N = F contiguous, K = H rows)
             ops.gemm(ops.kmajor(dxb_cur), ops.mnmajor(w2), ws.dh, M, F, H, ldd=F, epilogue=ops.EPI_GELU_BWD, aux_in=ws.hpre[l], ld_aux=F)
-            tgt(f"{f}.1.ff.2.weight")
-            self._wgrad(ops.mnmajor(dxb_cur), ops.mnmajor(ws.hact[l]), f"{f}.1.ff.2.weight", H, F, M, acc[f"{f}.1.ff.2.weight"])
+            wgrad(ops.mnmajor(dxb_cur), ops.mnmajor(ws.hact[l]), f"{f}.1.ff.2.weight", H, F, M)
             ops.colsum(dx_cur, gs[f"{f}.1.ff.2.bias"], accumulate=acc[f"{f}.1.ff.2.bias"])
             # d_xn = d_hpre @ W1                         W1 (F, H): MN-major B (N = H contiguous, K = F rows)
             ops.gemm(ops.kmajor(ws.dh), ops.mnmajor(w1), ws.dtmp, M, H, F, ldd=H)
-            tgt(f"{f}.1.ff.0.0.weight")
-            self._wgrad(ops.mnmajor(ws.dh), ops.mnmajor(ws.xn[iff]), f"{f}.1.ff.0.0.weight", F, H, M, acc[f"{f}.1.ff.0.0.weight"])
+            wgrad(ops.mnmajor(ws.dh), ops.mnmajor(ws.xn[iff]), f"{f}.1.ff.0.0.weight", F, H, M)
             ops.colsum(ws.dh, gs[f"{f}.1.ff.0.0.bias"], accumulate=acc[f"{f}.1.ff.0.0.bias"])
             ops.sublayer_bwd(dx_cur, ws.dtmp, ws.xs[iff], ws.rn[iff], self._p(f"{f}.0.0.g"), self._p(f"{f}.2.residual_scale"),
                              dx_nxt, dxb_nxt, gs[f"{f}.2.residual_scale"], gs[f"{f}.0.0.g"])
@@ -560,8 +587,7 @@ class Engine:
             wo = self._w16(f"{a}.1.to_out.weight")
             d_attn = ws.dtmp
             ops.gemm(ops.kmajor(dxb_cur), ops.mnmajor(wo), d_attn, M, H, H, ldd=H)
-            tgt(f"{a}.1.to_out.weight")
-            self._wgrad(ops.mnmajor(dxb_cur), ops.mnmajor(ws.attn[l]), f"{a}.1.to_out.weight", H, H, M, acc[f"{a}.1.to_out.weight"])
+            wgrad(ops.mnmajor(dxb_cur), ops.mnmajor(ws.attn[l]), f"{a}.1.to_out.weight", H, H, M)
             qkv = ws.qkv[l]
             # dP = dO V^T  (per (b, h); both K-major over head dims)
             if ops.attn_fusable(T, dh):
@@ -590,12 +616,9 @@ class Engine:
             # d_xn = dqkv @ Wqkv ;  dWqkv = dqkv^T xn
             wqkv = self._wqkv16(a)
             ops.gemm(ops.kmajor(ws.dqkv), ops.mnmajor(wqkv), ws.dtmp, M, H, 3 * H, ldd=H)
-            for n in ("to_q", "to_k", "to_v"):
-                tgt(f"{a}.1.{n}.weight")
             o = fl.offsets[f"{a}.1.to_q.weight"]
             gqkv = fl.grad[o: o + 3 * H * H].view(3 * H, H)
-            acc_qkv = acc[f"{a}.1.to_q.weight"]
-            self._wgrad(ops.mnmajor(ws.dqkv), ops.mnmajor(ws.xn[ia]), None, 3 * H, H, M, acc_qkv, out=gqkv)
+            wgrad(ops.mnmajor(ws.dqkv), ops.mnmajor(ws.xn[ia]), [f"{a}.1.{n}.weight" for n in ("to_q", "to_k", "to_v")], 3 * H, H, M, out=gqkv)
             ops.sublayer_bwd(dx_cur, ws.dtmp, ws.xs[ia], ws.rn[ia], self._p(f"{a}.0.0.g"), self._p(f"{a}.2.residual_scale"),
                              dx_nxt, dxb_nxt, gs[f"{a}.2.residual_scale"], gs[f"{a}.0.0.g"])
             dx_cur, dx_nxt, dxb_cur, dxb_nxt = dx_nxt, dx_cur, dxb_nxt, dxb_cur
@@ -622,11 +645,10 @@ class Engine:
                     continue
                 col = i * width if cat else 0
                 wn, bn = f"projectors.{mod}.weight", f"projectors.{mod}.bias"
-                tgt(wn)
                 gb = tgt(bn)
                 K = self.proj_in[mod]
                 a_op = ops.Operand(dxb_cur, inner=H, rows=M, row_stride=H, mn_major=True, inner_off=col)
-                self._wgrad(a_op, ops.mnmajor(ws.feat[mod]), wn, width, K, M, acc[wn])
+                wgrad(a_op, ops.mnmajor(ws.feat[mod]), wn, width, K, M)
                 ops.colsum(dx_cur[:, col: col + width], gb, accumulate=acc[bn])
         publish()
         if self.comm is not None:

@@ -415,7 +415,10 @@ class FmriEncoder(nn.Module):
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             self._check_gradient_sync()
-            return _Fn.apply(self._anchor(), x_in, eng, plan, data)
+            out = _Fn.apply(self._anchor(), x_in, eng, plan, data)
+            plan.awaiting = eng  # counted until its backward runs or autograd drops the graph (engine.Plan.settle)
+            eng._grad_plans += 1
+            return out
         out = eng.forward(plan, data, x_in)
         eng.release(plan)
         return out

@@ -92,8 +92,11 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
          res: torch.Tensor | None = None, ld_res: int = 0, res_row_mod: int = 0, res_batched: bool = False, rscale: torch.Tensor | None = None,
          aux_in: torch.Tensor | None = None, aux_out: torch.Tensor | None = None, ld_aux: int = 0,
          rope: torch.Tensor | None = None, rope_t: int = 0, rope_dim: int = 0, head_dim: int = 0, rope_cols: int = 0,
-         rope_sign: float = 1.0, kgroup: torch.Tensor | None = None, block_n: int = 0, probe=None) -> None:
-    """D[z] = epilogue(alpha * A[z] @ B[z]^T) on the tcgen05 GEMM.  ``out`` is bf16 or fp32."""
+         rope_sign: float = 1.0, kgroup: torch.Tensor | None = None, block_n: int = 0, probe=None, adam=None) -> None:
+    """D[z] = epilogue(alpha * A[z] @ B[z]^T) on the tcgen05 GEMM.  ``out`` is bf16 or fp32.
+    ``adam``: optional ``(p_ptr, m_ptr, v_ptr, shadow_ptr, hyper_ptr, keep_grad)`` — device addresses of the fp32 master
+    weights / Adam moments / bf16 shadow laid out like ``out`` (offset ``d_off`` included by the caller) and of the device
+    hyper-parameter block: the epilogue applies the optimizer step to the finished gradient tile (wgrad GEMMs)."""
     if out.dtype not in (torch.bfloat16, torch.float32) or not out.is_cuda:
         raise TribeError("gemm output must be a CUDA bf16/fp32 tensor")
     g = TribeGemm()
@@ -115,6 +118,9 @@ def gemm(a: Operand, b: Operand, out: torch.Tensor, m: int, n: int, k: int, *, l
     g.ld_res, g.res_row_mod, g.res_batched, g.ld_aux = ld_res, res_row_mod, int(res_batched), ld_aux
     g.rope_t, g.rope_dim, g.head_dim, g.rope_cols, g.rope_sign = rope_t, rope_dim, head_dim, rope_cols, rope_sign
     g.block_n = block_n
+    if adam is not None:
+        g.adam_p, g.adam_m, g.adam_v, g.adam_shadow, g.adam_hyper, g.adam_keep_grad = (int(adam[0]), int(adam[1]), int(adam[2]), int(adam[3]) or None,
+                                                                                       int(adam[4]), int(bool(adam[5])))
     if SPLITK:
         ws = _splitk_workspace(out.device)
         g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), ws.numel()

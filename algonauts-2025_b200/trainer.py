@@ -4,6 +4,7 @@ installed here): Lightning's *automatic optimisation* for one batch is
 gradient clipping / accumulation and precision 32-true (reference: algonauts2025/main.py:388-404)."""
 from __future__ import annotations
 
+import os
 import typing as tp
 
 import torch
@@ -32,12 +33,21 @@ class MiniTrainer:
     ``overlap_optimizer``: run the optimizer layer by layer behind the backward pass (``parallel.StepOverlap``)."""
 
     def __init__(self, module, optimizer, scheduler=None, grad_sync=None, use_graphs: bool = False, graph_collectives: bool = True,
-                 overlap_optimizer: bool = False):
+                 overlap_optimizer: bool = False, fuse_optimizer: bool | None = None):
         self.module, self.optimizer, self.scheduler, self.grad_sync = module, optimizer, scheduler, grad_sync
         self.global_step = 0
         self.graph_collectives = graph_collectives
         self._graphed = None
         model = getattr(module, "model", None)
+        # optimizer-in-backward (optim.TribeAdam.fuse_backward): single-GPU / ensemble-member steps have nothing between
+        # the weight gradients and Adam, so the update can ride in the wgrad GEMM epilogues.  Measured on B200 this is a
+        # wash (profiles/r02_adam_in_wgrad_ab.txt: the wgrad GEMMs already use ~80 % of an SM's L2 read bandwidth, the
+        # state traffic lengthens them by what the separate pass cost), so it is opt-in (or TRIBE_FUSED_ADAM=1).
+        if fuse_optimizer is None:
+            fuse_optimizer = os.environ.get("TRIBE_FUSED_ADAM", "0") == "1"
+        self.fuse_optimizer = bool(fuse_optimizer) and grad_sync is None and not overlap_optimizer and hasattr(optimizer, "arm_fused_backward")
+        if hasattr(optimizer, "arm_fused_backward"):
+            optimizer.fuse_backward = self.fuse_optimizer
         if overlap_optimizer and model is not None and hasattr(optimizer, "step_bucket"):
             # each encoder layer's Adam step runs on a side stream as soon as that layer's gradients are final
             # (after their all-reduce in data-parallel runs), hidden behind the backward of the earlier layers
@@ -57,6 +67,8 @@ class MiniTrainer:
     def run_step_body(self, batch) -> torch.Tensor:
         """Device work of one automatic-optimisation step (everything a CUDA graph may capture)."""
         self.optimizer.zero_grad(set_to_none=True)
+        if self.fuse_optimizer:
+            self.optimizer.arm_fused_backward()
         if self.grad_sync is not None:
             self.grad_sync.begin_step()
         loss = self.module.training_step(batch, self.global_step)

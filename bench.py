@@ -354,7 +354,8 @@ def train_leg(args, rank, world, local, *, contrastive: bool, dp: str, seed: int
     # whole-step CUDA graphs; NCCL all-reduces inside a step are only captured on request, our own step tail always is
     use_graphs = not args.eager and not args.stock_adam and (sync is None or args.graph_comm or sharded)
     trainer = MiniTrainer(module, opt, sched, grad_sync=sync, use_graphs=use_graphs, graph_collectives=args.graph_comm or sharded,
-                          overlap_optimizer=args.overlap and not args.stock_adam)
+                          overlap_optimizer=args.overlap and not args.stock_adam,
+                          fuse_optimizer=None if args.fused_adam < 0 else bool(args.fused_adam))
 
     # two distinct host batches (pinned) alternate through the two persistent device slots of a DevicePrefetcher;
     # 210 MB of features per step > L2 (126 MB), so inputs never sit in L2
@@ -455,7 +456,7 @@ def train_leg(args, rank, world, local, *, contrastive: bool, dp: str, seed: int
            "cuda_graphs": {"enabled": use_graphs, "variants_captured": n_graphs, "replays": trainer._graphed.replays if use_graphs else 0},
            "gradient_path": ("none (1 GPU)" if world == 1 else "none (independent ensemble members)" if dp == "none" else
                              sync.describe() if sharded else "NCCL all-reduce (fp32, 9 buckets) + replicated fused Adam"),
-           "clocks": clk}
+           "optimizer_in_backward": bool(trainer.fuse_optimizer), "clocks": clk}
     if e2e:
         out["e2e"] = {"value": n_models * B * K / (ms_e2e / 1e3), "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
     step_tflops = algorithmic_flops_per_window(contrastive) * B * K / (ms / 1e3) / 1e12
@@ -594,7 +595,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "contrastive": contrastive, "parallelism": f"dp{world}",
                            "gradient_path": main_leg["gradient_path"],
                            "optimizer": ("torch Adam(fused)" if args.stock_adam else "Adam (fused Adam+bf16-shadow kernel" + (", rank-sharded" if world > 1 and args.dp not in ("allreduce", "none") else "") + ")") + " + OneCycleLR, fp32 master weights",
-                           "optimizer_overlap": bool(args.overlap), "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
+                           "optimizer_overlap": bool(args.overlap), "optimizer_in_backward": main_leg["optimizer_in_backward"], "l2": "inputs larger than L2 (210 MB features/step, 2 alternating batches)",
                            "last_loss": main_leg["last_loss"], "host_enqueue_ms_per_step": main_leg["host_enqueue_ms_per_step"],
                            "cuda_graphs": main_leg["cuda_graphs"]},
                 "e2e": main_leg["e2e"], "gpu_launches": main_leg["gpu_launches"], "roofline": main_leg["roofline"], "clocks": main_leg["clocks"]}
@@ -707,6 +708,8 @@ def main():
     ap.add_argument("--comm-gemm-sms", type=int, default=0, help="N > 1: SMs the backward GEMMs use while gradient all-reduces are in flight (0 = all)")
     ap.add_argument("--watchdog", type=int, default=1500, help="dump all thread stacks and exit if the run takes longer than this many seconds (0 = off)")
     ap.add_argument("--overlap", action="store_true", help="run each layer's Adam step behind the backward (parallel.StepOverlap) instead of after it")
+    ap.add_argument("--fused-adam", type=int, default=-1, help="1/0: Adam update of the GEMM weights inside the wgrad GEMM epilogues (optimizer-in-backward); "
+                    "-1 = on whenever nothing sits between backward and step (1 GPU, ensemble members)")
     ap.add_argument("--stock-adam", action="store_true", help="keep torch's multi-tensor fused Adam instead of the TribeAdam kernel")
     args = ap.parse_args()
     if args.watchdog > 0:

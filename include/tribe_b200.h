@@ -114,6 +114,18 @@ typedef struct TribeGemm {
    * counters, which the kernel resets).  Must not be shared by GEMMs running concurrently on different streams. */
   void* splitk_ws;
   int64_t splitk_ws_bytes;
+  /* optional optimizer step fused into the epilogue (weight-gradient GEMMs; replaces the `optimizer.step()` pass of
+   * Lightning's automatic optimisation for this weight, main.py:396-413 / defaults.py:126-141): with adam_p != NULL the
+   * finished fp32 gradient element (after the epilogue, e.g. RESIDUAL with res = D for accumulation) at offset
+   * o = batch offset + row*ldd + col never has to reach memory: the epilogue reads adam_p/m/v[o], applies one Adam step
+   * with the device hyper-parameter block adam_hyper (tribe_adam_hyper layout) and writes adam_p/m/v[o] and the bf16
+   * shadow adam_shadow[o].  D itself is written only when adam_keep_grad != 0.  Requires d_f32 = 1, d_transposed = 0. */
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  void* adam_shadow;        /* bf16, optional */
+  const float* adam_hyper;
+  int32_t adam_keep_grad;
 } TribeGemm;
 
 int tribe_gemm_bf16(const TribeGemm* g, void* stream);
@@ -264,6 +276,11 @@ int tribe_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, 
 int tribe_adam_step_dev(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* hyper, int32_t max_blocks,
                         void* stream);
 int tribe_adam_hyper(float* hyper_dev, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
+/* The same for n blocks in one launch: block i lives at hyper_base + 8 * slots_host[i]; all arrays are HOST arrays of n
+ * entries (read before the call returns). */
+int tribe_adam_hyper_batch(float* hyper_base, const int32_t* slots_host, const int64_t* steps_host, const double* lr_host,
+                           const double* beta1_host, const double* beta2_host, const double* eps_host, const double* wd_host, int32_t n,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Data-parallel step tail over NVLink 5 / NVSwitch.  Replaces Lightning DDP's gradient all-reduce + the replicated

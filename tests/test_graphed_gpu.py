@@ -17,14 +17,15 @@ SMALL_DIMS = {"text": (2, 96), "audio": (2, 40), "video": (1, 72)}
 SMALL = dict(hidden=384, depth=2, heads=6)
 
 
-def _run(use_graphs: bool, contrastive: bool, steps: int, p_drop: float = 0.4, slots: int = 2, overlap: bool = False, lr: float = 3e-3):
+def _run(use_graphs: bool, contrastive: bool, steps: int, p_drop: float = 0.4, slots: int = 2, overlap: bool = False, lr: float = 3e-3,
+         fuse=None):
     torch.manual_seed(21)
     np.random.seed(21)
     cfg = FmriEncoderConfig(n_subjects=3, modality_dropout=p_drop, contrastive_enabled=contrastive)
     model = FmriEncoder(SMALL_DIMS, 200, 25, cfg, **SMALL)
     module = BrainModule(model=model, loss=torch.nn.MSELoss(), optim_config=None, metrics={}, max_epochs=1)
     opt, sched = default_optimizer(model.parameters(), total_steps=steps + 4, lr=lr, model=model)
-    trainer = MiniTrainer(module, opt, sched, use_graphs=use_graphs, overlap_optimizer=overlap)
+    trainer = MiniTrainer(module, opt, sched, use_graphs=use_graphs, overlap_optimizer=overlap, fuse_optimizer=fuse)
     spec = tuple((k, v[0], v[1]) for k, v in SMALL_DIMS.items())
     host = [synthetic_batch(batch_size=3, t=74, t_out=25, n_outputs=200, n_subjects=3, seed=70 + i, dims=spec) for i in range(2)]
     dev = [SegmentData(data={k: v.cuda() for k, v in b.data.items()}, segments=b.segments) for b in host]  # two fixed device slots
@@ -36,7 +37,10 @@ def _run(use_graphs: bool, contrastive: bool, steps: int, p_drop: float = 0.4, s
     torch.cuda.synchronize()
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     steps_of = {n: int(opt.state[p]["step"]) for n, p in model.named_parameters() if p in opt.state and len(opt.state[p])}
-    return dict(losses=torch.stack(losses).cpu(), masks=masks, none_grads=none_grads, state=state, steps_of=steps_of,
+    moments = {n: (opt.state[p]["exp_avg"].detach().clone(), opt.state[p]["exp_avg_sq"].detach().clone())
+               for n, p in model.named_parameters() if p in opt.state and len(opt.state[p])}
+    shadow = model._engine.flat.bf16.detach().clone()
+    return dict(moments=moments, shadow=shadow, losses=torch.stack(losses).cpu(), masks=masks, none_grads=none_grads, state=state, steps_of=steps_of,
                 next_rand=torch.rand(1).item(), lr=opt.param_groups[0]["lr"], trainer=trainer)
 
 
@@ -97,13 +101,13 @@ def test_optimizer_overlapped_with_backward_equals_plain_step(use_graphs, contra
     """parallel.StepOverlap: each layer's Adam launch moves behind the backward (side stream); same arithmetic, same
     step counts, same skipped projectors — also when the whole step is a replayed graph (forked capture streams)."""
     steps, kw = (20, {}) if not contrastive else (30, dict(p_drop=0.25, slots=1))
-    plain = _run(False, contrastive, steps, **kw)
+    plain = _run(False, contrastive, steps, fuse=False, **kw)  # (the overlapped optimizer excludes the in-backward one)
     over = _run(use_graphs, contrastive, steps, overlap=True, **kw)
     assert over["trainer"].grad_sync is not None and over["trainer"].grad_sync.opt_stream is not None
     _assert_same_bookkeeping(plain, over)
     assert float((over["losses"] - plain["losses"]).abs().max()) <= 0.05 * float(plain["losses"].abs().max())
     kw = dict(p_drop=0.0, slots=2, lr=5e-4)
-    plain, plain2 = _run(False, contrastive, 8, **kw), _run(False, contrastive, 8, **kw)
+    plain, plain2 = _run(False, contrastive, 8, fuse=False, **kw), _run(False, contrastive, 8, fuse=False, **kw)
     _assert_same_numbers(plain, plain2, _run(use_graphs, contrastive, 8, overlap=True, **kw))
 
 
@@ -162,3 +166,58 @@ def test_replayed_adam_reads_the_schedulers_current_hyper_parameters():
         want = [b1, b2, lr / (1.0 - b1 ** k), 1.0 / math.sqrt(1.0 - b2 ** k), eps, 0.0]
         for g_, w_ in zip(got[:6], want):
             assert abs(g_ - w_) <= 1e-6 * max(1.0, abs(w_)), (got, want)
+
+
+GEMM_WEIGHTS = ("to_q.weight", "to_k.weight", "to_v.weight", "to_out.weight", "ff.0.0.weight", "ff.2.weight", "predictor.weights")
+
+
+def _is_gemm_weight(name):
+    return name.endswith(GEMM_WEIGHTS) or (name.startswith("projectors.") and name.endswith(".weight"))
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+@pytest.mark.parametrize("contrastive", [False, True])
+def test_adam_fused_into_the_wgrad_epilogues_equals_the_plain_step(use_graphs, contrastive):
+    """optim.TribeAdam.fuse_backward: the Adam update of every GEMM weight runs inside its weight-gradient GEMM epilogue
+    (last backward pass of the step).  Those parameters keep ``grad is None``; everything else — step counts, skipped
+    projectors under modality dropout, RNG draws, lr schedule — is the plain step's.  After ONE step (no atomics-order
+    noise can have reached a weight gradient yet) parameters, moments and bf16 shadow weights are bit-identical."""
+    one_plain = _run(False, contrastive, 1, p_drop=0.0, fuse=False)
+    one_fused = _run(False, contrastive, 1, p_drop=0.0, fuse=True)
+    fused_names = [n for n in one_fused["none_grads"][0] if n not in one_plain["none_grads"][0]]
+    assert fused_names and all(_is_gemm_weight(n) for n in fused_names), fused_names
+    assert {n for n in one_plain["state"] if _is_gemm_weight(n)} == set(fused_names)  # every GEMM weight took the fused path
+    # the yardstick is a second plain run: bit-identical unless the step itself is not (the InfoNCE gradient of the
+    # contrastive branch accumulates with fp32 atomics, so its weight gradients carry run-to-run rounding noise)
+    one_plain2 = _run(False, contrastive, 1, p_drop=0.0, fuse=False)
+    deterministic = all(torch.equal(one_plain["state"][n], one_plain2["state"][n]) for n in fused_names)
+    assert deterministic or contrastive
+    for n in fused_names:
+        assert one_plain["steps_of"][n] == one_fused["steps_of"][n] == 1
+        pairs = [(one_plain["state"][n], one_plain2["state"][n], one_fused["state"][n])]
+        pairs += [(one_plain["moments"][n][i], one_plain2["moments"][n][i], one_fused["moments"][n][i]) for i in (0, 1)]
+        for ref, ref2, got in pairs:
+            if deterministic:
+                assert torch.equal(ref, got), n
+            else:
+                scale = float(ref.float().norm()) + 1e-20
+                noise = float((ref2.float() - ref.float()).norm()) / scale
+                assert float((got.float() - ref.float()).norm()) / scale <= max(10.0 * noise, 1e-6), n
+    if deterministic:
+        assert torch.equal(one_plain["shadow"], one_fused["shadow"])
+        assert float(one_plain["losses"][0]) == float(one_fused["losses"][0])
+
+    # under modality dropout: same discrete bookkeeping apart from the fused weights' missing .grad
+    steps, kw = (20, {}) if not contrastive else (30, dict(p_drop=0.25, slots=1))
+    plain = _run(False, contrastive, steps, fuse=False, **kw)
+    fused = _run(use_graphs, contrastive, steps, fuse=True, **kw)
+    if use_graphs:
+        assert fused["trainer"]._graphed.replays >= steps // 4
+    for a, b in zip(plain["none_grads"], fused["none_grads"]):
+        assert set(a) <= set(b) and all(_is_gemm_weight(n) for n in set(b) - set(a))
+    fused["none_grads"] = plain["none_grads"]
+    _assert_same_bookkeeping(plain, fused)
+    assert float((fused["losses"] - plain["losses"]).abs().max()) <= 0.05 * float(plain["losses"].abs().max())
+    kw = dict(p_drop=0.0, slots=2, lr=5e-4)
+    plain, plain2 = _run(False, contrastive, 8, fuse=False, **kw), _run(False, contrastive, 8, fuse=False, **kw)
+    _assert_same_numbers(plain, plain2, _run(use_graphs, contrastive, 8, fuse=True, **kw))

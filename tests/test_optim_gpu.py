@@ -63,3 +63,49 @@ def test_fused_adam_matches_torch_adam_with_onecycle_and_skipped_params():
         algonauts2025_b200.ops.cast_f32_bf16 = orig
     sd = opt.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+@pytest.mark.parametrize("m,n,k,accumulate", [(1024, 512, 320, False), (1096, 520, 256, False), (1280, 768, 192, True), (384, 200, 128, False)])
+def test_adam_in_the_wgrad_gemm_epilogue_is_bit_identical_to_gemm_then_adam(m, n, k, accumulate):
+    """TribeGemm.adam_* (include/tribe_b200.h): the optimizer step applied to the finished gradient tile inside the GEMM
+    epilogue — 2-CTA kernel through the coalescing transpose buffer for m >= 1024 (full and ragged row / column tiles),
+    1-CTA kernel row-per-thread otherwise, with and without in-place gradient accumulation — against the same GEMM
+    followed by the stand-alone Adam kernel: parameters, both moments and the bf16 shadow must agree bit for bit."""
+    import ctypes
+
+    from algonauts2025_b200 import _lib, ops
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    a = (torch.randn(k, m, device="cuda", generator=g) * 0.5).to(torch.bfloat16)  # wgrad form: both operands MN-major
+    b = (torch.randn(k, n, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    p0 = torch.randn(m, n, device="cuda", generator=g)
+    m0 = torch.randn(m, n, device="cuda", generator=g) * 0.1
+    v0 = torch.rand(m, n, device="cuda", generator=g) * 0.01
+    g_prev = torch.randn(m, n, device="cuda", generator=g)
+    hyper = torch.zeros(8, device="cuda")
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.tribe_adam_hyper(ctypes.c_void_p(hyper.data_ptr()), 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, stream), "tribe_adam_hyper")
+
+    def grad_gemm(out, **kw):
+        if accumulate:
+            ops.gemm(ops.mnmajor(a), ops.mnmajor(b), out, m, n, k, ldd=n, epilogue=ops.EPI_RESIDUAL, res=out, ld_res=n, res_batched=True, **kw)
+        else:
+            ops.gemm(ops.mnmajor(a), ops.mnmajor(b), out, m, n, k, ldd=n, **kw)
+
+    # reference: gradient GEMM, then the flat Adam kernel
+    gr = g_prev.clone()
+    pr, mr, vr, sr = p0.clone(), m0.clone(), v0.clone(), torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+    grad_gemm(gr)
+    _lib.check(lib.tribe_adam_step_dev(*(ctypes.c_void_p(t.data_ptr()) for t in (pr, gr, mr, vr, sr)), m * n, ctypes.c_void_p(hyper.data_ptr()), 0, stream),
+               "tribe_adam_step_dev")
+    for keep in (False, True):
+        gf = g_prev.clone()
+        pf, mf, vf, sf = p0.clone(), m0.clone(), v0.clone(), torch.zeros(m, n, device="cuda", dtype=torch.bfloat16)
+        grad_gemm(gf, adam=(pf.data_ptr(), mf.data_ptr(), vf.data_ptr(), sf.data_ptr(), hyper.data_ptr(), keep))
+        torch.cuda.synchronize()
+        assert torch.equal(pf, pr) and torch.equal(mf, mr) and torch.equal(vf, vr) and torch.equal(sf, sr), (m, n, k, keep)
+        assert torch.equal(gf, gr if keep else g_prev)  # the gradient is written only on request
+    with pytest.raises(algonauts2025_b200.TribeError):  # needs a row-major fp32 output
+        ops.gemm(ops.mnmajor(a), ops.mnmajor(b), torch.empty(m, n, device="cuda", dtype=torch.bfloat16), m, n, k, ldd=n,
+                 adam=(pf.data_ptr(), mf.data_ptr(), vf.data_ptr(), sf.data_ptr(), hyper.data_ptr(), False))

@@ -1,5 +1,8 @@
 """Achieved HBM bandwidth of the bandwidth-bound kernels at the TRIBE shapes (run under gpurun).
 ALGORITHMIC bytes / CUDA-event time, L2 flushed between launches; peak = MEASURED_PEAKS.json hbm_gbs.
+The flush READS a 256 MB buffer (BW_FLUSH=read, default): L2 ends up full of clean lines of foreign data.  The round-1
+flush (BW_FLUSH=write: zero-fill) left 126 MB of DIRTY lines whose write-back then ran concurrently with the measured
+kernel — for kernels that move only 100-250 MB that added up to +50 % HBM traffic to their clock.
 Also prints the Pearson-eval metric of BASELINE.json: parcel-TRs/s on (N_TR = 256 000, 1000) fp32 matrices."""
 import json
 import os
@@ -20,12 +23,18 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
 RESULTS = {}
 
 
+FLUSH_MODE = os.environ.get("BW_FLUSH", "read")
+
+
 def timeit(name, fn, nbytes, iters=10, extra=""):
     fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        if FLUSH_MODE == "write":
+            flush.zero_()
+        else:
+            flush.view(torch.int32).sum()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;");  // PDL: see tribe_internal.h
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma);
     prefetch_tmap(&p.tmb);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t stage_tx = kAttnAB + p.n_parts * kAttnBB;
 
   if (warp == 0) {
@@ -331,7 +333,10 @@ extern "C" int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, con
     attr_set = true;
   }
   const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
-  attn_scores_kernel<<<grid, kGemmThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+  {
+    cudaError_t le = launch_k(attn_scores_kernel, dim3(grid), dim3(kGemmThreads), kAttnSmem, reinterpret_cast<cudaStream_t>(stream), kp);
+    if (le != cudaSuccess) return set_cuda_error(le, "attn_scores launch");
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "attn_scores launch");

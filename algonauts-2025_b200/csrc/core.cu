@@ -1,6 +1,7 @@
 // Error reporting and launch accounting for the C ABI (include/tribe_b200.h).
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tribe_b200.h"
@@ -19,8 +20,22 @@ int set_cuda_error(cudaError_t e, const char* where) {
   return static_cast<int>(e);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("TRIBE_PDL");
+    v = (e && atoi(e) != 0) ? 1 : 0;  // opt-in: measured neutral on B200 inside whole-step CUDA graphs (profiles/r02_pdl_ab.txt)
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
 }  // namespace tribe
 
 extern "C" const char* tribe_last_error(void) { return tribe::g_err; }
 extern "C" int tribe_abi_version(void) { return 1; }
+extern "C" int tribe_set_pdl(int32_t on) {
+  tribe::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return TRIBE_OK;
+}
 extern "C" int64_t tribe_launch_count(void) { return tribe::g_launches.load(); }

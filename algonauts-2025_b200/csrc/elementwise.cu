@@ -107,10 +107,11 @@ __global__ void __launch_bounds__(256) ingest_kernel(const T* __restrict__ x, in
 // y = x / max(||x||, 1e-12) * sqrt(dim) * g   (oracle/xt_encoder.py ScaleNorm; F.normalize eps)
 __global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ rnorm, int64_t rows,
-                                                            int dim) {
+                                                            int dim, float mult, float eps) {
   __shared__ float red[32];
+  TRIBE_PDL_ENTRY();
   const int nvec = dim >> 2;
-  const float scale_g = sqrtf(static_cast<float>(dim)) * __ldg(g);
+  const float scale_g = mult * __ldg(g);
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
     float4 cache[4];
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restr
       ss += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
     }
     ss = block_sum(ss, red);
-    const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    const float rn = 1.0f / fmaxf(sqrtf(ss), eps);
     if (threadIdx.x == 0 && rnorm) rnorm[row] = rn;
     const float s = rn * scale_g;
     uint2* yr = reinterpret_cast<uint2*>(y + row * dim);
@@ -149,10 +150,12 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_kernel(const float* __restr
 // eight independent rows in flight per block.
 template <int NV>
 __global__ void __launch_bounds__(256) scalenorm_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                                                 __nv_bfloat16* __restrict__ y, float* __restrict__ rnorm, int64_t rows) {
+                                                                 __nv_bfloat16* __restrict__ y, float* __restrict__ rnorm, int64_t rows,
+                                                                 float mult, float eps) {
   constexpr int dim = NV * 128;
   const int lane = threadIdx.x & 31;
-  const float scale_g = sqrtf(static_cast<float>(dim)) * __ldg(g);
+  TRIBE_PDL_ENTRY();
+  const float scale_g = mult * __ldg(g);
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
     float4 c[NV];
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256) scalenorm_fwd_warp_kernel(const float* __
 #pragma unroll
     for (int i = 0; i < NV; ++i) ss += c[i].x * c[i].x + c[i].y * c[i].y + c[i].z * c[i].z + c[i].w * c[i].w;
     ss = warp_sum(ss);
-    const float rn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    const float rn = 1.0f / fmaxf(sqrtf(ss), eps);
     if (lane == 0 && rnorm) rnorm[row] = rn;
     const float sc = rn * scale_g;
     uint2* yr = reinterpret_cast<uint2*>(y + row * dim);
@@ -256,10 +259,11 @@ __global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __res
                                                               const float* __restrict__ x_in, const float* __restrict__ rnorm,
                                                               const float* __restrict__ g, const float* __restrict__ rs,
                                                               float* __restrict__ dx_in, __nv_bfloat16* __restrict__ dx_in_bf16,
-                                                              float* __restrict__ d_rs, float* __restrict__ d_g, int64_t rows, int dim) {
+                                                              float* __restrict__ d_rs, float* __restrict__ d_g, int64_t rows, int dim,
+                                                              float sqrt_dim /* the norm's constant gain factor: sqrt(dim) or 1 */) {
   __shared__ float red[32];
+  TRIBE_PDL_ENTRY();
   const int nvec = dim >> 2;
-  const float sqrt_dim = sqrtf(static_cast<float>(dim));
   const float gval = g ? __ldg(g) : 0.f;
   const bool has_dn = d_xn != nullptr, has_dy = dy_out != nullptr;
   float4 rs_acc[NV];
@@ -288,6 +292,41 @@ __global__ void __launch_bounds__(256, 2) sublayer_bwd_kernel(const float* __res
     }
   }
   if (d_g && threadIdx.x == 0) atomicAdd(d_g, sqrt_dim * dg_acc);
+}
+
+// ------------------------------------------------------------------------------------------------ half-split rotary
+// x_transformers 1.27.x rotary embedding (oracle/xt_encoder.py, semantics "v1.27"): inside every head the rotary dims are
+// paired (i, i + rot/2), both rotated by angle pos * inv_freq[i]:  x_i' = x_i cos - x_{i+rot/2} sin * sign,
+// x_{i+rot/2}' = x_{i+rot/2} cos + x_i sin * sign   (sign = -1: the transpose, for the backward).  In place on a bf16
+// (rows, ld) buffer; a thread owns 8 adjacent i of one (row, head): two 16-byte loads + two 16-byte stores.
+// (The interleaved pairing of >= 2.x is fused into the GEMM epilogue — TRIBE_EPI_ROPE; partners 96 columns apart do not
+// share an epilogue chunk, nor always a 256-wide tile.)
+__global__ void __launch_bounds__(256) rope_half_kernel(__nv_bfloat16* __restrict__ x, int64_t rows, int64_t ld, int64_t col_off, int n_heads,
+                                                        int head_dim, int rot_dim, const float2* __restrict__ table, int T, float sign) {
+  const int half = rot_dim >> 1, groups = half >> 3;
+  const int64_t total = rows * n_heads * groups;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int gq = static_cast<int>(idx % groups);
+    const int64_t rest = idx / groups;
+    const int h = static_cast<int>(rest % n_heads);
+    const int64_t row = rest / n_heads;
+    __nv_bfloat16* lo = x + row * ld + col_off + static_cast<int64_t>(h) * head_dim + gq * 8;
+    __nv_bfloat16* hi = lo + half;
+    const float2* tab = table + static_cast<int64_t>(row % T) * half + gq * 8;
+    uint4 a = *reinterpret_cast<const uint4*>(lo), b = *reinterpret_cast<const uint4*>(hi);
+    uint32_t* aw = reinterpret_cast<uint32_t*>(&a);
+    uint32_t* bw = reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x1 = unpack_bf16x2(aw[j]), x2 = unpack_bf16x2(bw[j]);
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(tab + 2 * j));  // (cos, sin) of i = 2j, 2j + 1
+      const float s0 = cs.y * sign, s1 = cs.w * sign;
+      aw[j] = pack_bf16x2(x1.x * cs.x - x2.x * s0, x1.y * cs.z - x2.y * s1);
+      bw[j] = pack_bf16x2(x2.x * cs.x + x1.x * s0, x2.y * cs.z + x1.y * s1);
+    }
+    *reinterpret_cast<uint4*>(lo) = a;
+    *reinterpret_cast<uint4*>(hi) = b;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ softmax
@@ -369,6 +408,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, c
                                                      int64_t rows, int64_t cols, int64_t ld, int64_t rows_per_block, int vec_ok) {
   // block = 32 (columns, x4 each) x 8 (row lanes); grid.x = column strips of 128, grid.y = row chunks
   __shared__ float red[8][128];
+  TRIBE_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 128 + tx * 4;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
@@ -426,6 +466,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, c
 __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t rows,
                                                             int64_t cols, int64_t ld, int64_t rows_per_block) {
   __shared__ float red[8][256];
+  TRIBE_PDL_ENTRY();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 256 + tx * 8;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
@@ -626,21 +667,25 @@ extern "C" int tribe_ingest_features(const void* x, int32_t src_dtype, int64_t B
   return TRIBE_OK;
 }
 
-extern "C" int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, void* stream) {
+extern "C" int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, float gain_mult, float eps,
+                                   void* stream) {
   if (!x || !g || !y_bf16 || rows <= 0 || dim <= 0 || dim % 4) return set_error(TRIBE_EINVAL, "scalenorm_fwd: bad arguments (dim % 4)");
+  if (gain_mult < 0.f || eps < 0.f) return set_error(TRIBE_EINVAL, "scalenorm_fwd: gain_mult and eps must be >= 0 (0 = default)");
+  const float mult = gain_mult > 0.f ? gain_mult : sqrtf(static_cast<float>(dim));
+  const float eps_ = eps > 0.f ? eps : 1e-12f;
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
   const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(y_bf16) & 7)) == 0;
   const int wgrid = grid_for(rows, 8, 148 * 2);
   if (al && dim == 3072) {
-    scalenorm_fwd_warp_kernel<24><<<wgrid, 256, 0, st_>>>(x, g, yb, rnorm, rows);
+    launch_k(scalenorm_fwd_warp_kernel<24>, dim3(wgrid), dim3(256), 0, st_, x, g, yb, rnorm, rows, mult, eps_);
   } else if (al && dim == 384) {
-    scalenorm_fwd_warp_kernel<3><<<wgrid, 256, 0, st_>>>(x, g, yb, rnorm, rows);
+    launch_k(scalenorm_fwd_warp_kernel<3>, dim3(wgrid), dim3(256), 0, st_, x, g, yb, rnorm, rows, mult, eps_);
   } else if (al && dim == 1024) {
-    scalenorm_fwd_warp_kernel<8><<<wgrid, 256, 0, st_>>>(x, g, yb, rnorm, rows);
+    launch_k(scalenorm_fwd_warp_kernel<8>, dim3(wgrid), dim3(256), 0, st_, x, g, yb, rnorm, rows, mult, eps_);
   } else {
     const int grid = grid_for(rows, 1, kMaxBlocks * 4);
-    scalenorm_fwd_kernel<<<grid, 256, 0, st_>>>(x, g, yb, rnorm, rows, static_cast<int>(dim));
+    launch_k(scalenorm_fwd_kernel, dim3(grid), dim3(256), 0, st_, x, g, yb, rnorm, rows, static_cast<int>(dim), mult, eps_);
   }
   TRIBE_CHECK_LAUNCH("scalenorm_fwd");
   return TRIBE_OK;
@@ -648,7 +693,9 @@ extern "C" int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16,
 
 extern "C" int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, const float* x_in, const float* rnorm, const float* g,
                                   const float* rs, float* dx_in, void* dx_in_bf16, float* d_rs, float* d_g, int64_t rows, int64_t dim,
-                                  void* stream) {
+                                  float gain_mult, void* stream) {
+  if (gain_mult < 0.f) return set_error(TRIBE_EINVAL, "sublayer_bwd: gain_mult must be >= 0 (0 = sqrt(dim))");
+  const float mult = gain_mult > 0.f ? gain_mult : sqrtf(static_cast<float>(dim));
   if (!x_in || rows <= 0 || dim <= 0 || dim % 4 || dim > 4096) return set_error(TRIBE_EINVAL, "sublayer_bwd: bad arguments (dim % 4, dim <= 4096)");
   if (d_xn_bf16 && (!rnorm || !g)) return set_error(TRIBE_EINVAL, "sublayer_bwd: d_xn needs rnorm and g");
   const int nv = static_cast<int>((dim / 4 + 255) / 256);
@@ -663,12 +710,26 @@ extern "C" int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, co
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_in_bf16);
   const int d = static_cast<int>(dim);
   switch (nv) {
-    case 1: sublayer_bwd_kernel<1><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
-    case 2: sublayer_bwd_kernel<2><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
-    case 3: sublayer_bwd_kernel<3><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
-    default: sublayer_bwd_kernel<4><<<grid, 256, 0, st>>>(dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d); break;
+    case 1: launch_k(sublayer_bwd_kernel<1>, dim3(grid), dim3(256), 0, st, dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d, mult); break;
+    case 2: launch_k(sublayer_bwd_kernel<2>, dim3(grid), dim3(256), 0, st, dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d, mult); break;
+    case 3: launch_k(sublayer_bwd_kernel<3>, dim3(grid), dim3(256), 0, st, dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d, mult); break;
+    default: launch_k(sublayer_bwd_kernel<4>, dim3(grid), dim3(256), 0, st, dy_out, dxn, x_in, rnorm, g, rs, dx_in, dxb, d_rs, d_g, rows, d, mult); break;
   }
   TRIBE_CHECK_LAUNCH("sublayer_bwd");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_rope_half(void* x_bf16, int64_t rows, int64_t ld, int64_t col_off, int64_t n_heads, int64_t head_dim, int64_t rot_dim,
+                               const float* table, int64_t T, float sign, void* stream) {
+  if (!x_bf16 || !table || rows <= 0 || n_heads <= 0 || T <= 0 || rot_dim <= 0 || rot_dim > head_dim || rot_dim % 16 || head_dim % 8 || ld % 8 ||
+      col_off % 8 || col_off + n_heads * head_dim > ld)
+    return set_error(TRIBE_EINVAL, "rope_half: bad arguments (rot_dim % 16, head_dim / ld / col_off % 8, heads inside the row)");
+  if ((reinterpret_cast<uintptr_t>(x_bf16) & 15) || (reinterpret_cast<uintptr_t>(table) & 15)) return set_error(TRIBE_EINVAL, "rope_half: 16-byte alignment required");
+  const int64_t total = rows * n_heads * (rot_dim / 16);
+  rope_half_kernel<<<grid_for(total, 256, kMaxBlocks * 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(x_bf16), rows, ld, col_off, static_cast<int>(n_heads), static_cast<int>(head_dim), static_cast<int>(rot_dim),
+      reinterpret_cast<const float2*>(table), static_cast<int>(T), sign);
+  TRIBE_CHECK_LAUNCH("rope_half");
   return TRIBE_OK;
 }
 
@@ -717,7 +778,7 @@ extern "C" int tribe_colsum(const void* x, int32_t x_dtype, const void* y, int32
     if (chunks8 < 1) chunks8 = 1;
     const int64_t rpb8 = (rows + chunks8 - 1) / chunks8;
     dim3 grid8(static_cast<unsigned>(strips8), static_cast<unsigned>((rows + rpb8 - 1) / rpb8));
-    colsum_bf16x8_kernel<<<grid8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ld, rpb8);
+    launch_k(colsum_bf16x8_kernel, grid8, dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ld, rpb8);
     TRIBE_CHECK_LAUNCH("colsum");
     return TRIBE_OK;
   }
@@ -729,12 +790,12 @@ extern "C" int tribe_colsum(const void* x, int32_t x_dtype, const void* y, int32
   dim3 grid(static_cast<unsigned>(strips), static_cast<unsigned>((rows + rpb - 1) / rpb));
   using bf = __nv_bfloat16;
   const int vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (!y || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
-  if (x_dtype == 0 && !y) colsum_kernel<float, float, false><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), nullptr, out, rows, cols, ld, rpb, vec_ok);
-  else if (x_dtype == 2 && !y) colsum_kernel<bf, bf, false><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), nullptr, out, rows, cols, ld, rpb, vec_ok);
-  else if (x_dtype == 0 && y_dtype == 0) colsum_kernel<float, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb, vec_ok);
-  else if (x_dtype == 2 && y_dtype == 2) colsum_kernel<bf, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb, vec_ok);
-  else if (x_dtype == 0 && y_dtype == 2) colsum_kernel<float, bf, true><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb, vec_ok);
-  else if (x_dtype == 2 && y_dtype == 0) colsum_kernel<bf, float, true><<<grid, 256, 0, s>>>(reinterpret_cast<const bf*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb, vec_ok);
+  if (x_dtype == 0 && !y) launch_k(colsum_kernel<float, float, false>, grid, dim3(256), 0, s, reinterpret_cast<const float*>(x), nullptr, out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 2 && !y) launch_k(colsum_kernel<bf, bf, false>, grid, dim3(256), 0, s, reinterpret_cast<const bf*>(x), nullptr, out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 0 && y_dtype == 0) launch_k(colsum_kernel<float, float, true>, grid, dim3(256), 0, s, reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 2 && y_dtype == 2) launch_k(colsum_kernel<bf, bf, true>, grid, dim3(256), 0, s, reinterpret_cast<const bf*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 0 && y_dtype == 2) launch_k(colsum_kernel<float, bf, true>, grid, dim3(256), 0, s, reinterpret_cast<const float*>(x), reinterpret_cast<const bf*>(y), out, rows, cols, ld, rpb, vec_ok);
+  else if (x_dtype == 2 && y_dtype == 0) launch_k(colsum_kernel<bf, float, true>, grid, dim3(256), 0, s, reinterpret_cast<const bf*>(x), reinterpret_cast<const float*>(y), out, rows, cols, ld, rpb, vec_ok);
   else return set_error(TRIBE_EINVAL, "colsum: unsupported dtype combination");
   TRIBE_CHECK_LAUNCH("colsum");
   return TRIBE_OK;

@@ -94,6 +94,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  asm volatile("griddepcontrol.launch_dependents;");  // PDL: see tribe_internal.h
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma);
@@ -120,6 +121,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
   cluster_sync_all();  // peer barriers are initialised and both halves of the TMEM allocation exist
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)

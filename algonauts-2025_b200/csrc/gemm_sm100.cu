@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kGemmThreads, SMALL ? 2 : 1) gemm_bf16_kernel(
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;");  // PDL: see tribe_internal.h
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma);
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kGemmThreads, SMALL ? 2 : 1) gemm_bf16_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above overlapped the previous kernel's tail
   const int n_kouter = p.kgroup ? p.kgroup_len : 1;
 
   if (warp == 0) {
@@ -408,9 +410,9 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(kp);
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, stream, kp);
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "gemm launch");
   return TRIBE_OK;
 }
@@ -425,9 +427,9 @@ static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm2)");
     attr_set = true;
   }
-  kern<<<grid, kGemm2Threads, Cfg::SMEM_BYTES, stream>>>(kp);  // __cluster_dims__(2,1,1): grid is a multiple of 2
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(kGemm2Threads), Cfg::SMEM_BYTES, stream, kp);  // __cluster_dims__(2,1,1): grid is a multiple of 2
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "gemm2 launch");
   return TRIBE_OK;
 }

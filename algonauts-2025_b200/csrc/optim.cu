@@ -24,6 +24,7 @@ __device__ __forceinline__ uint32_t opt_pack2(float a, float b) {
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    __nv_bfloat16* __restrict__ p16, int64_t n, float beta1, float beta2, float step_size,
                                                    float inv_bc2_sqrt, float eps, float wd, const float* __restrict__ hyper) {
+  TRIBE_PDL_ENTRY();
   if (hyper) beta1 = hyper[0], beta2 = hyper[1], step_size = hyper[2], inv_bc2_sqrt = hyper[3], eps = hyper[4], wd = hyper[5];
   const int64_t nvec = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -79,9 +80,9 @@ extern "C" int tribe_adam_step(float* p, const float* g, float* m, float* v, voi
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   const float step_size = static_cast<float>(lr / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
-  adam_kernel<<<grid_for(n / 4 + 1, 256, max_blocks > 0 ? max_blocks : 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, static_cast<float>(beta1), static_cast<float>(beta2), step_size, inv_bc2_sqrt,
-      static_cast<float>(eps), static_cast<float>(weight_decay), nullptr);
+  launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, 256, max_blocks > 0 ? max_blocks : 148 * 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p, g,
+           m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, static_cast<float>(beta1), static_cast<float>(beta2), step_size, inv_bc2_sqrt,
+           static_cast<float>(eps), static_cast<float>(weight_decay), static_cast<const float*>(nullptr));
   TRIBE_CHECK_LAUNCH("adam_step");
   return TRIBE_OK;
 }
@@ -91,8 +92,8 @@ extern "C" int tribe_adam_step_dev(float* p, const float* g, float* m, float* v,
   if (!p || !g || !m || !v || !hyper || n <= 0) return set_error(TRIBE_EINVAL, "adam_step_dev: bad arguments");
   const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v);
   if ((al & 15) || (reinterpret_cast<uintptr_t>(p_bf16) & 7)) return set_error(TRIBE_EINVAL, "adam_step_dev: buffers must be 16-byte aligned (bf16: 8)");
-  adam_kernel<<<grid_for(n / 4 + 1, 256, max_blocks > 0 ? max_blocks : 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, hyper);
+  launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, 256, max_blocks > 0 ? max_blocks : 148 * 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p, g,
+           m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, hyper);
   TRIBE_CHECK_LAUNCH("adam_step_dev");
   return TRIBE_OK;
 }

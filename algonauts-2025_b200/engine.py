@@ -228,6 +228,11 @@ class Engine:
         # update of every GEMM weight inside its wgrad epilogue
         self.fused_opt = None
         self._grad_plans = 0  # grad-enabled forward passes whose backward has not run yet
+        # which x_transformers release's arithmetic the encoder follows (oracle/xt_encoder.py): ">= 2.x" = ScaleNorm
+        # F.normalize * sqrt(dim) * g and interleaved rotary pairs (fused into the GEMM epilogues); "v1.27" = ScaleNorm
+        # x / norm.clamp(1e-5) * g and half-split rotary pairs (a separate in-place pass over q, k / dq, dk)
+        self.v127 = getattr(model, "xt_semantics", "v2") == "v1.27"
+        self.norm_mult, self.norm_eps = (1.0, 1e-5) if self.v127 else (0.0, 0.0)
 
     # ------------------------------------------------------------------------------------------------ parameters
     def materialize(self, device):
@@ -389,10 +394,14 @@ class Engine:
             a, f = self._names(l)
             ia, iff = 2 * l, 2 * l + 1
             # ---- attention sub-layer
-            ops.scalenorm_fwd(ws.xs[ia], self._p(f"{a}.0.0.g"), ws.xn[ia], ws.rn[ia])
+            ops.scalenorm_fwd(ws.xs[ia], self._p(f"{a}.0.0.g"), ws.xn[ia], ws.rn[ia], self.norm_mult, self.norm_eps)
             qkv = ws.qkv[l]
-            ops.gemm(ops.kmajor(ws.xn[ia]), ops.kmajor(self._wqkv16(a)), qkv, M, 3 * H, H, ldd=3 * H, epilogue=ops.EPI_ROPE,
-                     rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=2 * H)
+            if self.v127:
+                ops.gemm(ops.kmajor(ws.xn[ia]), ops.kmajor(self._wqkv16(a)), qkv, M, 3 * H, H, ldd=3 * H)
+                ops.rope_half(qkv, 0, 2 * heads, dh, self.rot, rope, T)  # q and k heads are adjacent in the packed buffer
+            else:
+                ops.gemm(ops.kmajor(ws.xn[ia]), ops.kmajor(self._wqkv16(a)), qkv, M, 3 * H, H, ldd=3 * H, epilogue=ops.EPI_ROPE,
+                         rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=2 * H)
             if ops.attn_fusable(T, dh):
                 # P = softmax(q k^T d^-1/2) formed in the tcgen05 epilogue: whole score rows live in TMEM, no fp32 S in HBM
                 ops.attn_scores(qkv, 0, qkv, H, B, T, heads, dh, scale, ws.P[l])
@@ -409,13 +418,13 @@ class Engine:
             ops.gemm(ops.kmajor(ws.attn[l]), ops.kmajor(self._w16(f"{a}.1.to_out.weight")), ws.xs[ia + 1], M, H, H, ldd=H,
                      epilogue=ops.EPI_RESIDUAL, res=ws.xs[ia], ld_res=H, rscale=self._p(f"{a}.2.residual_scale"))
             # ---- feed-forward sub-layer
-            ops.scalenorm_fwd(ws.xs[iff], self._p(f"{f}.0.0.g"), ws.xn[iff], ws.rn[iff])
+            ops.scalenorm_fwd(ws.xs[iff], self._p(f"{f}.0.0.g"), ws.xn[iff], ws.rn[iff], self.norm_mult, self.norm_eps)
             ops.gemm(ops.kmajor(ws.xn[iff]), ops.kmajor(self._w16(f"{f}.1.ff.0.0.weight")), ws.hact[l], M, F, H, ldd=F,
                      bias=self._p(f"{f}.1.ff.0.0.bias"), epilogue=ops.EPI_GELU, aux_out=ws.hpre[l], ld_aux=F)
             ops.gemm(ops.kmajor(ws.hact[l]), ops.kmajor(self._w16(f"{f}.1.ff.2.weight")), ws.xs[iff + 1], M, H, F, ldd=H,
                      bias=self._p(f"{f}.1.ff.2.bias"), epilogue=ops.EPI_RESIDUAL, res=ws.xs[iff], ld_res=H,
                      rscale=self._p(f"{f}.2.residual_scale"))
-        ops.scalenorm_fwd(ws.xs[2 * self.depth], self._p("encoder.final_norm.g"), ws.xnf, ws.rnf)
+        ops.scalenorm_fwd(ws.xs[2 * self.depth], self._p("encoder.final_norm.g"), ws.xnf, ws.rnf, self.norm_mult, self.norm_eps)
 
         if plan.mode == "latents":
             lat = torch.empty(B, T, H, device=self.device, dtype=torch.float32)
@@ -553,7 +562,8 @@ class Engine:
             else:
                 d_xnf = d_xp
         # final ScaleNorm backward
-        ops.sublayer_bwd(None, d_xnf, ws.xs[2 * self.depth], ws.rnf, self._p("encoder.final_norm.g"), None, dx_cur, dxb_cur, None, gfin)
+        ops.sublayer_bwd(None, d_xnf, ws.xs[2 * self.depth], ws.rnf, self._p("encoder.final_norm.g"), None, dx_cur, dxb_cur, None, gfin,
+                         self.norm_mult)
 
         rope = self._rope_table(T)
         scale = dh ** -0.5
@@ -581,7 +591,7 @@ class Engine:
             wgrad(ops.mnmajor(ws.dh), ops.mnmajor(ws.xn[iff]), f"{f}.1.ff.0.0.weight", F, H, M)
             ops.colsum(ws.dh, gs[f"{f}.1.ff.0.0.bias"], accumulate=acc[f"{f}.1.ff.0.0.bias"])
             ops.sublayer_bwd(dx_cur, ws.dtmp, ws.xs[iff], ws.rn[iff], self._p(f"{f}.0.0.g"), self._p(f"{f}.2.residual_scale"),
-                             dx_nxt, dxb_nxt, gs[f"{f}.2.residual_scale"], gs[f"{f}.0.0.g"])
+                             dx_nxt, dxb_nxt, gs[f"{f}.2.residual_scale"], gs[f"{f}.0.0.g"], self.norm_mult)
             dx_cur, dx_nxt, dxb_cur, dxb_nxt = dx_nxt, dx_cur, dxb_nxt, dxb_cur
             # ================= attention sub-layer
             wo = self._w16(f"{a}.1.to_out.weight")
@@ -607,12 +617,13 @@ class Engine:
             ds_op = ops.Operand(ws.dS, inner=Tp, rows=T, row_stride=Tp, batch=BH, batch_stride=T * Tp)
             km_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, mn_major=True, inner_off=H,
                                 zin_stride=dh, zdiv=heads)
-            ops.gemm(ds_op, km_op, ws.dqkv, T, dh, Tp, ldd=3 * H, batch=BH, z_inner=heads, d_zo=T * 3 * H, d_zi=dh, epilogue=ops.EPI_ROPE,
-                     rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=dh, rope_sign=-1.0)
+            unrope = {} if self.v127 else dict(epilogue=ops.EPI_ROPE, rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=dh, rope_sign=-1.0)
+            ops.gemm(ds_op, km_op, ws.dqkv, T, dh, Tp, ldd=3 * H, batch=BH, z_inner=heads, d_zo=T * 3 * H, d_zi=dh, **unrope)
             dst_op = ops.Operand(ws.dS, inner=Tp, rows=T, row_stride=Tp, batch=BH, batch_stride=T * Tp, mn_major=True)
             qm_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, mn_major=True, zin_stride=dh, zdiv=heads)
-            ops.gemm(dst_op, qm_op, ws.dqkv, T, dh, T, ldd=3 * H, batch=BH, z_inner=heads, d_zo=T * 3 * H, d_zi=dh, d_off=H,
-                     epilogue=ops.EPI_ROPE, rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=dh, rope_sign=-1.0)
+            ops.gemm(dst_op, qm_op, ws.dqkv, T, dh, T, ldd=3 * H, batch=BH, z_inner=heads, d_zo=T * 3 * H, d_zi=dh, d_off=H, **unrope)
+            if self.v127:
+                ops.rope_half(ws.dqkv, 0, 2 * heads, dh, self.rot, rope, T, sign=-1.0)  # transpose of the rotation on dq and dk
             # d_xn = dqkv @ Wqkv ;  dWqkv = dqkv^T xn
             wqkv = self._wqkv16(a)
             ops.gemm(ops.kmajor(ws.dqkv), ops.mnmajor(wqkv), ws.dtmp, M, H, 3 * H, ldd=H)
@@ -620,7 +631,7 @@ class Engine:
             gqkv = fl.grad[o: o + 3 * H * H].view(3 * H, H)
             wgrad(ops.mnmajor(ws.dqkv), ops.mnmajor(ws.xn[ia]), [f"{a}.1.{n}.weight" for n in ("to_q", "to_k", "to_v")], 3 * H, H, M, out=gqkv)
             ops.sublayer_bwd(dx_cur, ws.dtmp, ws.xs[ia], ws.rn[ia], self._p(f"{a}.0.0.g"), self._p(f"{a}.2.residual_scale"),
-                             dx_nxt, dxb_nxt, gs[f"{a}.2.residual_scale"], gs[f"{a}.0.0.g"])
+                             dx_nxt, dxb_nxt, gs[f"{a}.2.residual_scale"], gs[f"{a}.0.0.g"], self.norm_mult)
             dx_cur, dx_nxt, dxb_cur, dxb_nxt = dx_nxt, dx_cur, dxb_nxt, dxb_cur
             if self.comm is not None:
                 publish()

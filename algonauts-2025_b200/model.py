@@ -39,6 +39,8 @@ class FmriEncoderConfig(pydantic.BaseModel):
     contrastive_modalities: list[str] = ["video"]
     contrastive_weight: float = 0.1
     contrastive_temperature: float = 0.07
+    # extension (not in the reference schema): arithmetic of the third-party encoder, see FmriEncoder.__init__
+    xt_semantics: tp.Literal["v2", "v1.27"] = "v2"
 
     def build(self, feature_dims: dict, n_outputs: int, n_output_timesteps: int) -> nn.Module:
         return FmriEncoder(feature_dims, n_outputs, n_output_timesteps, config=self)
@@ -182,9 +184,9 @@ class AdaptiveAvgPool1d(nn.Module):
 
 
 class _ScaleNorm(nn.Module):
-    def __init__(self):
+    def __init__(self, g_init: float = 1.0):
         super().__init__()
-        self.g = nn.Parameter(torch.ones(1))
+        self.g = nn.Parameter(torch.ones(1) * g_init)
 
 
 class _Attention(nn.Module):
@@ -219,17 +221,18 @@ class TribeEncoder(nn.Module):
     ``layers.<i>.1.ff.0.0.weight``, ``layers.<i>.2.residual_scale``, ``final_norm.g``, ``rotary_pos_emb.inv_freq``);
     creation order = x_transformers' so a seed reproduces the reference's init.  ``forward`` runs the fused engine."""
 
-    def __init__(self, dim, depth, heads):
+    def __init__(self, dim, depth, heads, semantics: str = "v2"):
         super().__init__()
-        self.dim, self.depth, self.heads = dim, depth, heads
+        self.dim, self.depth, self.heads, self.semantics = dim, depth, heads, semantics
+        g_init = dim ** -0.5 if semantics == "v1.27" else 1.0  # 1.27.x ScaleNorm: g = ones(1) * dim ** -0.5, no sqrt(dim) factor
         self.rotary_pos_emb = _Rotary(max(dim // heads // 2, 32))
         layers = []
         for _ in range(depth):
             for kind in ("a", "f"):
                 block = _Attention(dim) if kind == "a" else _FeedForward(dim)
-                layers.append(nn.ModuleList([nn.ModuleList([_ScaleNorm(), None, None]), block, _Residual(dim)]))
+                layers.append(nn.ModuleList([nn.ModuleList([_ScaleNorm(g_init), None, None]), block, _Residual(dim)]))
         self.layers = nn.ModuleList(layers)
-        self.final_norm = _ScaleNorm()
+        self.final_norm = _ScaleNorm(g_init)
         self._owner = None
 
     def forward(self, x):
@@ -241,8 +244,15 @@ class TribeEncoder(nn.Module):
 
 class FmriEncoder(nn.Module):
     def __init__(self, feature_dims: dict[str, tuple[int, int]], n_outputs: int, n_output_timesteps: int, config: FmriEncoderConfig,
-                 *, hidden: int = HIDDEN, depth: int = 8, heads: int = 8, device=None):
+                 *, hidden: int = HIDDEN, depth: int = 8, heads: int = 8, device=None, xt_semantics: str | None = None):
+        """``xt_semantics`` (extension; also a config field): which x_transformers release's arithmetic the fusion encoder
+        follows — ``"v2"`` (>= 1.30 / 2.x, default) or ``"v1.27"`` (the oldest release modeling_utils/pyproject.toml:12
+        admits).  State-dict keys are the same under both, so a checkpoint must be evaluated with the semantics of the
+        library version that trained it."""
         super().__init__()
+        self.xt_semantics = xt_semantics or getattr(config, "xt_semantics", "v2")
+        if self.xt_semantics not in ("v2", "v1.27"):
+            raise ValueError(f"xt_semantics must be 'v2' or 'v1.27', got {self.xt_semantics!r}")
         self.config = config
         self.feature_dims = feature_dims
         self.n_outputs = n_outputs
@@ -271,7 +281,7 @@ class FmriEncoder(nn.Module):
             raise ValueError(f"dim ({hidden}) must be divisible by the number of heads ({heads})")  # transformer.py:46-49
         if hidden < 256:
             raise ValueError(f"dim ({hidden}) is less than 256, which causes weird bug in x-transformers")  # :50-53
-        self.encoder = TribeEncoder(hidden, depth, heads)
+        self.encoder = TribeEncoder(hidden, depth, heads, self.xt_semantics)
         import weakref
 
         self.encoder._owner = weakref.ref(self)

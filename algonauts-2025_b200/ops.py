@@ -173,16 +173,26 @@ def ingest_features(x: torch.Tensor, out: torch.Tensor, col_off: int, layer_mean
                                             _stream())
 
 
-def scalenorm_fwd(x, g, y, rnorm) -> None:
+def scalenorm_fwd(x, g, y, rnorm, gain_mult: float = 0.0, eps: float = 0.0) -> None:
+    """y = x / max(||x||, eps) * gain_mult * g; the zeros select sqrt(dim) and 1e-12 (x_transformers >= 2.x ScaleNorm)."""
     _need(x, torch.float32, "scalenorm x"), _need(y, torch.bfloat16, "scalenorm y")
     rows, dim = x.shape
-    _run("tribe_scalenorm_fwd", _ptr(x), _ptr(g), _ptr(y), _ptr(rnorm), rows, dim, _stream())
+    _run("tribe_scalenorm_fwd", _ptr(x), _ptr(g), _ptr(y), _ptr(rnorm), rows, dim, float(gain_mult), float(eps), _stream())
 
 
-def sublayer_bwd(dy_out, d_xn, x_in, rnorm, g, rs, dx_in, dx_in_bf16, d_rs, d_g) -> None:
+def sublayer_bwd(dy_out, d_xn, x_in, rnorm, g, rs, dx_in, dx_in_bf16, d_rs, d_g, gain_mult: float = 0.0) -> None:
     rows, dim = x_in.shape
     _run("tribe_sublayer_bwd", _ptr(dy_out), _ptr(d_xn), _ptr(x_in), _ptr(rnorm), _ptr(g), _ptr(rs), _ptr(dx_in),
-                                         _ptr(dx_in_bf16), _ptr(d_rs), _ptr(d_g), rows, dim, _stream())
+                                         _ptr(dx_in_bf16), _ptr(d_rs), _ptr(d_g), rows, dim, float(gain_mult), _stream())
+
+
+def rope_half(x, col_off: int, n_heads: int, head_dim: int, rot_dim: int, table, T: int, sign: float = 1.0) -> None:
+    """Half-split rotary (x_transformers 1.27.x) in place on the heads at columns [col_off, col_off + n_heads*head_dim) of
+    the bf16 (rows, ld) buffer ``x``; ``table`` is the engine's (T, rot_dim/2, 2) cos/sin table; sign=-1: transpose."""
+    _need(x, torch.bfloat16, "rope_half x"), _need(table, torch.float32, "rope_half table")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise TribeError("rope_half: 2-D row-major buffer expected")
+    _run("tribe_rope_half", _ptr(x), x.shape[0], x.stride(0), col_off, n_heads, head_dim, rot_dim, _ptr(table), T, float(sign), _stream())
 
 
 def softmax_fwd(s, p, n_valid) -> None:

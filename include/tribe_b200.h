@@ -39,6 +39,11 @@ const char* tribe_last_error(void);
 int tribe_abi_version(void);
 /* Number of kernels launched through this library since load (bench.py's `gpu_launches`). */
 int64_t tribe_launch_count(void);
+/* Programmatic dependent launch for the hot kernels (GEMMs, attention, norm / sub-layer tails, column sums, Adam): a
+ * kernel's prologue and launch latency overlap its predecessor's tail; stream order is preserved (every CTA waits for
+ * the predecessor's completion before touching memory).  Off by default (measured neutral inside whole-step CUDA
+ * graphs); TRIBE_PDL=1 in the environment or this call turns it on. */
+int tribe_set_pdl(int32_t on);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * tcgen05 / TMEM / TMA GEMM:  D[z] = epilogue( alpha * A[z] (M x K) * B[z]^T (N x K) )
@@ -156,16 +161,26 @@ int tribe_gemm_bf16_probe(const TribeGemm* g, void* stream, uint32_t k_lbo, uint
 int tribe_ingest_features(const void* x, int32_t src_dtype, int64_t B, int64_t L, int64_t D, int64_t T, int32_t layer_mean,
                           void* out_bf16, int64_t ld_out, int64_t col_off, void* stream);
 
-/* ScaleNorm forward (x_transformers ScaleNorm, see oracle/xt_encoder.py): y = x / max(||x||, 1e-12) * sqrt(dim) * g[0].
- * x fp32 (rows, dim) -> y bf16 (rows, dim), rnorm fp32 (rows) = 1 / max(||x||, eps). */
-int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, void* stream);
+/* ScaleNorm forward (x_transformers ScaleNorm, see oracle/xt_encoder.py): y = x / max(||x||, eps) * gain_mult * g[0].
+ * x fp32 (rows, dim) -> y bf16 (rows, dim), rnorm fp32 (rows) = 1 / max(||x||, eps).
+ * gain_mult = 0 -> sqrt(dim), eps = 0 -> 1e-12: the >= 2.x form F.normalize(x) * sqrt(dim) * g;
+ * gain_mult = 1, eps = 1e-5: the 1.27.x form x / norm.clamp(min = eps) * g. */
+int tribe_scalenorm_fwd(const float* x, const float* g, void* y_bf16, float* rnorm, int64_t rows, int64_t dim, float gain_mult, float eps,
+                        void* stream);
 
 /* Sub-layer backward tail: given dy_out (fp32 grad wrt the sub-layer output x_out = branch + x_in*rs) and d_xn (bf16
  * grad wrt the ScaleNorm output), produces dx_in (fp32 and bf16 copies), and accumulates d_rs (fp32 [dim]) and d_g
  * (fp32 [1]) atomically.  d_xn may be NULL (final norm handled by tribe_scalenorm_bwd). rs may be NULL (=1). */
 int tribe_sublayer_bwd(const float* dy_out, const void* d_xn_bf16, const float* x_in, const float* rnorm, const float* g,
                        const float* rs, float* dx_in, void* dx_in_bf16, float* d_rs, float* d_g, int64_t rows, int64_t dim,
-                       void* stream);
+                       float gain_mult /* as in tribe_scalenorm_fwd */, void* stream);
+
+/* Half-split rotary embedding of x_transformers 1.27.x, in place on a bf16 (rows, ld) buffer: for each of the n_heads
+ * heads at columns col_off + h*head_dim, dims i and i + rot_dim/2 (i < rot_dim/2) are rotated by the angle of position
+ * row % T and frequency i (table: fp32 (T, rot_dim/2, 2) = (cos, sin), the tribe_gemm rope table); sign = -1 applies
+ * the transpose (backward).  The >= 2.x interleaved pairing is fused into the GEMM epilogue instead (TRIBE_EPI_ROPE). */
+int tribe_rope_half(void* x_bf16, int64_t rows, int64_t ld, int64_t col_off, int64_t n_heads, int64_t head_dim, int64_t rot_dim,
+                    const float* table, int64_t T, float sign, void* stream);
 
 /* Row softmax over the first n_valid of ld columns: s fp32 (rows, ld) -> p bf16 (rows, ld), columns >= n_valid zeroed. */
 int tribe_softmax_fwd(const float* s, void* p_bf16, int64_t rows, int64_t n_valid, int64_t ld, void* stream);

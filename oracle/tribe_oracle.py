@@ -103,7 +103,7 @@ class OracleFmriEncoder(nn.Module):
     [subject_embed], encoder."""
 
     def __init__(self, feature_dims, n_outputs, n_output_timesteps, config: OracleConfig,
-                 hidden: int = HIDDEN, depth: int = 8, heads: int = 8):
+                 hidden: int = HIDDEN, depth: int = 8, heads: int = 8, xt_semantics: str = "v2"):
         super().__init__()
         self.config, self.feature_dims, self.n_outputs = config, feature_dims, n_outputs
         self.n_output_timesteps, self.hidden = n_output_timesteps, hidden
@@ -127,7 +127,7 @@ class OracleFmriEncoder(nn.Module):
         if config.subject_embedding:
             self.subject_embed = nn.Embedding(config.n_subjects, hidden)
         self.encoder = Encoder(dim=hidden, depth=depth, heads=heads, attn_dim_head=hidden // heads, ff_mult=4,
-                               use_scalenorm=True, rotary_pos_emb=True, scale_residual=True)
+                               use_scalenorm=True, rotary_pos_emb=True, scale_residual=True, semantics=xt_semantics)
 
     # -- state-dict bridge to the reference / product naming ----------------------------------------------------
     def reference_state_dict(self):

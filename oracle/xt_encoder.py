@@ -20,6 +20,11 @@ vector for it, so the semantics below are *declared* (x_transformers >= 1.30 / 2
   ``(0,1),(2,3),...``, ``inv_freq = 10000 ** (-arange(0, rot_dim, 2) / rot_dim)``, angles computed in fp32;
   ``sim = q k^T * dim_head ** -0.5``; ``softmax(dtype=float32)``.
 * ``FeedForward``: ``Linear(dim, 4 dim, bias) -> GELU(erf) -> Linear(4 dim, dim, bias)``.
+* ``semantics="v1.27"`` (the oldest release the pin admits, x_transformers 1.27.x) differs in exactly two places:
+  ``ScaleNorm`` is ``x / norm(x).clamp(min=1e-5) * g`` with ``g = ones(1) * dim ** -0.5`` (no ``sqrt(dim)`` factor), and the
+  rotary embedding is *half-split*: ``freqs = cat((f, f))``, ``rotate_half`` pairs dim ``i`` with ``i + rot_dim/2``.
+  A checkpoint trained under one release must be evaluated with that release's arithmetic (the state-dict keys are
+  identical), hence the switch.
 * parameter names mirror the library's module nesting so that a reference checkpoint's ``state_dict`` keys line up:
   ``layers.<i>.0.0.g``, ``layers.<i>.1.{to_q,to_k,to_v,to_out}.weight``, ``layers.<i>.1.ff.0.0.{weight,bias}``,
   ``layers.<i>.1.ff.2.{weight,bias}``, ``layers.<i>.2.residual_scale``, ``final_norm.g``,
@@ -34,25 +39,39 @@ import torch.nn.functional as F
 from torch import nn
 
 
+SEMANTICS = ("v2", "v1.27")
+
+
 class ScaleNorm(nn.Module):
-    def __init__(self, dim: int):
+    def __init__(self, dim: int, semantics: str = "v2"):
         super().__init__()
-        self.scale = dim**0.5
-        self.g = nn.Parameter(torch.ones(1))
+        self.semantics = semantics
+        if semantics == "v1.27":
+            self.eps = 1e-5
+            self.g = nn.Parameter(torch.ones(1) * (dim**-0.5))
+        else:
+            self.scale = dim**0.5
+            self.g = nn.Parameter(torch.ones(1))
 
     def forward(self, x):
+        if self.semantics == "v1.27":
+            norm = torch.norm(x, dim=-1, keepdim=True)
+            return x / norm.clamp(min=self.eps) * self.g
         return F.normalize(x, dim=-1) * self.scale * self.g
 
 
 class RotaryEmbedding(nn.Module):
-    def __init__(self, dim: int, base: float = 10000.0):
+    def __init__(self, dim: int, base: float = 10000.0, semantics: str = "v2"):
         super().__init__()
+        self.semantics = semantics
         inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim))
         self.register_buffer("inv_freq", inv_freq)
 
     def forward(self, seq_len: int, device=None):
         t = torch.arange(seq_len, device=device).type_as(self.inv_freq)
         freqs = torch.einsum("i,j->ij", t, self.inv_freq)
+        if self.semantics == "v1.27":
+            return torch.cat((freqs, freqs), dim=-1)  # half-split: (f0, f1, ..., f0, f1, ...)
         # interleave: (f0, f0, f1, f1, ...)
         return torch.stack((freqs, freqs), dim=-1).reshape(seq_len, -1)
 
@@ -63,18 +82,24 @@ def _rotate_pairs(x):
     return torch.stack((-x2, x1), dim=-1).reshape(*x.shape[:-2], -1)
 
 
-def apply_rotary(t, freqs):
+def _rotate_half(x):
+    x1, x2 = x.reshape(*x.shape[:-1], 2, -1).unbind(dim=-2)
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary(t, freqs, semantics: str = "v2"):
     rot_dim = freqs.shape[-1]
     dtype = t.dtype
     t_rot, t_pass = t[..., :rot_dim], t[..., rot_dim:]
-    t_rot = t_rot.float() * freqs.cos() + _rotate_pairs(t_rot.float()) * freqs.sin()
+    rot = _rotate_half if semantics == "v1.27" else _rotate_pairs
+    t_rot = t_rot.float() * freqs.cos() + rot(t_rot.float()) * freqs.sin()
     return torch.cat((t_rot.to(dtype), t_pass), dim=-1)
 
 
 class Attention(nn.Module):
-    def __init__(self, dim: int, dim_head: int, heads: int):
+    def __init__(self, dim: int, dim_head: int, heads: int, semantics: str = "v2"):
         super().__init__()
-        self.heads, self.dim_head = heads, dim_head
+        self.heads, self.dim_head, self.semantics = heads, dim_head, semantics
         self.scale = dim_head**-0.5
         inner = dim_head * heads
         self.to_q = nn.Linear(dim, inner, bias=False)
@@ -87,7 +112,7 @@ class Attention(nn.Module):
         h, d = self.heads, self.dim_head
         q, k, v = (f(x).view(b, n, h, d).transpose(1, 2) for f in (self.to_q, self.to_k, self.to_v))
         if freqs is not None:
-            q, k = apply_rotary(q, freqs), apply_rotary(k, freqs)
+            q, k = apply_rotary(q, freqs, self.semantics), apply_rotary(k, freqs, self.semantics)
         sim = torch.einsum("bhid,bhjd->bhij", q, k) * self.scale
         attn = sim.softmax(dim=-1, dtype=torch.float32).to(sim.dtype)
         out = torch.einsum("bhij,bhjd->bhid", attn, v)
@@ -119,8 +144,11 @@ class Encoder(nn.Module):
     """``x_transformers.Encoder`` restatement; accepts (and checks) exactly the kwargs the reference passes."""
 
     def __init__(self, dim: int, depth: int, heads: int = 8, attn_dim_head: int = 64, ff_mult: int = 4,
-                 use_scalenorm: bool = False, rotary_pos_emb: bool = False, scale_residual: bool = False, **kw):
+                 use_scalenorm: bool = False, rotary_pos_emb: bool = False, scale_residual: bool = False, semantics: str = "v2", **kw):
         super().__init__()
+        if semantics not in SEMANTICS:
+            raise ValueError(f"semantics must be one of {SEMANTICS}")
+        self.semantics = semantics
         unsupported = {"cross_attend": False, "attn_flash": False, "attn_dropout": 0.0, "ff_dropout": 0.0,
                        "use_rmsnorm": False, "rel_pos_bias": False, "alibi_pos_bias": False, "rotary_xpos": False,
                        "residual_attn": False, "layer_dropout": 0.0}
@@ -130,15 +158,15 @@ class Encoder(nn.Module):
         if not use_scalenorm:
             raise NotImplementedError("oracle Encoder restates only use_scalenorm=True")
         self.dim, self.depth, self.heads, self.dim_head = dim, depth, heads, attn_dim_head
-        self.rotary_pos_emb = RotaryEmbedding(max(attn_dim_head // 2, 32)) if rotary_pos_emb else None
+        self.rotary_pos_emb = RotaryEmbedding(max(attn_dim_head // 2, 32), semantics=semantics) if rotary_pos_emb else None
         layers = []
         for _ in range(depth):
             for kind in ("a", "f"):
-                block = Attention(dim, attn_dim_head, heads) if kind == "a" else FeedForward(dim, ff_mult)
-                norms = nn.ModuleList([ScaleNorm(dim), None, None])
+                block = Attention(dim, attn_dim_head, heads, semantics) if kind == "a" else FeedForward(dim, ff_mult)
+                norms = nn.ModuleList([ScaleNorm(dim, semantics), None, None])
                 layers.append(nn.ModuleList([norms, block, Residual(dim, scale_residual)]))
         self.layers = nn.ModuleList(layers)
-        self.final_norm = ScaleNorm(dim)
+        self.final_norm = ScaleNorm(dim, semantics)
 
     def forward(self, x):
         freqs = self.rotary_pos_emb(x.shape[1], x.device) if self.rotary_pos_emb is not None else None

@@ -398,3 +398,82 @@ def test_standalone_subject_layers_is_differentiable():
     assert float(layer.bias.grad[2].abs().max()) == 0.0
     with pytest.raises(AssertionError):
         layer(xg, torch.tensor([[4], [0], [0], [0], [0]]).cuda())
+
+
+# ----------------------------------------------------------------------------------------------- x_transformers 1.27.x semantics
+def _pair_v127(cfg_kw=None, seed=5):
+    cfg_kw = dict(n_subjects=3, **(cfg_kw or {}))
+    torch.manual_seed(seed)
+    model = FmriEncoder(SMALL_DIMS, 200, 25, FmriEncoderConfig(xt_semantics="v1.27", **cfg_kw), **SMALL)
+    oracle = O.OracleFmriEncoder(SMALL_DIMS, 200, 25, O.OracleConfig(**cfg_kw), xt_semantics="v1.27", **SMALL)
+    oracle.load_reference_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    return model, oracle
+
+
+def test_xt_semantics_v127_forward_and_gradients_match_the_oracle():
+    """modeling_utils/pyproject.toml:12 admits x_transformers 1.27.x, whose ScaleNorm (x / norm.clamp(1e-5) * g with
+    g = dim ** -0.5) and rotary embedding (half-split pairs i, i + rot/2) differ from >= 2.x while the state-dict keys
+    are identical.  ``xt_semantics="v1.27"``: forward, loss and every parameter gradient vs oracle/xt_encoder.py in that
+    mode; the ScaleNorm gains are initialised like that release; and the two semantics really differ on the same weights."""
+    model, oracle = _pair_v127()
+    H = SMALL["hidden"]
+    for g in (model.encoder.final_norm.g, model.encoder.layers[0][0][0].g):
+        assert abs(float(g.detach()) - H ** -0.5) < 1e-7  # fp32 of dim ** -0.5
+    batch = small_batch()
+    model.eval(), oracle.eval()
+    with torch.no_grad():
+        y, ref = model(batch), oracle(as_oracle_batch(batch))
+        lat = model.transformer_forward(torch.randn(2, 50, H, generator=torch.Generator().manual_seed(3)).cuda())
+        lat_ref = oracle.transformer_forward(torch.randn(2, 50, H, generator=torch.Generator().manual_seed(3)))
+    assert_pred_close(y, ref)
+    assert_pred_close(lat, lat_ref)
+    # same weights under the other release's arithmetic: a clearly different function
+    torch.manual_seed(5)
+    other = FmriEncoder(SMALL_DIMS, 200, 25, FmriEncoderConfig(n_subjects=3), **SMALL)
+    other.load_state_dict(model.state_dict())
+    other.eval()
+    with torch.no_grad():
+        y2 = other(batch)
+    assert rel_l2(y2, ref) > 0.1
+    # train step: every gradient
+    model.train(), oracle.train()
+    torch.manual_seed(11), np.random.seed(11)
+    loss = mse_loss(model(batch), batch.data["fmri"])
+    loss.backward()
+    torch.manual_seed(11), np.random.seed(11)
+    ref_loss, *_ = O.run_step(oracle, as_oracle_batch(batch))
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
+    ref_grads = {k.replace("predictor_weights", "predictor.weights").replace("predictor_bias", "predictor.bias"): v.grad
+                 for k, v in oracle.named_parameters()}
+    for name, p in model.named_parameters():
+        assert p.grad is not None and ref_grads[name] is not None, name
+        err = rel_l2(p.grad, ref_grads[name])
+        # the scalar ScaleNorm gains sum signed bf16-rounded terms over every token (cancellation): a little more head-room
+        assert err <= (5e-2 if name.endswith(".g") else 3e-2), (name, err)
+
+
+def test_rope_half_kernel_matches_the_oracle_rotation_and_its_transpose():
+    from oracle import xt_encoder as X
+
+    from algonauts2025_b200 import ops
+
+    torch.manual_seed(0)
+    rows_b, T, heads, dh = 3, 37, 4, 64
+    rot = max(dh // 2, 32)
+    x = torch.randn(rows_b * T, 3 * heads * dh)
+    xb = x.to(torch.bfloat16).cuda()
+    emb = X.RotaryEmbedding(rot, semantics="v1.27")
+    freqs = emb(T)
+    ang = torch.arange(T).float()[:, None] * emb.inv_freq[None, :]
+    table = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().cuda()
+    ref = xb.float().cpu().view(rows_b, T, 3 * heads, dh).clone()
+    q = ref[:, :, : 2 * heads].permute(0, 2, 1, 3)  # (b, h, T, dh)
+    ref[:, :, : 2 * heads] = X.apply_rotary(q, freqs, "v1.27").permute(0, 2, 1, 3)
+    y = xb.clone()
+    ops.rope_half(y, 0, 2 * heads, dh, rot, table, T)
+    got = y.float().cpu().view(rows_b, T, 3 * heads, dh)
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+    assert torch.equal(got[:, :, 2 * heads:], xb.float().cpu().view(rows_b, T, 3 * heads, dh)[:, :, 2 * heads:])  # v heads untouched
+    ops.rope_half(y, 0, 2 * heads, dh, rot, table, T, sign=-1.0)  # the transpose is the inverse rotation
+    assert float((y.float().cpu() - xb.float().cpu()).abs().max()) <= 3e-2 * float(xb.float().abs().max())

@@ -125,3 +125,32 @@ def test_full_model_matches_reference(golden_dir):
         got = grads[str(name)].double().norm().item()
         assert abs(got - norm) <= 2e-4 * max(norm, 1e-12), (name, got, norm)
     np.testing.assert_allclose(grads["predictor.bias"].numpy(), g["grad_predictor_bias"], rtol=1e-3, atol=1e-8)
+
+
+def test_xt_v127_restatement_is_the_v2_encoder_under_a_head_dim_permutation():
+    """Independent check of the 1.27.x restatement (oracle/xt_encoder.py): half-split rotary pairs (i, i + rot/2) are the
+    interleaved pairs (2i, 2i+1) after permuting the rotary dims of every q / k head, and attention scores are invariant
+    to a common permutation of q and k head dims — so permuting the rows of to_q / to_k turns a v1.27 attention block
+    into the v2 one, output for output.  ScaleNorm: g_v127 = g_v2 * sqrt(dim) (away from the eps clamps)."""
+    import torch
+
+    from oracle import xt_encoder as X
+
+    torch.manual_seed(0)
+    dim, heads, dh, T = 256, 4, 64, 19
+    rot = max(dh // 2, 32)
+    a1, a2 = X.Attention(dim, dh, heads, "v1.27"), X.Attention(dim, dh, heads, "v2")
+    a2.load_state_dict(a1.state_dict())
+    perm = torch.arange(dh)
+    perm[:rot] = torch.stack((torch.arange(rot // 2), torch.arange(rot // 2) + rot // 2), dim=-1).reshape(-1)  # interleaved slot -> half-split index
+    rows = (torch.arange(heads)[:, None] * dh + perm[None, :]).reshape(-1)
+    with torch.no_grad():
+        a2.to_q.weight.copy_(a1.to_q.weight[rows]), a2.to_k.weight.copy_(a1.to_k.weight[rows])
+    x = torch.randn(2, T, dim)
+    f1, f2 = X.RotaryEmbedding(rot, semantics="v1.27")(T), X.RotaryEmbedding(rot, semantics="v2")(T)
+    torch.testing.assert_close(a1(x, f1), a2(x, f2), rtol=1e-4, atol=1e-5)
+    n1, n2 = X.ScaleNorm(dim, "v1.27"), X.ScaleNorm(dim, "v2")
+    with torch.no_grad():
+        n1.g.fill_(0.37), n2.g.fill_(0.37 / dim ** 0.5)
+    torch.testing.assert_close(n1(x), n2(x), rtol=1e-5, atol=1e-6)
+    assert abs(float(X.ScaleNorm(dim, "v1.27").g) - dim ** -0.5) < 1e-9 and float(X.ScaleNorm(dim, "v2").g) == 1.0

@@ -67,23 +67,31 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = 128 * BK * 2;        // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // the optimizer-carrying instance trades one ring stage for eight per-warp transpose buffers (adam_tile_coalesced)
-  static constexpr int EPI_STAGE_BYTES = ADAM ? 8 * kAdamStageFloats * 4 : 0;
-  static constexpr int STAGES_RAW = (220 * 1024 - EPI_STAGE_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // eight per-warp epilogue staging tiles (4 KB each: transpose buffer of the fp32 / optimizer epilogues, TMA-store source
+  // of the bf16 ones) sit between the operand ring and the barriers; the ring keeps 6 stages at BN = 256
+  static constexpr int EPI_STAGE_BYTES = 8 * kEpiStageFloats * 4;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024;
 };
 
-// ADAM: the instance whose epilogue can carry the optimizer step (weight gradients; see adam_chunk) — a separate
-// instantiation so that every other launch keeps the leaner epilogue (148 registers, no spills).
-template <int BN, bool A_MN, bool B_MN, bool ADAM = false>
+// EPI: which epilogue family this instance carries — separate instantiations so that each keeps only its own live state
+// inside the 168-register budget (with everything in one body the fp32 path spilled its eight in-flight residual
+// loads right behind each LDG, serialising them):
+//   kEpiGeneric  bf16 outputs through TMA stores (+ every fused epilogue: bias, GELU, GELU', rotary) and the generic fallback
+//   kEpiF32      fp32 row-major outputs, STORE / RESIDUAL: transposed, coalesced epilogue
+//   kEpiAdam     weight gradients whose epilogue carries the optimizer step (see adam_tile_coalesced)
+constexpr int kEpiGeneric = 0, kEpiF32 = 1, kEpiAdam = 2;
+template <int BN, bool A_MN, bool B_MN, int EPI = kEpiGeneric>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) gemm2_bf16_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr bool ADAM = EPI == kEpiAdam;
+  constexpr bool LEAN = EPI != kEpiGeneric;  // only bias / RESIDUAL math can occur
   using Cfg = Gemm2Cfg<BN, ADAM>;
   static_assert(BN == 128 || BN == 256, "2-CTA tiles: BN/2 must be a multiple of 64");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -99,6 +107,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma);
     prefetch_tmap(&p.tmb);
+    if (p.tma_store) {
+      prefetch_tmap(&p.tmd);
+      if (p.epilogue == TRIBE_EPI_GELU) prefetch_tmap(&p.tmaux);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -212,19 +224,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
     const int row_in_half = q * 32 + lane;
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t leader_tempty1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
-    float* adam_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES) + (warp - 2) * kAdamStageFloats;
-    // one finished 32-column chunk of this thread's row: optimizer step through the transpose buffer (weight gradients
-    // with an armed optimizer, full chunks) or the generic fused epilogue
+    float* stage_f = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES) + (warp - 2) * kEpiStageFloats;
+    uint8_t* stage_b = reinterpret_cast<uint8_t*>(stage_f);  // bf16 TMA-store tiles: D at +0, aux_out at +2048 (32 rows x 64 B each)
+    // where a finished chunk goes (all warp-uniform):
+    //   fp32 row-major D, STORE / RESIDUAL   -> transposed through the staging tile, coalesced bias / residual / store
+    //   bf16 row-major D with tensor maps     -> fused math in registers, tile staged in SWIZZLE_64B, one TMA store per chunk
+    //   weight gradient with an armed optimizer (ADAM instance) -> Adam step through the staging tile
+    //   anything else (ragged last chunk, transposed / batched outputs) -> generic row-per-thread epilogue
+    const bool path_f32 = EPI == kEpiF32 && p.vec_ok && !p.bias_gathered;  // (host: fp32 row-major D, STORE / RESIDUAL)
+    const bool path_tma = EPI == kEpiGeneric && p.tma_store != 0;
+    const bool gelu = p.epilogue == TRIBE_EPI_GELU;
+    bool store_pending = false;  // lane 0: a bulk store may still be reading this warp's staging tile
     auto finish_chunk = [&](float (&v)[32], int row, bool row_ok, int col0, long long zoff, const float* bias, int res_row, int pos,
                             const uint4* pre_aux) {
+      const bool full_chunk = col0 + 32 <= p.n;
       if constexpr (ADAM) {
-        if (p.adam_p && p.vec_ok && col0 + 32 <= p.n) {  // warp-uniform
+        if (p.adam_p && p.vec_ok && full_chunk) {
           epilogue_math<true>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux);
-          adam_tile_coalesced(p, v, adam_stage, lane, row - lane, col0, zoff);
+          adam_tile_coalesced(p, v, stage_f, lane, row - lane, col0, zoff);
           return;
         }
       }
-      epilogue_chunk<ADAM, false, ADAM>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux);
+      if constexpr (EPI == kEpiF32) {
+        if (path_f32 && full_chunk) {
+          store_tile_f32_coalesced(p, v, stage_f, lane, row - lane, col0, zoff, bias);
+          return;
+        }
+      }
+      if constexpr (EPI == kEpiGeneric) {
+        if (path_tma && full_chunk) {
+          uint4 auxp[4], pk[4];
+          epilogue_math<false>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux, gelu ? auxp : nullptr);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            pk[j >> 3] = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+          if (lane == 0 && store_pending) tma_store_wait_read();
+          __syncwarp();
+          stage_write_bf16_sw64(stage_b, lane, pk);
+          if (gelu) stage_write_bf16_sw64(stage_b + 2048, lane, auxp);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmd, stage_b, col0, row);  // lane 0's row is the tile's first row
+            if (gelu) tma_store_2d(&p.tmaux, stage_b + 2048, col0, row);
+            tma_store_commit();
+          }
+          store_pending = true;
+          return;
+        }
+      }
+      epilogue_chunk<ADAM, false, LEAN>(p, v, row, row_ok, col0, zoff, bias, res_row, pos, pre_aux);
     };
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -264,7 +313,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
       if (!w.partial) {
         // GELU' epilogue (dgrad of FF2): the bf16 pre-activations of the NEXT chunk are requested before this chunk's
         // accumulator is read, one chunk ahead of their use
-        const bool pre = !ADAM && p.epilogue == TRIBE_EPI_GELU_BWD && p.vec_ok && row_ok;  // (never a weight gradient)
+        const bool pre = !LEAN && p.epilogue == TRIBE_EPI_GELU_BWD && p.vec_ok && row_ok;  // (bf16 outputs only)
         uint4 ax_cur[4], ax_nxt[4];
         auto ld_aux = [&](int c, uint4 (&a)[4]) {
           const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + static_cast<long long>(row) * p.ld_aux + t.n0 + c * 32);
@@ -350,6 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // bulk stores complete before the CTA retires
   }
 
   tc_fence_before();

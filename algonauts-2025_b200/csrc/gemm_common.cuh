@@ -20,6 +20,9 @@ constexpr int kMaxTailTiles = 160;  // split-K counters (4 ints per tail tile) r
 
 struct alignas(64) GemmKParams {
   CUtensorMap tma, tmb;
+  CUtensorMap tmd, tmaux;  // TMA-store maps of D and aux_out (bf16 outputs of the 2-CTA kernel, box 32 x 32, SWIZZLE_64B)
+  int tma_store;           // 1: tmd (and tmaux for the GELU epilogue) are valid
+  int f32_coalesce;        // 1: fp32 row-major outputs of the 2-CTA kernel take the transposed (coalesced) epilogue
   int m, n, k, batch, z_inner;
   int a_inner_off, a_zin_stride, a_zdiv;
   int b_inner_off, b_zin_stride, b_zdiv;
@@ -206,9 +209,10 @@ __device__ __forceinline__ void adam_chunk(const GemmKParams& p, const float (&g
 // first use of this load).
 // Part 1: everything that changes the VALUES of the chunk (bias, activation, residual, rotary); aux_out side store of GELU.
 // LEAN: only what a weight-gradient GEMM can ask for (bias, RESIDUAL accumulation) is compiled in.
+// aux_pack (optional, GELU): receives the chunk's 32 bf16 pre-activations instead of the direct aux_out store.
 template <bool LEAN = false>
 __device__ __forceinline__ void epilogue_math(const GemmKParams& p, float (&v)[32], int row, bool row_ok, int col0, long long zoff,
-                                              const float* bias, int res_row, int pos, const uint4* pre_aux = nullptr) {
+                                              const float* bias, int res_row, int pos, const uint4* pre_aux = nullptr, uint4* aux_pack = nullptr) {
   const int nvalid = min(32, p.n - col0);
   const bool full = (nvalid == 32) && p.vec_ok;
 
@@ -227,7 +231,11 @@ __device__ __forceinline__ void epilogue_math(const GemmKParams& p, float (&v)[3
   }
 
   if (!LEAN && p.epilogue == TRIBE_EPI_GELU) {
-    if (row_ok) {
+    if (aux_pack) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        aux_pack[j >> 3] = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+    } else if (row_ok) {
       __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
       if (full) {
 #pragma unroll
@@ -359,19 +367,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float (&v)[
 // quarter-row), after which lane l owns columns 4*(l%8)..+3 of rows l/8, l/8 + 4, ...: every warp-wide access covers four
 // full 128-byte lines of p / m / v (row-per-thread accesses touch 32 lines for the same bytes and ran the fused step at
 // a third of the stand-alone kernel's bandwidth).  Four row groups (12 x 16-byte loads per lane) are in flight at once.
-constexpr int kAdamStageRow = 36;
-constexpr int kAdamStageFloats = 32 * kAdamStageRow;
+// ---- per-warp epilogue staging tile (2-CTA kernel): 32 rows x 32 fp32 columns = 4 KB, 16-byte chunk c of row r stored at
+// chunk (c ^ (r & 7)): conflict-free both for the writers (thread = row, after tcgen05.ld) and for the readers
+// (lane = 4 columns of rows l/8, l/8 + 4, ...), who then touch global memory in full 128-byte lines.
+constexpr int kEpiStageFloats = 32 * 32;
+__device__ __forceinline__ void stage_write_row(float* stage, int lane, const float (&g)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+}
+__device__ __forceinline__ float4 stage_read(const float* stage, int r, int c4) {
+  return *reinterpret_cast<const float4*>(stage + r * 32 + ((c4 ^ (r & 7)) << 2));
+}
+
+// Adam step on a warp's 32-row x 32-column gradient tile with COALESCED state traffic (row-per-thread accesses touch 32
+// lines for the same bytes and ran the fused step at a third of the stand-alone kernel's bandwidth).  Four row groups
+// (12 x 16-byte loads per lane) are in flight at once.
 __device__ __forceinline__ void adam_tile_coalesced(const GemmKParams& p, const float (&g)[32], float* stage, int lane, int row0, int col0,
                                                     long long zoff) {
   __syncwarp();  // the previous chunk's reads of `stage` are complete
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(stage + lane * kAdamStageRow + 4 * j) = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+  stage_write_row(stage, lane, g);
   __syncwarp();
   const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.adam_hyper));
   const float2 h1 = __ldg(reinterpret_cast<const float2*>(p.adam_hyper + 4));
   const float beta1 = h0.x, beta2 = h0.y, step_size = h0.z, inv_bc2_sqrt = h0.w, eps = h1.x, wd = h1.y;
-  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  const int sub = lane >> 3, c4 = lane & 7;
 #pragma unroll
   for (int it0 = 0; it0 < 8; it0 += 4) {
     float4 P[4], M[4], V[4];
@@ -381,7 +401,7 @@ __device__ __forceinline__ void adam_tile_coalesced(const GemmKParams& p, const 
     for (int u = 0; u < 4; ++u) {
       const int r = (it0 + u) * 4 + sub;
       ok[u] = row0 + r < p.m;
-      off[u] = zoff + static_cast<long long>(row0 + r) * p.ldd + col0 + c4;
+      off[u] = zoff + static_cast<long long>(row0 + r) * p.ldd + col0 + c4 * 4;
       if (ok[u]) {
         P[u] = __ldcs(reinterpret_cast<const float4*>(p.adam_p + off[u]));
         M[u] = __ldcs(reinterpret_cast<const float4*>(p.adam_m + off[u]));
@@ -391,8 +411,7 @@ __device__ __forceinline__ void adam_tile_coalesced(const GemmKParams& p, const 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (!ok[u]) continue;
-      const int r = (it0 + u) * 4 + sub;
-      const float4 G = *reinterpret_cast<const float4*>(stage + r * kAdamStageRow + c4);
+      const float4 G = stage_read(stage, (it0 + u) * 4 + sub, c4);
       adam_one(P[u].x, G.x, M[u].x, V[u].x, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
       adam_one(P[u].y, G.y, M[u].y, V[u].y, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
       adam_one(P[u].z, G.z, M[u].z, V[u].z, beta1, beta2, step_size, inv_bc2_sqrt, eps, wd);
@@ -404,6 +423,59 @@ __device__ __forceinline__ void adam_tile_coalesced(const GemmKParams& p, const 
       if (p.adam_keep_grad) __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.d) + off[u]), G);
     }
   }
+}
+
+// fp32 outputs (projector / out-projection / FF2 forward with their residual, weight gradients): the accumulator chunk
+// (thread = row) is transposed through the staging tile; bias, residual * rscale and the store then run with lane = 4
+// columns, i.e. every warp-wide access covers four full 128-byte lines of res / D (row-per-thread accesses need 32
+// line visits for the same bytes, which kept the LSU busier than the tensor pipe on the K = 3072 GEMMs).  All eight
+// residual loads of the chunk are issued before the first use.
+__device__ __forceinline__ void store_tile_f32_coalesced(const GemmKParams& p, const float (&acc)[32], float* stage, int lane, int row0, int col0,
+                                                         long long zoff, const float* bias) {
+  __syncwarp();
+  stage_write_row(stage, lane, acc);
+  __syncwarp();
+  const int sub = lane >> 3, c4 = lane & 7;
+  const int col = col0 + c4 * 4;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+  const bool has_res = p.epilogue == TRIBE_EPI_RESIDUAL;
+  if (has_res && p.rscale) s4 = __ldg(reinterpret_cast<const float4*>(p.rscale + col));
+  float4 R[8];
+  if (has_res) {
+    // residual row of output row r: r % res_row_mod (positional-embedding table) or r; one modulo per chunk, then stepped
+    const int mod = p.res_row_mod;
+    int rr = row0 + sub;
+    if (mod) rr %= mod;
+    const float* rbase = p.res + (p.res_batched ? zoff : 0) + col;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if (row0 + it * 4 + sub < p.m) R[it] = __ldg(reinterpret_cast<const float4*>(rbase + static_cast<long long>(rr) * p.ld_res));
+      rr += 4;
+      if (mod) {
+        while (rr >= mod) rr -= mod;
+      }
+    }
+  }
+  float* dbase = reinterpret_cast<float*>(p.d) + zoff + col;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + sub, row = row0 + r;
+    if (row >= p.m) continue;
+    float4 o = stage_read(stage, r, c4);
+    o.x += b4.x, o.y += b4.y, o.z += b4.z, o.w += b4.w;
+    if (has_res) o.x += R[it].x * s4.x, o.y += R[it].y * s4.y, o.z += R[it].z * s4.z, o.w += R[it].w * s4.w;
+    *reinterpret_cast<float4*>(dbase + static_cast<long long>(row) * p.ldd) = o;
+  }
+}
+
+// bf16 outputs through a TMA store: the warp's 32 x 32 chunk goes to its staging tile in the SWIZZLE_64B layout the tensor
+// map expects (64-byte rows; 16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3): conflict-free for thread = row
+// writers), is published to the async proxy and stored by one lane with cp.async.bulk.tensor (rows past m are clipped
+// by the hardware).  `pk` = the thread's 32 packed bf16 values.
+__device__ __forceinline__ void stage_write_bf16_sw64(uint8_t* stage, int lane, const uint4 (&pk)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = pk[c];
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }

@@ -370,6 +370,22 @@ static int encode_operand(const TribeOperand& op, int box_rows, CUtensorMap* out
   return TRIBE_OK;
 }
 
+// 2-D bf16 output map for the TMA-store epilogue of the 2-CTA kernel: box = 32 columns x 32 rows, SWIZZLE_64B.
+static int encode_out_bf16(const void* ptr, int64_t cols, int64_t rows, int64_t ld, CUtensorMap* out) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(TRIBE_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  alignas(64) CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TRIBE_ETMAP, "cuTensorMapEncodeTiled failed for the output map");
+  *out = tm;
+  return TRIBE_OK;
+}
+
 static std::atomic<int> g_sm_limit{0};  // tribe_gemm_set_sm_limit: 0 = all SMs
 
 static int device_sms() {
@@ -417,11 +433,11 @@ static int launch_gemm(const GemmKParams& kp, int grid, cudaStream_t stream) {
   return TRIBE_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool ADAM = false>
+template <int BN, bool A_MN, bool B_MN, int EPI = kEpiGeneric>
 static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN, ADAM>;
+  using Cfg = Gemm2Cfg<BN, EPI == kEpiAdam>;
   static bool attr_set = false;
-  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, ADAM>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, EPI>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm2)");
@@ -434,13 +450,19 @@ static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
   return TRIBE_OK;
 }
 
+template <int BN, int EPI>
+static int dispatch_major2e(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm2<BN, false, false, EPI>(kp, grid, s);
+  if (a_mn && !b_mn) return launch_gemm2<BN, true, false, EPI>(kp, grid, s);
+  if (!a_mn && b_mn) return launch_gemm2<BN, false, true, EPI>(kp, grid, s);
+  return launch_gemm2<BN, true, true, EPI>(kp, grid, s);
+}
+
 template <int BN>
 static int dispatch_major2(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_gemm2<BN, false, false>(kp, grid, s);
-  if (a_mn && !b_mn) return launch_gemm2<BN, true, false>(kp, grid, s);
-  if (!a_mn && b_mn) return launch_gemm2<BN, false, true>(kp, grid, s);
-  if (kp.adam_p) return launch_gemm2<BN, true, true, true>(kp, grid, s);
-  return launch_gemm2<BN, true, true>(kp, grid, s);
+  if (kp.adam_p) return launch_gemm2<BN, true, true, kEpiAdam>(kp, grid, s);  // (host: wgrad form only)
+  if (kp.f32_coalesce) return dispatch_major2e<BN, kEpiF32>(kp, grid, a_mn, b_mn, s);
+  return dispatch_major2e<BN, kEpiGeneric>(kp, grid, a_mn, b_mn, s);
 }
 
 template <int BN>
@@ -556,6 +578,26 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
     kp.adam_shadow = reinterpret_cast<__nv_bfloat16*>(g->adam_shadow), kp.adam_hyper = g->adam_hyper, kp.adam_keep_grad = g->adam_keep_grad;
   }
   kp.vec_ok = vec ? 1 : 0;
+  // bf16 row-major outputs of the 2-CTA kernel leave through TMA stores (TRIBE_TMA_STORE=0: per-thread 16-byte stores)
+  static const int allow_tma_store = [] {
+    const char* e = getenv("TRIBE_TMA_STORE");
+    return e ? atoi(e) : 1;
+  }();
+  static const int allow_f32_coalesce = [] {
+    const char* e = getenv("TRIBE_EPI_COALESCE");
+    return e ? atoi(e) : 1;
+  }();
+  kp.f32_coalesce = allow_f32_coalesce && use2 && g->d_f32 && !g->d_transposed && !g->adam_p &&
+                    (g->epilogue == TRIBE_EPI_STORE || g->epilogue == TRIBE_EPI_RESIDUAL);
+  if (allow_tma_store && use2 && vec && !g->d_f32 && !g->d_transposed && g->batch == 1 && !g->adam_p && g->ldd % 8 == 0) {
+    rc = encode_out_bf16(g->d, g->n, g->m, g->ldd, &kp.tmd);
+    if (rc) return rc;
+    if (g->epilogue == TRIBE_EPI_GELU) {
+      rc = encode_out_bf16(g->aux_out, g->n, g->m, g->ld_aux, &kp.tmaux);
+      if (rc) return rc;
+    }
+    kp.tma_store = 1;
+  }
 
   // ---- schedule: whole tiles round-robin; the ragged last wave is split along K when a workspace is provided
   const int workers_max = use2 ? num_sms() / 2 : (small ? 2 * num_sms() : num_sms());  // persistent CTAs, or CTA pairs

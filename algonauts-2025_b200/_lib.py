@@ -88,7 +88,8 @@ def _build_locked(verbose: bool) -> None:
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB_PATH + f".tmp{os.getpid()}"
-    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
+    # the arch flag at the link step too: without it nvcc's device-link stub is an (empty) sm_52 cubin
+    r = subprocess.run([nvcc, *NVCC_FLAGS[:2], "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise TribeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
@@ -194,10 +195,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if _stale():
-        build()
+    override = os.environ.get("TRIBE_LIB_OVERRIDE")  # A/B measurements against a library built from another commit
+    if override:
+        path = override
+    else:
+        if _stale():
+            build()
+        path = LIB_PATH
     try:
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
     except OSError as e:  # pragma: no cover
         raise TribeError(f"cannot load {LIB_PATH}: {e} — the CUDA extension is required (no CPU fallback)") from e
     for name, args in _SIGS.items():

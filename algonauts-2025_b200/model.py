@@ -39,8 +39,9 @@ class FmriEncoderConfig(pydantic.BaseModel):
     contrastive_modalities: list[str] = ["video"]
     contrastive_weight: float = 0.1
     contrastive_temperature: float = 0.07
-    # extension (not in the reference schema): arithmetic of the third-party encoder, see FmriEncoder.__init__
-    xt_semantics: tp.Literal["v2", "v1.27"] = "v2"
+    # extension (not in the reference schema, hence excluded from model_dump() — experiment ids / config hashes stay the
+    # reference's): arithmetic of the third-party encoder, see FmriEncoder.__init__
+    xt_semantics: tp.Literal["v2", "v1.27"] = pydantic.Field("v2", exclude=True)
 
     def build(self, feature_dims: dict, n_outputs: int, n_output_timesteps: int) -> nn.Module:
         return FmriEncoder(feature_dims, n_outputs, n_output_timesteps, config=self)

@@ -26,6 +26,11 @@ def test_config_surface_matches_reference():
     assert cfg.model_dump() == {"name": "FmriEncoder", "n_subjects": 4, "feature_aggregation": "cat", "layer_aggregation": "cat",
                                 "subject_embedding": False, "modality_dropout": 0.0, "contrastive_enabled": False,
                                 "contrastive_modalities": ["video"], "contrastive_weight": 0.1, "contrastive_temperature": 0.07}
+    # the one extension field stays out of the dump (config hashes = the reference's) and is validated
+    assert FmriEncoderConfig(n_subjects=4, xt_semantics="v1.27").xt_semantics == "v1.27"
+    assert "xt_semantics" not in FmriEncoderConfig(n_subjects=4, xt_semantics="v1.27").model_dump()
+    with pytest.raises(pydantic.ValidationError):
+        FmriEncoderConfig(n_subjects=4, xt_semantics="v3")
     with pytest.raises(pydantic.ValidationError):
         FmriEncoderConfig(n_subjects=4, bogus=1)  # extra="forbid" (model.py:21)
     with pytest.raises(pydantic.ValidationError):

@@ -82,16 +82,24 @@ def same_on_all_ranks(t, what):
 mine = [batch_of(100 + 10 * rank + i) for i in range(2)]
 everyone = [cat([batch_of(100 + 10 * r + i) for r in range(world)]) for i in range(2)]
 for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
-    base_sd, base_losses, _, base_shadow, base_mom = train(p_drop, "allreduce", False, mine, contrastive=contrastive)
+    # the contrastive step draws two dropout masks (49 variants per batch slot): one slot and 24 steps, so that variants
+    # repeat and the graph runs really replay (a variant is captured at its second sighting)
+    kw = dict(contrastive=contrastive, steps=24) if contrastive else dict(contrastive=contrastive)
+    data = mine[:1] if contrastive else mine
+    base_sd, base_losses, _, base_shadow, base_mom = train(p_drop, "allreduce", False, data, **kw)
     flat = torch.cat([v.flatten().float() for v in base_sd.values()])
     same_on_all_ranks(flat, "allreduce masters")
     # noise floor: the SAME path run twice (atomically accumulated small gradients + Adam's normalisation of tiny gradients)
-    again_sd, again_losses, _, _, again_mom = train(p_drop, "allreduce", False, mine, contrastive=contrastive)
+    again_sd, again_losses, _, _, again_mom = train(p_drop, "allreduce", False, data, **kw)
 
     def deviation(a_sd, b_sd):
         return max(float((a_sd[k].float() - b_sd[k].float()).abs().max()) / (1e-3 + float(b_sd[k].float().abs().max())) for k in a_sd)
 
+    def deviation_l2(a_sd, b_sd):
+        return max(float((a_sd[k].float() - b_sd[k].float()).norm()) / (1e-12 + float(b_sd[k].float().norm())) for k in a_sd)
+
     floor = deviation(again_sd, base_sd)
+    floor_l2 = deviation_l2(again_sd, base_sd)
     floor_mom = float((again_mom - base_mom).abs().max()) / float(base_mom.abs().max())
     if p_drop == 0.0:
         ref_sd, _, _, _, _ = train(0.0, "single", False, everyone)
@@ -101,15 +109,19 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
     for path, graphs in (("staged", False), ("staged", True), ("nvls", True), ("p2p", True), ("allreduce", True)):
         if contrastive and path == "allreduce":
             continue
-        sd, losses, tr, shadow, mom = train(p_drop, path, graphs, mine, contrastive=contrastive)
+        sd, losses, tr, shadow, mom = train(p_drop, path, graphs, data, **kw)
         same_on_all_ranks(torch.cat([v.flatten().float() for v in sd.values()]), f"{path} masters")
         same_on_all_ranks(shadow.view(torch.uint8), f"{path} bf16 shadow")
         if graphs:
             assert tr._graphed.replays >= 1, f"{path}: graphs were not replayed"
         # separate runs differ by the run-to-run noise of the atomically accumulated small gradients (norm gains, residual
         # scales, positional embedding): compare against the all-reduce run like test_graphed_gpu compares graph vs eager
-        worst = deviation(sd, base_sd)
-        assert worst <= 4.0 * floor + 2e-3, (path, graphs, worst, floor)
+        # Adam moves an element whose gradient is ~0 by ~lr per step in a direction the atomics order decides, so the
+        # element-wise maximum is bimodal from run to run (1.8e-2 or 3e-4 for the SAME pair of runs): the criterion is the
+        # relative L2 distance per tensor against the noise floor; the element-wise figure is only bounded grossly
+        worst, worst_l2 = deviation(sd, base_sd), deviation_l2(sd, base_sd)
+        assert worst_l2 <= max(10.0 * floor_l2, 5e-3), (path, graphs, worst_l2, floor_l2)
+        assert worst <= max(4.0 * floor, 5e-2), (path, graphs, worst, floor)
         same_on_all_ranks(mom, f"{path} gathered Adam moments")
         dev_mom = float((mom - base_mom).abs().max()) / float(base_mom.abs().max())
         assert dev_mom <= 4.0 * floor_mom + 1e-3, (path, "Adam moments", dev_mom, floor_mom)
@@ -117,7 +129,8 @@ for p_drop, contrastive in ((0.0, False), (0.5, False), (0.5, True)):
         dist.barrier()
         if rank == 0:
             print(f"dp train check p_drop={p_drop} contrastive={contrastive} path={path} graphs={graphs}: ranks bit-identical, "
-                  f"relative deviation from the all-reduce run {worst:.1e} (two all-reduce runs differ by {floor:.1e}), Adam moments {dev_mom:.1e} ({floor_mom:.1e})", flush=True)
+                  f"relative L2 deviation from the all-reduce run {worst_l2:.1e} (two all-reduce runs differ by {floor_l2:.1e}; element-wise max {worst:.1e} / {floor:.1e}), "
+                  f"Adam moments {dev_mom:.1e} ({floor_mom:.1e})", flush=True)
 
 # ---- the Lightning route: BrainModule.configure_optimizers installs the gradient path itself in a multi-rank job;
 # torch DDP around the module is a harmless no-op (its reducer never sees a gradient); a bare model fails loudly

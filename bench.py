@@ -530,7 +530,9 @@ def eval_sweep_leg(model, rank, world, n_windows: int = EVAL_WINDOWS, batch: int
     host = [synthetic_batch(batch_size=batch, seed=4321 + 31 * rank + i, pin=True) for i in range(2)]
     prefetch = DevicePrefetcher(())
     model.eval()
-    metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(2)), distributed="parcels", n_windows=2 * batch)  # warm-up
+    # warm-up = one full-size pass: NCCL connects the channels of a peer pair lazily, and a 256 MB all-to-all uses more of
+    # them than a small one (measured: first large exchange 0.4-4 s, steady state 0.8 ms; tools/a2a_probe.py)
+    metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(n_batches)), distributed="parcels", n_windows=per_rank)
     _barrier(world)
     timings = {}
     t0 = time.perf_counter()

@@ -496,17 +496,22 @@ def ensemble_eval_leg(model, rank, world, B):
     shared = [synthetic_batch(batch_size=B, seed=999 + i) for i in range(4)]
     shared = [type(b)(data={k: v.cuda() for k, v in b.data.items()}, segments=b.segments) for b in shared]
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.no_grad():
-        model(shared[0])
-        _barrier(world)
-        f0.record()
+
+    def evaluate():
         preds = torch.empty(4 * B, 1000, 100, device="cuda")
         for i, b in enumerate(shared):
             model(b, out=preds[i * B:(i + 1) * B])                              # this member's predictions, written in place
         trues = torch.cat([b.data["fmri"] for b in shared])
         r_member = ops.pearson_r(preds, trues, layout="bdt")[0]                # (O,) per-parcel r of this member
         ens = parallel.ensemble_average(preds, r_member, temperature=0.3)      # weighted all-reduce (reference weighting)
-        r_ens, mean_ens = ops.pearson_r(ens.contiguous(), trues, layout="bdt", want_mean=True)
+        _, mean_ens = ops.pearson_r(ens.contiguous(), trues, layout="bdt", want_mean=True)
+        return r_member, mean_ens
+
+    with torch.no_grad():
+        evaluate()  # warm-up pass: NCCL sets up its channels for this message size on first use (0.2 s once)
+        _barrier(world)
+        f0.record()
+        r_member, mean_ens = evaluate()
         f1.record()
     _barrier(world)
     (ms_eval,) = _max_over_ranks([f0.elapsed_time(f1)], world)
@@ -533,13 +538,19 @@ def eval_sweep_leg(model, rank, world, n_windows: int = EVAL_WINDOWS, batch: int
     # warm-up = one full-size pass: NCCL connects the channels of a peer pair lazily, and a 256 MB all-to-all uses more of
     # them than a small one (measured: first large exchange 0.4-4 s, steady state 0.8 ms; tools/a2a_probe.py)
     metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(n_batches)), distributed="parcels", n_windows=per_rank)
-    _barrier(world)
-    timings = {}
-    t0 = time.perf_counter()
-    r = metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(n_batches)), distributed="parcels",
-                                         n_windows=per_rank, timings=timings)
-    wall = time.perf_counter() - t0
-    torch.cuda.synchronize()
+    best = None
+    for _ in range(2):  # two timed passes, the faster one is reported (the set is small: 2560 windows = 0.2 s at 8 GPUs)
+        _barrier(world)
+        timings = {}
+        t0 = time.perf_counter()
+        r = metrics.compute_multidim_pearson(model, prefetch.feed(host[j % 2] for j in range(n_batches)), distributed="parcels",
+                                             n_windows=per_rank, timings=timings)
+        wall = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        (wall_max,) = _max_over_ranks([wall], world)
+        if best is None or wall_max < best[0]:
+            best = (wall_max, wall, timings, r)
+    _, wall, timings, r = best
     assert r.shape == (EVAL_PARCELS,) and np_isfinite(r)
     stage = {k: v[0].elapsed_time(v[-1]) for k, v in timings.items() if len(v) >= 2}
     vals = _max_over_ranks([wall] + [stage.get(k, 0.0) for k in ("predict", "exchange", "pearson", "gather")], world)

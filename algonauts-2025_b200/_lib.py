@@ -139,6 +139,7 @@ _SIGS = {
     "tribe_gemm_set_sm_limit": [c_i32],
     "tribe_set_pdl": [c_i32],
     "tribe_attn_scores": [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp, c_vp, c_i64, c_vp],
+    "tribe_attn_fwd": [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp],
     "tribe_ingest_features": [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp],
     "tribe_scalenorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_f32, c_vp],
     "tribe_sublayer_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_vp],

@@ -294,6 +294,278 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused forward
+// Flash-style forward of one (batch, head, 128-query block) per tile: S = Q K^T in TMEM -> row softmax by the epilogue
+// threads (as in mode 0) -> P written as bf16 into SHARED memory in the canonical K-major SWIZZLE_128B layout -> the MMA
+// thread multiplies it with V (streamed through the same TMA ring as MN-major B tiles) into TMEM columns that re-use
+// the score columns -> the epilogue drains O.  P reaches HBM only when the caller wants it (training: the backward
+// reads it); an evaluation pass never writes it.  One launch instead of two (attn_scores + the batched P.V GEMM), Q is
+// loaded once, P never round-trips.  Requires 160 < T <= 320 (two score parts, five 64-key blocks of P) and a head
+// dim that is 64, 128, 192, 256 or 2 x {64..256 step 64} (O is accumulated as one or two N-halves).
+constexpr int kFwdStages = 2;
+constexpr int kFwdPBytes = 5 * BM * BK * 2;  // 80 KiB: P tile 128 x 320 bf16 as five K-major SW128 k-blocks
+constexpr int kFwdSmem = kFwdStages * kAttnStage + kFwdPBytes + 256 + 1024;
+
+struct alignas(64) AttnFwdParams {
+  CUtensorMap tmq, tmk, tmv;
+  int T, Tp, heads, dh, num_kb, m_blocks, num_tiles;
+  int q_off, k_off, v_off;
+  int n_halves, half_n;
+  float scale;
+  __nv_bfloat16* p_out;  // optional (Z, T, Tp)
+  __nv_bfloat16* o_out;  // (n_batch * T, o_ld), head h at columns o_off + h * dh
+  long long o_ld;
+  int o_off;
+  uint32_t k_lbo, k_sbo, mn_lbo, mn_sbo;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* p_s = smem + kFwdStages * kAttnStage;  // 1 KiB aligned (stage size is a multiple of 1 KiB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(p_s + kFwdPBytes);
+  uint64_t* empty_bar = full_bar + kFwdStages;
+  uint64_t* sfull_bar = empty_bar + kFwdStages;  // MMA -> epilogue: scores complete
+  uint64_t* pready_bar = sfull_bar + 1;          // epilogue (128 threads) -> MMA: P tile in shared memory, S columns free
+  uint64_t* ofull_bar = pready_bar + 1;          // MMA -> epilogue: O complete
+  uint64_t* tempty_bar = ofull_bar + 1;          // epilogue (128 threads) -> MMA: TMEM free for the next tile
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmq);
+    prefetch_tmap(&p.tmk);
+    prefetch_tmap(&p.tmv);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kFwdStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(sfull_bar, 1);
+      mbar_init(pready_bar, 128);
+      mbar_init(ofull_bar, 1);
+      mbar_init(tempty_bar, 128);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  constexpr int kVkb = 5;  // 64-key blocks of the P.V contraction (keys >= T: zero columns of P, zero-filled rows of V)
+  const uint32_t v_tx = static_cast<uint32_t>(p.dh) * BK * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int z = tile / p.m_blocks, mb = tile - z * p.m_blocks;
+        const int b = z / p.heads, h = z - b * p.heads;
+        for (int kb = 0; kb < p.num_kb; ++kb) {  // Q and K over the head dims
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kAttnStage;
+          uint8_t* sb = sa + kAttnAB;
+          mbar_expect_tx(&full_bar[stage], kAttnAB + 2 * kAttnBB);
+          tma_load_3d(sa, &p.tmq, &full_bar[stage], p.q_off + h * p.dh + kb * BK, mb * BM, b);
+          for (int j = 0; j < 2; ++j) tma_load_3d(sb + j * kAttnBB, &p.tmk, &full_bar[stage], p.k_off + h * p.dh + kb * BK, j * kAttnNP, b);
+          if (++stage == kFwdStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        for (int kb = 0; kb < kVkb; ++kb) {  // V over the keys: dh / 64 boxes of (64 dims x 64 keys), MN-major B tiles
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sv = smem + stage * kAttnStage;
+          mbar_expect_tx(&full_bar[stage], v_tx);
+          for (int j = 0; j < p.dh / 64; ++j) tma_load_3d(sv + j * (BK * 128), &p.tmv, &full_bar[stage], p.v_off + h * p.dh + j * 64, kb * BK, b);
+          if (++stage == kFwdStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BM, kAttnNP, false, false);
+      const uint32_t idesc_o = make_idesc_bf16(BM, p.half_n, false, true);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar, tphase ^ 1);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kAttnStage);
+          const uint32_t sb = sa + kAttnAB;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_smem_desc(sa + kk * 32, p.k_lbo, p.k_sbo);
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t db = make_smem_desc(sb + j * kAttnBB + kk * 32, p.k_lbo, p.k_sbo);
+              umma_bf16(tmem_base + j * kAttnNP, da, db, idesc_s, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kFwdStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(sfull_bar);
+        // ---- O = P V: A = the P tile the epilogue threads wrote, B = V k-blocks from the ring, D re-uses the S columns
+        mbar_wait(pready_bar, tphase);
+        tc_fence_after();
+        accumulate = 0;
+        for (int kb = 0; kb < kVkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sp = smem_u32(p_s + kb * (BM * BK * 2));
+          const uint32_t sv = smem_u32(smem + stage * kAttnStage);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_smem_desc(sp + kk * 32, p.k_lbo, p.k_sbo);
+            for (int hf = 0; hf < p.n_halves; ++hf) {
+              const uint64_t db = make_smem_desc(sv + hf * (p.half_n / 64) * (BK * 128) + kk * (16 * 128), p.mn_lbo, p.mn_sbo);
+              umma_bf16(tmem_base + hf * p.half_n, da, db, idesc_o, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kFwdStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(ofull_bar);
+        tphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    constexpr int nchunks = 2 * (kAttnNP / 32);  // 10 chunks = 320 score columns
+    const float sl2 = p.scale * 1.4426950408889634f;
+    uint8_t* p_row = p_s + row_in_tile * 128;    // this query row inside every k-block tile
+    const int swz = row_in_tile & 7;
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int z = tile / p.m_blocks, mb = tile - z * p.m_blocks;
+      const int b = z / p.heads, h = z - b * p.heads;
+      const int row = mb * BM + row_in_tile;
+      const bool row_ok = row < p.T;
+      const long long roff = (static_cast<long long>(z) * p.T + row) * p.Tp;
+      mbar_wait(sfull_bar, tphase);
+      tc_fence_after();
+      constexpr int G = 4;
+      uint32_t rg[G][32];
+      constexpr int ngroups = (nchunks + G - 1) / G;
+      auto load_group = [&](int g) {
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+          if (g * G + i < nchunks) tmem_ld_32x32(t_addr + (g * G + i) * 32, rg[i]);
+        tmem_ld_wait();
+      };
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int g = 0; g < ngroups; ++g) {
+        if (g * G * 32 >= p.T) break;
+        load_group(g);
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int col0 = (g * G + i) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.T) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rg[i][j]));
+        }
+      }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float msl = m * sl2;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int g = 0; g < ngroups; ++g) {
+        if (g * G * 32 >= p.T) break;
+        load_group(g);
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int col0 = (g * G + i) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.T) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+        }
+      }
+      const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      for (int g = 0; g < ngroups; ++g) {  // every one of the 320 columns goes to shared memory (zeros past T)
+        load_group(g);
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          if (g * G + i >= nchunks) continue;
+          const int col0 = (g * G + i) * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
+          uint8_t* kb_row = p_row + (col0 >> 6) * (BM * BK * 2);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const uint4 pk = attn_pack8(v + g8 * 8);
+            const int c = ((col0 & 63) >> 3) + g8;  // 16-byte chunk inside the 128-byte row of this k-block
+            *reinterpret_cast<uint4*>(kb_row + ((c ^ swz) << 4)) = pk;
+            if (p.p_out && row_ok && col0 + g8 * 8 < p.Tp) *reinterpret_cast<uint4*>(p.p_out + roff + col0 + g8 * 8) = pk;
+          }
+        }
+      }
+      fence_proxy_async();  // the P tile was written through the generic proxy; tcgen05.mma reads it through the async proxy
+      tc_fence_before();
+      mbar_arrive(pready_bar);
+      // ---- drain O
+      mbar_wait(ofull_bar, tphase);
+      tc_fence_after();
+      __nv_bfloat16* orow = p.o_out + (static_cast<long long>(b) * p.T + row) * p.o_ld + p.o_off + h * p.dh;
+      const int ochunks = p.dh / 32;
+      for (int g = 0; g * G < ochunks; ++g) {
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+          if (g * G + i < ochunks) tmem_ld_32x32(t_addr + (g * G + i) * 32, rg[i]);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            if (g * G + i >= ochunks) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rg[i][j]);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) *reinterpret_cast<uint4*>(orow + (g * G + i) * 32 + g8 * 8) = attn_pack8(v + g8 * 8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar);
+      tphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace tribe
 
 extern "C" int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, const void* b, int64_t b_ld, int64_t b_off, int64_t n_batch,
@@ -340,5 +612,55 @@ extern "C" int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, con
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "attn_scores launch");
+  return TRIBE_OK;
+}
+
+extern "C" int tribe_attn_fwd(const void* q, int64_t q_ld, int64_t q_off, const void* k, int64_t k_ld, int64_t k_off, const void* v, int64_t v_ld,
+                              int64_t v_off, int64_t n_batch, int64_t T, int64_t heads, int64_t dh, float scale, void* p_out, int64_t Tp,
+                              void* o_out, int64_t o_ld, int64_t o_off, void* stream) {
+  using namespace tribe;
+  if (!q || !k || !v || !o_out || n_batch <= 0 || T <= 0 || heads <= 0 || dh <= 0) return set_error(TRIBE_EINVAL, "attn_fwd: bad arguments");
+  if (dh % BK || T <= kAttnNP || T > 2 * kAttnNP || Tp < T || Tp > 2 * kAttnNP || Tp % 8)
+    return set_error(TRIBE_EINVAL, "attn_fwd: needs head_dim % 64 == 0, 160 < T <= Tp <= 320, Tp % 8 == 0");
+  const int n_halves = dh > 256 ? 2 : 1;
+  const int64_t half_n = dh / n_halves;
+  if (half_n % 64 || half_n > 256 || dh * BK * 2 > kAttnStage) return set_error(TRIBE_EINVAL, "attn_fwd: head_dim must be 64..256 or 2 x (64..256), multiples of 64");
+  if ((reinterpret_cast<uintptr_t>(o_out) | reinterpret_cast<uintptr_t>(p_out)) & 15 || o_ld % 8 || o_off % 8)
+    return set_error(TRIBE_EINVAL, "attn_fwd: outputs must be 16-byte aligned");
+  AttnFwdParams kp;
+  memset(&kp, 0, sizeof(kp));
+  TribeOperand oq, ok, ov;
+  memset(&oq, 0, sizeof(oq)), memset(&ok, 0, sizeof(ok)), memset(&ov, 0, sizeof(ov));
+  oq.ptr = q, oq.inner = q_ld, oq.rows = T, oq.batch = n_batch, oq.row_stride = q_ld, oq.batch_stride = T * q_ld;
+  ok.ptr = k, ok.inner = k_ld, ok.rows = T, ok.batch = n_batch, ok.row_stride = k_ld, ok.batch_stride = T * k_ld;
+  ov.ptr = v, ov.inner = v_ld, ov.rows = T, ov.batch = n_batch, ov.row_stride = v_ld, ov.batch_stride = T * v_ld;
+  int rc = encode_operand(oq, BM, &kp.tmq);
+  if (rc) return rc;
+  rc = encode_operand(ok, kAttnNP, &kp.tmk);
+  if (rc) return rc;
+  rc = encode_operand(ov, BK, &kp.tmv);  // MN-major operand: boxes of 64 dims x 64 keys
+  if (rc) return rc;
+  kp.T = static_cast<int>(T), kp.Tp = static_cast<int>(Tp), kp.heads = static_cast<int>(heads), kp.dh = static_cast<int>(dh);
+  kp.num_kb = static_cast<int>(dh / BK);
+  kp.m_blocks = static_cast<int>((T + BM - 1) / BM);
+  kp.num_tiles = static_cast<int>(kp.m_blocks * n_batch * heads);
+  kp.q_off = static_cast<int>(q_off), kp.k_off = static_cast<int>(k_off), kp.v_off = static_cast<int>(v_off);
+  kp.n_halves = n_halves, kp.half_n = static_cast<int>(half_n);
+  kp.scale = scale;
+  kp.p_out = reinterpret_cast<__nv_bfloat16*>(p_out);
+  kp.o_out = reinterpret_cast<__nv_bfloat16*>(o_out);
+  kp.o_ld = o_ld, kp.o_off = static_cast<int>(o_off);
+  kp.k_lbo = 16, kp.k_sbo = 1024, kp.mn_lbo = BK * 128, kp.mn_sbo = 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attn_fwd)");
+    attr_set = true;
+  }
+  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  cudaError_t le = launch_k(attn_fwd_kernel, dim3(grid), dim3(kGemmThreads), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), kp);
+  count_launch();
+  if (le == cudaSuccess) le = cudaGetLastError();
+  if (le != cudaSuccess) return set_cuda_error(le, "attn_fwd launch");
   return TRIBE_OK;
 }

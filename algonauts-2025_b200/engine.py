@@ -193,6 +193,7 @@ class Plan:
         self.training = False
         self.out = None         # optional preallocated (B, O, T') fp32 output (evaluation sweeps write predictions in place)
         self.awaiting = None    # the Engine that counts this plan among its grad-enabled forwards awaiting a backward
+        self.keep = True        # a backward may follow: keep what it reads (attention probabilities); False under no_grad
 
     def settle(self):
         eng, self.awaiting = self.awaiting, None
@@ -402,19 +403,24 @@ class Engine:
             else:
                 ops.gemm(ops.kmajor(ws.xn[ia]), ops.kmajor(self._wqkv16(a)), qkv, M, 3 * H, H, ldd=3 * H, epilogue=ops.EPI_ROPE,
                          rope=rope, rope_t=T, rope_dim=self.rot, head_dim=dh, rope_cols=2 * H)
-            if ops.attn_fusable(T, dh):
-                # P = softmax(q k^T d^-1/2) formed in the tcgen05 epilogue: whole score rows live in TMEM, no fp32 S in HBM
-                ops.attn_scores(qkv, 0, qkv, H, B, T, heads, dh, scale, ws.P[l])
+            if ops.attn_fwd_fusable(T, dh):
+                # flash-style forward, one launch: S in TMEM -> softmax -> P as the shared-memory A operand of P.V -> O;
+                # P goes to HBM only when a backward will read it
+                ops.attn_fwd(qkv, 0, H, 2 * H, B, T, heads, dh, scale, ws.attn[l], p_out=ws.P[l] if plan.keep else None)
             else:
-                q_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, zin_stride=dh, zdiv=heads)
-                k_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, inner_off=H, zin_stride=dh,
-                                   zdiv=heads)
-                ops.gemm(q_op, k_op, ws.S, T, T, dh, ldd=Tp, batch=BH, z_inner=heads, d_zo=heads * T * Tp, d_zi=T * Tp, alpha=scale)
-                ops.softmax_fwd(ws.S, ws.P[l], T)
-            p_op = ops.Operand(ws.P[l], inner=Tp, rows=T, row_stride=Tp, batch=BH, batch_stride=T * Tp)
-            v_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, mn_major=True,
-                               inner_off=2 * H, zin_stride=dh, zdiv=heads)
-            ops.gemm(p_op, v_op, ws.attn[l], T, dh, Tp, ldd=H, batch=BH, z_inner=heads, d_zo=T * H, d_zi=dh)
+                if ops.attn_fusable(T, dh):
+                    # P = softmax(q k^T d^-1/2) formed in the tcgen05 epilogue: whole score rows live in TMEM, no fp32 S in HBM
+                    ops.attn_scores(qkv, 0, qkv, H, B, T, heads, dh, scale, ws.P[l])
+                else:
+                    q_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, zin_stride=dh, zdiv=heads)
+                    k_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, inner_off=H, zin_stride=dh,
+                                       zdiv=heads)
+                    ops.gemm(q_op, k_op, ws.S, T, T, dh, ldd=Tp, batch=BH, z_inner=heads, d_zo=heads * T * Tp, d_zi=T * Tp, alpha=scale)
+                    ops.softmax_fwd(ws.S, ws.P[l], T)
+                p_op = ops.Operand(ws.P[l], inner=Tp, rows=T, row_stride=Tp, batch=BH, batch_stride=T * Tp)
+                v_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=B, batch_stride=T * 3 * H, mn_major=True,
+                                   inner_off=2 * H, zin_stride=dh, zdiv=heads)
+                ops.gemm(p_op, v_op, ws.attn[l], T, dh, Tp, ldd=H, batch=BH, z_inner=heads, d_zo=T * H, d_zi=dh)
             ops.gemm(ops.kmajor(ws.attn[l]), ops.kmajor(self._w16(f"{a}.1.to_out.weight")), ws.xs[ia + 1], M, H, H, ldd=H,
                      epilogue=ops.EPI_RESIDUAL, res=ws.xs[ia], ld_res=H, rscale=self._p(f"{a}.2.residual_scale"))
             # ---- feed-forward sub-layer

@@ -424,6 +424,7 @@ class FmriEncoder(nn.Module):
                 if plan.subjects.numel() != x_in.shape[0]:
                     raise TribeError(f"transformer_forward: {plan.subjects.numel()} subject ids for a batch of {x_in.shape[0]}")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        plan.keep = needs_grad
         if needs_grad:
             self._check_gradient_sync()
             out = _Fn.apply(self._anchor(), x_in, eng, plan, data)

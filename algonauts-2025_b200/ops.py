@@ -489,6 +489,33 @@ def attn_scores(a, a_off: int, b, b_off: int, n_batch: int, T: int, heads: int, 
          0 if p_in is None else 1, _ptr(p_in), _ptr(out), out.shape[-1], _stream())
 
 
+# opt-in: correct and one launch instead of two, but measured slower than the two-launch path at TRIBE's shape
+FUSED_ATTN_FWD = bool(int(__import__("os").environ.get("TRIBE_FUSED_ATTN_FWD", "0")))
+
+
+def attn_fwd_fusable(T: int, dh: int) -> bool:
+    """The flash-style forward (scores + softmax + P.V in one launch) needs two score parts (160 < T <= 320) and a head dim
+    that splits into one or two MMA-N halves of 64..256."""
+    return FUSED_ATTN and FUSED_ATTN_FWD and attn_fwd_supported(T, dh)
+
+
+def attn_fwd_supported(T: int, dh: int) -> bool:
+    half = dh // 2 if dh > 256 else dh
+    return 160 < T <= 320 and dh % 64 == 0 and half % 64 == 0 and half <= 256 and dh <= 448
+
+
+def attn_fwd(qkv, q_off: int, k_off: int, v_off: int, n_batch: int, T: int, heads: int, dh: int, scale: float, out, out_off: int = 0, *,
+             p_out=None) -> None:
+    """out[(b, t), out_off + h*dh + :] = softmax(scale * q k^T) v per (batch, head); q / k / v are column blocks of the packed
+    bf16 (n_batch * T, ld) buffer ``qkv``; ``p_out`` (optional bf16 (n_batch*heads, T, Tp)) receives P for the backward."""
+    _need(qkv, torch.bfloat16, "attn qkv"), _need(out, torch.bfloat16, "attn out")
+    if p_out is not None:
+        _need(p_out, torch.bfloat16, "attn P")
+    Tp = p_out.shape[-1] if p_out is not None else (T + 7) // 8 * 8
+    _run("tribe_attn_fwd", _ptr(qkv), qkv.shape[-1], q_off, _ptr(qkv), qkv.shape[-1], k_off, _ptr(qkv), qkv.shape[-1], v_off, n_batch, T, heads, dh,
+         float(scale), _ptr(p_out), Tp, _ptr(out), out.shape[-1], out_off, _stream())
+
+
 def zero_(t) -> None:
     """Stream-ordered zero fill of a contiguous CUDA tensor (cudaMemsetAsync through the C ABI; capturable)."""
     if not t.is_contiguous():

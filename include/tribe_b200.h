@@ -145,6 +145,15 @@ int tribe_gemm_bf16(const TribeGemm* g, void* stream);
  * Requires dh % 64 == 0, T <= Tp <= 320, Tp % 8 == 0. */
 int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, const void* b, int64_t b_ld, int64_t b_off, int64_t n_batch, int64_t T,
                       int64_t heads, int64_t dh, float scale, int32_t mode, const void* p_in, void* out, int64_t Tp, void* stream);
+/* Flash-style attention forward, one launch per layer: O = softmax(scale * q k^T) v per (batch, head) with the scores and
+ * the probabilities never leaving the SM (S in TMEM, P as the shared-memory A operand of P.V); replaces tribe_attn_scores
+ * (mode 0) + the batched P.V GEMM.  q / k / v: bf16 row-major (n_batch * T, ld) with head h at columns [off + h*dh, ...);
+ * p_out: optional bf16 (n_batch*heads, T, Tp) copy of P (the training backward reads it; NULL for inference);
+ * o_out: bf16 (n_batch * T, o_ld), head h at columns [o_off + h*dh, ...).
+ * Requires 160 < T <= Tp <= 320, Tp % 8 == 0, dh a multiple of 64 that is <= 256 or twice such a value (<= 448). */
+int tribe_attn_fwd(const void* q, int64_t q_ld, int64_t q_off, const void* k, int64_t k_ld, int64_t k_off, const void* v, int64_t v_ld,
+                   int64_t v_off, int64_t n_batch, int64_t T, int64_t heads, int64_t dh, float scale, void* p_out, int64_t Tp, void* o_out,
+                   int64_t o_ld, int64_t o_off, void* stream);
 /* Persistent GEMM grids use at most n_sms SMs from the next launch on (0 = all).  While a collective's CTAs occupy SMs
  * next to the backward pass, a one-CTA-per-SM grid would wait a whole kernel for the occupied SMs; a smaller grid runs
  * beside them (parallel.StepOverlap sets / clears this around the gradient all-reduces). */

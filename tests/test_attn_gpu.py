@@ -48,3 +48,45 @@ def test_fused_attention_rejects_unsupported_shapes():
     with pytest.raises(algonauts2025_b200.TribeError):
         ops.attn_scores(x, 0, x, 64, 1, 400, 1, 64, 0.125, out)   # 400 keys do not fit one TMEM accumulator
     assert not ops.attn_fusable(400, 64) and not ops.attn_fusable(298, 96) and ops.attn_fusable(298, 384) == ops.FUSED_ATTN
+
+
+@pytest.mark.parametrize("Bsz,T,heads,dh", [(2, 298, 8, 384), (1, 200, 2, 128), (1, 320, 2, 64), (2, 161, 1, 256), (3, 298, 2, 192)])
+@pytest.mark.parametrize("keep_p", [True, False])
+def test_flash_style_forward_matches_scores_then_pv(Bsz, T, heads, dh, keep_p):
+    """tribe_attn_fwd: softmax(q k^T d^-1/2) v in ONE launch (S in TMEM, P as the shared-memory A operand of P.V) against
+    (a) plain torch fp32 attention on the same bf16 operands and (b) the two-launch path it replaces (tribe_attn_scores +
+    batched P.V GEMM): the P it optionally stores is bit-identical to the scores kernel's, O agrees to bf16 rounding."""
+    torch.manual_seed(T + dh)
+    H = heads * dh
+    Tp = (T + 7) // 8 * 8
+    assert ops.attn_fwd_supported(T, dh)
+    qkv = (torch.randn(Bsz * T, 3 * H, device=DEV) * 1.2).to(torch.bfloat16)
+    scale = dh ** -0.5
+    out = torch.full((Bsz * T, H), float("nan"), device=DEV, dtype=torch.bfloat16)
+    P = torch.full((Bsz * heads, T, Tp), float("nan"), device=DEV, dtype=torch.bfloat16) if keep_p else None
+    ops.attn_fwd(qkv, 0, H, 2 * H, Bsz, T, heads, dh, scale, out, p_out=P)
+    q4 = qkv.float().view(Bsz, T, 3, heads, dh)
+    S = torch.einsum("bihd,bjhd->bhij", q4[:, :, 0], q4[:, :, 1]) * scale
+    ref = torch.einsum("bhij,bjhd->bihd", S.softmax(-1), q4[:, :, 2]).reshape(Bsz * T, H)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= 1.5e-2 * float(ref.abs().max())
+    # the path it replaces
+    P2 = torch.empty(Bsz * heads, T, Tp, device=DEV, dtype=torch.bfloat16)
+    ops.attn_scores(qkv, 0, qkv, H, Bsz, T, heads, dh, scale, P2)
+    out2 = torch.empty(Bsz * T, H, device=DEV, dtype=torch.bfloat16)
+    p_op = ops.Operand(P2, inner=Tp, rows=T, row_stride=Tp, batch=Bsz * heads, batch_stride=T * Tp)
+    v_op = ops.Operand(qkv, inner=3 * H, rows=T, row_stride=3 * H, batch=Bsz, batch_stride=T * 3 * H, mn_major=True, inner_off=2 * H,
+                       zin_stride=dh, zdiv=heads)
+    ops.gemm(p_op, v_op, out2, T, dh, Tp, ldd=H, batch=Bsz * heads, z_inner=heads, d_zo=T * H, d_zi=dh)
+    if keep_p:
+        assert torch.equal(P, P2)
+    assert float((got - out2.float()).abs().max()) <= 8e-3 * float(ref.abs().max())
+
+
+def test_flash_style_forward_rejects_unsupported_shapes():
+    assert not ops.attn_fwd_supported(74, 64) and not ops.attn_fwd_supported(400, 64) and not ops.attn_fwd_supported(298, 96)
+    assert ops.attn_fwd_supported(298, 384)
+    x = torch.zeros(74, 3 * 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(algonauts2025_b200.TribeError):
+        ops.attn_fwd(x, 0, 64, 128, 1, 74, 1, 64, 0.125, torch.zeros(74, 64, device=DEV, dtype=torch.bfloat16))

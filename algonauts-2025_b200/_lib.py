@@ -138,6 +138,8 @@ _SIGS = {
     "tribe_gemm_bf16_probe": [ctypes.POINTER(TribeGemm), c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
     "tribe_gemm_set_sm_limit": [c_i32],
     "tribe_set_pdl": [c_i32],
+    "tribe_peek_last_error": [],
+    "tribe_take_last_error": [],
     "tribe_attn_scores": [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp, c_vp, c_i64, c_vp],
     "tribe_attn_fwd": [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp],
     "tribe_ingest_features": [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp],

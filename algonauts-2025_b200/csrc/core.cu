@@ -1,5 +1,6 @@
 // Error reporting and launch accounting for the C ABI (include/tribe_b200.h).
 #include <atomic>
+#include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,6 +35,8 @@ bool pdl_enabled() {
 
 extern "C" const char* tribe_last_error(void) { return tribe::g_err; }
 extern "C" int tribe_abi_version(void) { return 1; }
+extern "C" int tribe_peek_last_error(void) { return static_cast<int>(cudaPeekAtLastError()); }
+extern "C" int tribe_take_last_error(void) { return static_cast<int>(cudaGetLastError()); }
 extern "C" int tribe_set_pdl(int32_t on) {
   tribe::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
   return TRIBE_OK;

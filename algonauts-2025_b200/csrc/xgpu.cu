@@ -323,8 +323,9 @@ extern "C" int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream) 
 extern "C" int tribe_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream) {
   if (!dst || !src || n_bytes < 0) return set_error(TRIBE_EINVAL, "memcpy_async: bad arguments");
   if (n_bytes == 0) return TRIBE_OK;
-  // copy-engine transfer (no SM): local -> peer-mapped symmetric memory over NVLink, or device-local
-  cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(n_bytes), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream));
+  // copy-engine transfer (no SM): local -> peer-mapped symmetric memory over NVLink, device-local, or device -> pinned
+  // host (the direction is inferred from the unified address space)
+  cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(n_bytes), cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return set_cuda_error(e, "memcpy_async");
   return TRIBE_OK;
 }

@@ -113,6 +113,9 @@ class GraphedTrainStep:
         model, opt = tr.module.model, tr.optimizer
         opt.init_all_state()
         model.flush_subject_check()
+        from . import ops
+
+        ops.drain_stale_error("before a CUDA-graph capture")  # a stale error would abort the capture at its first checked call
         model._preset_dropped = [list(m) for m in masks]
         graph = torch.cuda.CUDAGraph()
         lib = _lib.load()

@@ -340,6 +340,7 @@ class FmriEncoder(nn.Module):
         flags = self.__dict__.get("_subject_flags")
         if flags is not None:
             torch.cuda.current_stream(flags[0].device).synchronize()
+            ops.drain_stale_error("before reading the subject-range flag")
             bad = int(flags[0].item())
             flags[0].zero_()
             flags[1].zero_()
@@ -368,7 +369,7 @@ class FmriEncoder(nn.Module):
             safe = torch.empty_like(subj)  # ids clamped into range: the enqueued step stays in bounds until the flag is read
             ops.check_subjects(subj, n, dev_flag, safe)
             subj = safe
-            host_flag.copy_(dev_flag, non_blocking=True)
+            ops.copy_to_pinned(host_flag, dev_flag)  # (not Tensor.copy_: see ops.copy_to_pinned)
             self.__dict__["_subject_event"] = None
             if not torch.cuda.is_current_stream_capturing():  # graph replays poll host_flag themselves (graphed.py)
                 event = torch.cuda.Event()

@@ -29,10 +29,36 @@ def _ptr(t):
 _DEBUG_CAPTURE = bool(int(__import__("os").environ.get("TRIBE_DEBUG_CAPTURE", "0")))
 
 
+_DEBUG_LASTERR = bool(int(__import__("os").environ.get("TRIBE_DEBUG_LASTERR", "0")))
+
+
+def peek_last_error(where: str) -> None:
+    """Debugging aid: raise when the CUDA runtime's (non-sticky) last-error slot is set — some earlier call failed without
+    anyone consuming its error, and torch would report it at an unrelated later call."""
+    rc = int(_lib.load().tribe_peek_last_error())
+    if rc:
+        raise TribeError(f"CUDA last-error {rc} is set {where}")
+
+
+def drain_stale_error(where: str) -> int:
+    """Clear a non-sticky CUDA error somebody else left in the runtime's last-error slot (every call of this library
+    consumes its own), so that torch does not report it at the synchronisation that follows; warns with the code."""
+    rc = int(_lib.load().tribe_take_last_error())
+    if rc:
+        import warnings
+
+        warnings.warn(f"cleared a stale CUDA runtime error ({rc}) found {where}; it was not raised by a tribe kernel", RuntimeWarning, stacklevel=2)
+    return rc
+
+
 def _run(name, *args):
+    if _DEBUG_LASTERR:
+        peek_last_error(f"BEFORE {name} (left behind by torch or by an earlier call)")
     rc = getattr(_lib.load(), name)(*args)
     if rc:
         check(rc, name)
+    if _DEBUG_LASTERR:
+        peek_last_error(f"AFTER {name}")
     if _DEBUG_CAPTURE:  # bisecting a broken CUDA-graph capture: the stream status turns into an error right after the culprit
         try:
             torch.cuda.is_current_stream_capturing()
@@ -530,6 +556,19 @@ def copy_(dst, src) -> None:
         raise TribeError("copy_: contiguous CUDA tensors of equal byte size required")
     if dst.numel():
         _run("tribe_memcpy_async", _ptr(dst), _ptr(src), dst.numel() * dst.element_size(), _stream())
+
+
+def copy_to_pinned(dst_host, src) -> None:
+    """Stream-ordered device -> PINNED host copy through the C ABI (cudaMemcpyAsync, capturable).  Deliberately not
+    ``dst.copy_(src, non_blocking=True)``: torch's caching host allocator then tracks the pinned block's stream uses with
+    events, and an event recorded while the stream was being captured makes a later, unrelated host allocation fail once
+    with "invalid argument" (seen as a flaky ``.item()`` after graph captures)."""
+    if dst_host.is_cuda or not dst_host.is_pinned() or not src.is_cuda or not (dst_host.is_contiguous() and src.is_contiguous()):
+        raise TribeError("copy_to_pinned: contiguous pinned host destination and CUDA source required")
+    if dst_host.numel() * dst_host.element_size() != src.numel() * src.element_size():
+        raise TribeError("copy_to_pinned: sizes differ")
+    if src.numel():
+        _run("tribe_memcpy_async", ctypes.c_void_p(dst_host.data_ptr()), _ptr(src), src.numel() * src.element_size(), _stream())
 
 
 def scale_dev(src, scalar):

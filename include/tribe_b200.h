@@ -44,6 +44,14 @@ int64_t tribe_launch_count(void);
  * the predecessor's completion before touching memory).  Off by default (measured neutral inside whole-step CUDA
  * graphs); TRIBE_PDL=1 in the environment or this call turns it on. */
 int tribe_set_pdl(int32_t on);
+/* cudaPeekAtLastError() of the calling thread's context (debugging aid: TRIBE_DEBUG_LASTERR=1 makes the Python layer
+ * check it after every call, naming the first entry point after which the runtime's error state is set). */
+int tribe_peek_last_error(void);
+/* cudaGetLastError(): returns AND clears the runtime's non-sticky last-error slot.  Every entry point of this library
+ * consumes the error of its own launches; a value found here was left behind by some other user of the runtime, and
+ * torch would attribute it to whatever call it checks next (seen once in ~10 runs of the test suite as "invalid
+ * argument" at an unrelated .item()).  The Python layer drains it before its own synchronisation points. */
+int tribe_take_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * tcgen05 / TMEM / TMA GEMM:  D[z] = epilogue( alpha * A[z] (M x K) * B[z]^T (N x K) )
@@ -352,9 +360,11 @@ typedef struct TribeShardedAdam {
   int32_t world, rank, bcast_master, max_blocks;
 } TribeShardedAdam;
 int tribe_sharded_adam_step(const TribeShardedAdam* a, void* stream);
-/* Copy-engine transfer dst <- src (device pointers of this process: local memory or peer-mapped symmetric memory).  The
- * data-parallel step PUSHES each finished gradient bucket's slices into their owners' staging buffers with it while the
- * backward pass keeps every SM (grad_peer[] of tribe_sharded_adam_step then points at the LOCAL staged copies). */
+/* Copy-engine transfer dst <- src (pointers of this process's unified address space: local device memory, peer-mapped
+ * symmetric memory, or PINNED host memory — cudaMemcpyDefault).  The data-parallel step PUSHES each finished gradient
+ * bucket's slices into their owners' staging buffers with it while the backward pass keeps every SM (grad_peer[] of
+ * tribe_sharded_adam_step then points at the LOCAL staged copies); the subject-range flag of SubjectLayers
+ * (common.py:53-55) travels to its pinned host word with it, also as a memcpy node of a captured step. */
 int tribe_memcpy_async(void* dst, const void* src, int64_t n_bytes, void* stream);
 /* Micro-benchmark of the pieces of the kernel above (tools/xgpu_probe.py; not used by the product path): mode 0 =
  * multimem.ld_reduce only, 1 = peer loads only, 2 = local param/m/v stream only, 3 = multimem.st only, 4 = ld_reduce x4. */

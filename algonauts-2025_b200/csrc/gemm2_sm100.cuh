@@ -109,7 +109,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
     prefetch_tmap(&p.tmb);
     if (p.tma_store) {
       prefetch_tmap(&p.tmd);
-      if (p.epilogue == TRIBE_EPI_GELU) prefetch_tmap(&p.tmaux);
+      if (p.epilogue == TRIBE_EPI_GELU && p.aux_out) prefetch_tmap(&p.tmaux);
     }
   }
   if (warp == 1) {
@@ -233,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
     //   anything else (ragged last chunk, transposed / batched outputs) -> generic row-per-thread epilogue
     const bool path_f32 = EPI == kEpiF32 && p.vec_ok && !p.bias_gathered;  // (host: fp32 row-major D, STORE / RESIDUAL)
     const bool path_tma = EPI == kEpiGeneric && p.tma_store != 0;
-    const bool gelu = p.epilogue == TRIBE_EPI_GELU;
+    const bool gelu = p.epilogue == TRIBE_EPI_GELU && p.aux_out != nullptr;  // second TMA-store tile only when the pre-activation is wanted
     bool store_pending = false;  // lane 0: a bulk store may still be reading this warp's staging tile
     auto finish_chunk = [&](float (&v)[32], int row, bool row_ok, int col0, long long zoff, const float* bias, int res_row, int pos,
                             const uint4* pre_aux) {

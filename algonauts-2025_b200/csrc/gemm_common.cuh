@@ -235,7 +235,7 @@ __device__ __forceinline__ void epilogue_math(const GemmKParams& p, float (&v)[3
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
         aux_pack[j >> 3] = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
-    } else if (row_ok) {
+    } else if (row_ok && p.aux_out) {  // (aux_out == NULL: inference, nobody will read the pre-activation)
       __nv_bfloat16* ap = p.aux_out + static_cast<long long>(row) * p.ld_aux + col0;
       if (full) {
 #pragma unroll

@@ -515,7 +515,6 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
     if (!g->rope || g->rope_t <= 0 || g->head_dim % 32 || g->rope_dim % 32 || g->rope_dim > g->head_dim)
       return set_error(TRIBE_EINVAL, "gemm: rope epilogue needs a table and head_dim/rope_dim multiples of 32");
   }
-  if (g->epilogue == TRIBE_EPI_GELU && !g->aux_out) return set_error(TRIBE_EINVAL, "gemm: GELU epilogue needs aux_out");
   if (g->epilogue == TRIBE_EPI_GELU_BWD && !g->aux_in) return set_error(TRIBE_EINVAL, "gemm: GELU_BWD epilogue needs aux_in");
   if (g->epilogue == TRIBE_EPI_RESIDUAL && !g->res) return set_error(TRIBE_EINVAL, "gemm: RESIDUAL epilogue needs res");
 
@@ -592,7 +591,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   if (allow_tma_store && use2 && vec && !g->d_f32 && !g->d_transposed && g->batch == 1 && !g->adam_p && g->ldd % 8 == 0) {
     rc = encode_out_bf16(g->d, g->n, g->m, g->ldd, &kp.tmd);
     if (rc) return rc;
-    if (g->epilogue == TRIBE_EPI_GELU) {
+    if (g->epilogue == TRIBE_EPI_GELU && g->aux_out) {
       rc = encode_out_bf16(g->aux_out, g->n, g->m, g->ld_aux, &kp.tmaux);
       if (rc) return rc;
     }

@@ -426,7 +426,7 @@ class Engine:
             # ---- feed-forward sub-layer
             ops.scalenorm_fwd(ws.xs[iff], self._p(f"{f}.0.0.g"), ws.xn[iff], ws.rn[iff], self.norm_mult, self.norm_eps)
             ops.gemm(ops.kmajor(ws.xn[iff]), ops.kmajor(self._w16(f"{f}.1.ff.0.0.weight")), ws.hact[l], M, F, H, ldd=F,
-                     bias=self._p(f"{f}.1.ff.0.0.bias"), epilogue=ops.EPI_GELU, aux_out=ws.hpre[l], ld_aux=F)
+                     bias=self._p(f"{f}.1.ff.0.0.bias"), epilogue=ops.EPI_GELU, aux_out=ws.hpre[l] if plan.keep else None, ld_aux=F)  # pre-activation only for a backward
             ops.gemm(ops.kmajor(ws.hact[l]), ops.kmajor(self._w16(f"{f}.1.ff.2.weight")), ws.xs[iff + 1], M, H, F, ldd=H,
                      bias=self._p(f"{f}.1.ff.2.bias"), epilogue=ops.EPI_RESIDUAL, res=ws.xs[iff], ld_res=H,
                      rscale=self._p(f"{f}.2.residual_scale"))

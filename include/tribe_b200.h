@@ -82,7 +82,8 @@ typedef struct TribeOperand {
 
 enum TribeEpilogue {
   TRIBE_EPI_STORE = 0,     /* D = alpha*acc (+bias)                                                     */
-  TRIBE_EPI_GELU = 1,      /* aux_out = bf16(acc+bias); D = gelu_erf(acc+bias)        (FF up-projection) */
+  TRIBE_EPI_GELU = 1,      /* aux_out = bf16(acc+bias) (skipped when aux_out == NULL: inference);
+                              D = gelu_erf(acc+bias)                                   (FF up-projection) */
   TRIBE_EPI_RESIDUAL = 2,  /* D = acc (+bias) + res[row % res_row_mod] * (rscale ? rscale[col] : 1)      */
   TRIBE_EPI_GELU_BWD = 3,  /* D = acc * gelu_erf'(aux_in)                                                */
   TRIBE_EPI_ROPE = 4       /* D = rotate(acc): interleaved-pair rotary on the first rope_dim dims of every

@@ -96,6 +96,43 @@ def test_gemm_epilogues_bias_gelu_residual():
     assert float(wide[:, :n].abs().max()) == 0.0 and float(wide[:, 2 * n:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("m,n", [(1280, 768), (1100, 520)])
+def test_gemm_2cta_staged_epilogues(m, n):
+    """The 2-CTA kernel's round-2 epilogues — bf16 outputs through the shared-memory tile + TMA store (plain, GELU with and
+    without its pre-activation side output, GELU'), fp32 outputs through the transposed coalesced path (bias, periodic
+    residual rows x column scale, in-place accumulation) — on full tiles and on ragged rows / a ragged last chunk."""
+    torch.manual_seed(m + n)
+    k, T = 320, 100
+    A, W = bf(torch.randn(m, k, device=DEV)), bf(torch.randn(n, k, device=DEV) / 16)
+    bias = torch.randn(n, device=DEV)
+    acc = A.float() @ W.float().t() + bias
+    out, aux = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16), torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear(A, W, out, bias=bias, epilogue=ops.EPI_GELU, aux_out=aux, ld_aux=n)
+    assert_close_bf16(aux, acc)
+    assert_close_bf16(out, torch.nn.functional.gelu(acc))
+    out_inf = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear(A, W, out_inf, bias=bias, epilogue=ops.EPI_GELU)  # inference: no pre-activation output
+    assert torch.equal(out_inf, out)
+    hpre = bf(torch.randn(m, n, device=DEV))
+    out_b = torch.full((m, n), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear(A, W, out_b, epilogue=ops.EPI_GELU_BWD, aux_in=hpre, ld_aux=n)
+    h = hpre.float().requires_grad_(True)
+    torch.nn.functional.gelu(h).sum().backward()
+    assert_close_bf16(out_b, (A.float() @ W.float().t()) * h.grad)
+    res, rs = torch.randn(T, n, device=DEV), torch.rand(n, device=DEV) + 0.5
+    out_r = torch.full((m, n), float("nan"), device=DEV)
+    ops.linear(A, W, out_r, bias=bias, epilogue=ops.EPI_RESIDUAL, res=res, ld_res=n, res_row_mod=T, rscale=rs)
+    assert_close_bf16(out_r, acc + res[torch.arange(m, device=DEV) % T] * rs)
+    g0 = torch.randn(m, n, device=DEV)
+    g = g0.clone()
+    ops.linear(A, W, g, epilogue=ops.EPI_RESIDUAL, res=g, ld_res=n, res_batched=True)  # D += acc (second-pass gradient accumulation)
+    assert_close_bf16(g - g0, A.float() @ W.float().t())
+    wide = torch.zeros(m, 2 * n + 8, device=DEV, dtype=torch.bfloat16)
+    ops.linear(A, W, wide, ldd=2 * n + 8, d_off=8, bias=bias)  # column block of a wider bf16 buffer (TMA store with an offset base)
+    assert_close_bf16(wide[:, 8:8 + n], acc)
+    assert float(wide[:, :8].abs().max()) == 0.0 and float(wide[:, 8 + n:].abs().max()) == 0.0
+
+
 def _rope_table(T, rot_dim):
     inv = 1.0 / (10000 ** (torch.arange(0, rot_dim, 2).float() / rot_dim))
     ang = torch.arange(T).float()[:, None] * inv[None, :]

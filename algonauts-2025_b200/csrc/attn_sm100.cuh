@@ -11,10 +11,11 @@
 //   mode 0 (forward):   out = P  = softmax(scale * A B^T)            A = q rows, B = k rows (both K-major over head dims)
 //   mode 1 (backward):  out = dS = P o (A B^T - rowsum(A B^T o P)) * scale      A = dO rows, B = v rows, P read back (bf16)
 //
-// One persistent CTA per SM, 192 threads: warp 0 = TMA producer (3-stage ring; A box 64 x 128, B as one or two
+// One persistent CTA per SM, 320 threads: warp 0 = TMA producer (3-stage ring; A box 64 x 128, B as one or two
 // 64 x 160 boxes — key rows >= T are zero-filled by TMA), warp 1 = one thread issuing tcgen05.mma 128 x 160 x 16 per B
-// part into TMEM columns [0,160) / [160,320), warps 2..5 = epilogue, one thread per query row, three (mode 0) or two
-// (mode 1) sweeps over the row's TMEM columns.  The accumulator is single-buffered (2 x 320 columns do not fit), so MMA
+// part into TMEM columns [0,160) / [160,320), warps 2..9 = epilogue, TWO threads per query row (each owns half of the
+// row's columns; maxima / sums / dot products meet in a 2 KB exchange area), three (mode 0) or two (mode 1) sweeps over
+// the row's TMEM columns.  (Round 1 ran four epilogue warps: forward 57 -> 46 us with eight.)  The accumulator is single-buffered (2 x 320 columns do not fit), so MMA
 // and epilogue of one CTA alternate while the producer already streams the next tile's operands.
 
 namespace tribe {
@@ -24,7 +25,8 @@ constexpr int kAttnAB = BM * BK * 2;                  // 16 KiB
 constexpr int kAttnBB = kAttnNP * BK * 2;             // 20 KiB per part
 constexpr int kAttnStage = kAttnAB + 2 * kAttnBB;     // 56 KiB
 constexpr int kAttnStages = 3;
-constexpr int kAttnSmem = kAttnStages * kAttnStage + 256 + 1024;
+constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kAttnSmem = kAttnStages * kAttnStage + 256 + 2048 + 1024;
 
 struct alignas(64) AttnKParams {
   CUtensorMap tma, tmb;
@@ -45,7 +47,7 @@ __device__ __forceinline__ uint4 attn_pack8(const float* v) {
   return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __grid_constant__ AttnKParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kAttnStages * kAttnStage);
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
   uint64_t* tfull_bar = empty_bar + kAttnStages;
   uint64_t* tempty_bar = tfull_bar + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // 2 x (2 halves x 128 rows) floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(tfull_bar, 1);
-      mbar_init(tempty_bar, 128);
+      mbar_init(tempty_bar, 256);
       fence_mbar_init();
     }
     __syncwarp();
@@ -140,40 +143,50 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
     }
     __syncwarp();
   } else {
+    // Eight epilogue warps: two per TMEM lane quarter, each thread owns HALF of its query row's score columns, so two
+    // warps per scheduler overlap each other's TMEM-load latencies; row maxima / sums / dot products are combined through
+    // a 2 KB exchange area (one named barrier per exchange).
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = q * 32 + lane;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int nchunks = p.n_parts * (kAttnNP / 32);
+    const int c_mid = (nchunks + 1) >> 1;
+    const int c_lo = half ? c_mid : 0, c_hi = half ? nchunks : c_mid;  // this thread's 32-column chunks
     const float sl2 = p.scale * 1.4426950408889634f;  // exp(scale * x) = exp2(sl2 * x)
+    float* xch_a = xch, *xch_b = xch + 256;
+    auto epi_sync = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+    auto exchange = [&](float* area, float mine) {  // returns the partner thread's value
+      area[half * 128 + row_in_tile] = mine;
+      epi_sync();
+      return area[(half ^ 1) * 128 + row_in_tile];
+    };
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int tile_parity = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_parity ^= 1) {
       const int z = tile / p.m_blocks, mb = tile - z * p.m_blocks;
       const int row = mb * BM + row_in_tile;
       const bool row_ok = row < p.T;
       const long long roff = (static_cast<long long>(z) * p.T + row) * p.Tp;
       mbar_wait(tfull_bar, acc_phase);
       tc_fence_after();
-      // One thread owns one query row.  Only four epilogue warps run per SM (one per scheduler), so nothing hides
-      // latencies for them: TMEM is read in groups of up to four 32-column chunks per tcgen05.wait::ld (the wait covers all
-      // loads in flight), every reduction runs as four independent dependency chains, and the backward prefetches its
-      // P row one group ahead.
-      constexpr int G = 4;
+      constexpr int G = 2;  // (320 threads: 168 registers each — two 32-column chunks in flight per thread)
       uint32_t rg[G][32];
-      const int ngroups = (nchunks + G - 1) / G;
-      auto load_group = [&](int g) {
+      auto load_group = [&](int cb) {  // chunks cb .. cb+G-1 of this thread's range
 #pragma unroll
         for (int i = 0; i < G; ++i)
-          if (g * G + i < nchunks) tmem_ld_32x32(t_addr + (g * G + i) * 32, rg[i]);
+          if (cb + i < c_hi) tmem_ld_32x32(t_addr + (cb + i) * 32, rg[i]);
         tmem_ld_wait();
       };
       if (p.mode == 0) {
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int g = 0; g < ngroups; ++g) {
-          if (g * G * 32 >= p.T) break;
-          load_group(g);
+        for (int cb = c_lo; cb < c_hi; cb += G) {
+          if (cb * 32 >= p.T) break;
+          load_group(cb);
 #pragma unroll
           for (int i = 0; i < G; ++i) {
-            const int col0 = (g * G + i) * 32;
+            const int col0 = (cb + i) * 32;
+            if (cb + i >= c_hi) continue;
             if (col0 + 32 <= p.T) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rg[i][j]));
@@ -184,15 +197,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
             }
           }
         }
-        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        m = fmaxf(m, exchange(xch_a, m));
         const float msl = m * sl2;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int g = 0; g < ngroups; ++g) {
-          if (g * G * 32 >= p.T) break;
-          load_group(g);
+        for (int cb = c_lo; cb < c_hi; cb += G) {
+          if (cb * 32 >= p.T) break;
+          load_group(cb);
 #pragma unroll
           for (int i = 0; i < G; ++i) {
-            const int col0 = (g * G + i) * 32;
+            const int col0 = (cb + i) * 32;
+            if (cb + i >= c_hi) continue;
             if (col0 + 32 <= p.T) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
@@ -203,14 +218,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
             }
           }
         }
-        const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-        for (int g = 0; g < ngroups; ++g) {
-          if (g * G * 32 >= p.Tp) break;
-          load_group(g);
+        const float mine = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        const float other = exchange(xch_b, mine);
+        const float inv = 1.0f / (half ? other + mine : mine + other);  // the same operand order in both threads of a row
+        for (int cb = c_lo; cb < c_hi; cb += G) {
+          if (cb * 32 >= p.Tp) break;
+          load_group(cb);
 #pragma unroll
           for (int i = 0; i < G; ++i) {
-            const int col0 = (g * G + i) * 32;
-            if (col0 < p.Tp && g * G + i < nchunks) {
+            const int col0 = (cb + i) * 32;
+            if (col0 < p.Tp && cb + i < c_hi) {
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
@@ -225,23 +242,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
       } else {
         const __nv_bfloat16* pr = p.p_in + roff;
         uint4 pu[G][4];
-        auto load_p = [&](int g) {
+        auto load_p = [&](int cb) {
 #pragma unroll
           for (int i = 0; i < G; ++i)
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
-              const int col = (g * G + i) * 32 + g8 * 8;
-              pu[i][g8] = (row_ok && col < p.Tp) ? __ldg(reinterpret_cast<const uint4*>(pr + col)) : make_uint4(0u, 0u, 0u, 0u);
+              const int col = (cb + i) * 32 + g8 * 8;
+              pu[i][g8] = (row_ok && cb + i < c_hi && col < p.Tp) ? __ldg(reinterpret_cast<const uint4*>(pr + col)) : make_uint4(0u, 0u, 0u, 0u);
             }
         };
         float d4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int g = 0; g < ngroups; ++g) {
-          if (g * G * 32 >= p.T) break;
-          load_p(g);  // global loads and TMEM loads of the group are in flight together
-          load_group(g);
+        for (int cb = c_lo; cb < c_hi; cb += G) {
+          if (cb * 32 >= p.T) break;
+          load_p(cb);  // global loads and TMEM loads of the group are in flight together
+          load_group(cb);
 #pragma unroll
           for (int i = 0; i < G; ++i) {
-            if (g * G + i < nchunks) {
+            if (cb + i < c_hi) {
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8) {  // padding columns of P are zero: they add nothing
                 const float2 a = unpack_bf16x2(pu[i][g8].x), b2 = unpack_bf16x2(pu[i][g8].y), c2 = unpack_bf16x2(pu[i][g8].z),
@@ -255,18 +272,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_scores_kernel(const __gr
             }
           }
         }
-        const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-        for (int g = 0; g < ngroups; ++g) {
-          if (g * G * 32 >= p.Tp) break;
-          load_p(g);  // second sweep: the row is L1/L2-resident now
-          load_group(g);
+        const float mine = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        const float other = exchange(tile_parity ? xch_b : xch_a, mine);  // one exchange per tile: alternate the area
+        const float dot = half ? other + mine : mine + other;
+        for (int cb = c_lo; cb < c_hi; cb += G) {
+          if (cb * 32 >= p.Tp) break;
+          load_p(cb);  // second sweep: the row is L1/L2-resident now
+          load_group(cb);
           if (row_ok) {
 #pragma unroll
             for (int i = 0; i < G; ++i) {
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8) {
-                const int col = (g * G + i) * 32 + g8 * 8;
-                if (col < p.Tp && g * G + i < nchunks) {
+                const int col = (cb + i) * 32 + g8 * 8;
+                if (col < p.Tp && cb + i < c_hi) {
                   const float2 a = unpack_bf16x2(pu[i][g8].x), b2 = unpack_bf16x2(pu[i][g8].y), c2 = unpack_bf16x2(pu[i][g8].z),
                                e2 = unpack_bf16x2(pu[i][g8].w);
                   const float pv[8] = {a.x, a.y, b2.x, b2.y, c2.x, c2.y, e2.x, e2.y};
@@ -606,7 +625,7 @@ extern "C" int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, con
   }
   const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
   {
-    cudaError_t le = launch_k(attn_scores_kernel, dim3(grid), dim3(kGemmThreads), kAttnSmem, reinterpret_cast<cudaStream_t>(stream), kp);
+    cudaError_t le = launch_k(attn_scores_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, reinterpret_cast<cudaStream_t>(stream), kp);
     if (le != cudaSuccess) return set_cuda_error(le, "attn_scores launch");
   }
   count_launch();

@@ -55,7 +55,7 @@ def test_fused_attention_rejects_unsupported_shapes():
 def test_flash_style_forward_matches_scores_then_pv(Bsz, T, heads, dh, keep_p):
     """tribe_attn_fwd: softmax(q k^T d^-1/2) v in ONE launch (S in TMEM, P as the shared-memory A operand of P.V) against
     (a) plain torch fp32 attention on the same bf16 operands and (b) the two-launch path it replaces (tribe_attn_scores +
-    batched P.V GEMM): the P it optionally stores is bit-identical to the scores kernel's, O agrees to bf16 rounding."""
+    batched P.V GEMM): the P it optionally stores equals the scores kernel's up to one bf16 rounding step, O agrees to bf16 rounding."""
     torch.manual_seed(T + dh)
     H = heads * dh
     Tp = (T + 7) // 8 * 8
@@ -80,7 +80,10 @@ def test_flash_style_forward_matches_scores_then_pv(Bsz, T, heads, dh, keep_p):
                        zin_stride=dh, zdiv=heads)
     ops.gemm(p_op, v_op, out2, T, dh, Tp, ldd=H, batch=Bsz * heads, z_inner=heads, d_zo=T * H, d_zi=dh)
     if keep_p:
-        assert torch.equal(P, P2)
+        # same exponentials; the row sum is formed as one chain here and as two half-row partial sums by the eight-warp
+        # scores kernel, so single elements may differ by one bf16 rounding step
+        assert float((P.float() - P2.float()).abs().max()) <= 2 ** -8 * float(P2.float().max())
+        assert float((P != P2).float().mean()) < 0.05
     assert float((got - out2.float()).abs().max()) <= 8e-3 * float(ref.abs().max())
 
 

@@ -26,10 +26,13 @@ constexpr int kAttnBB = kAttnNP * BK * 2;             // 20 KiB per part
 constexpr int kAttnStage = kAttnAB + 2 * kAttnBB;     // 56 KiB
 constexpr int kAttnStages = 3;
 constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int kAttnSmem = kAttnStages * kAttnStage + 256 + 2048 + 1024;
+constexpr int kAttnEpiStage = 8 * 2 * 2048;  // per epilogue warp: two 32 x 32 bf16 TMA-store tiles (SWIZZLE_64B)
+constexpr int kAttnSmem = kAttnStages * kAttnStage + 3072 + kAttnEpiStage + 1024;  // 3072: barriers (256) + exchange area (2048), padded
 
 struct alignas(64) AttnKParams {
   CUtensorMap tma, tmb;
+  CUtensorMap tmo;  // 3-D store map of out: (Tp columns, T rows, batch x heads), box 32 x 32, SWIZZLE_64B
+  int tma_store;
   int T, Tp, heads, dh, n_parts, num_kb, m_blocks, num_tiles;
   int a_off, b_off;
   float scale;
@@ -41,6 +44,14 @@ struct alignas(64) AttnKParams {
 
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// 2^x as ONE MUFU.EX2 (exp2f() wraps it in a range test and two conditional multiplies to produce denormal results: four
+// instructions per score, twice per score in the forward epilogue).  Probabilities below 2^-126 become exact zeros.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ uint4 attn_pack8(const float* v) {
@@ -56,6 +67,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
   uint64_t* tempty_bar = tfull_bar + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 1);
   float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // 2 x (2 halves x 128 rows) floats
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(full_bar) + 3072;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -63,6 +75,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma);
     prefetch_tmap(&p.tmb);
+    if (p.tma_store) prefetch_tmap(&p.tmo);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -161,6 +174,26 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
       epi_sync();
       return area[(half ^ 1) * 128 + row_in_tile];
     };
+    // Output chunks (the warp's 32 rows x 32 columns) leave through a TMA store from a per-warp staging tile: the
+    // row-per-thread 16-byte stores they replace touched 32 different lines per warp instruction (4864 of them per tile).
+    uint8_t* my_stage = epi_stage + (warp - 2) * 4096;
+    int stage_buf = 0;
+    auto store_chunk = [&](const float* v, int col0, int row0, int z) {  // warp-uniform arguments except v
+      uint4 pk[4];
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) pk[g8] = attn_pack8(v + g8 * 8);
+      uint8_t* sbuf = my_stage + stage_buf * 2048;
+      if (lane == 0) tma_store_wait_read1();  // the store issued from this buffer two chunks ago has read it
+      __syncwarp();
+      stage_write_bf16_sw64(sbuf, lane, pk);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && row0 < p.T) {
+        tma_store_3d(&p.tmo, sbuf, col0, row0, z);  // rows >= T and columns >= Tp are clipped by the hardware
+        tma_store_commit();
+      }
+      stage_buf ^= 1;
+    };
     uint32_t acc_phase = 0;
     int tile_parity = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, tile_parity ^= 1) {
@@ -168,6 +201,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
       const int row = mb * BM + row_in_tile;
       const bool row_ok = row < p.T;
       const long long roff = (static_cast<long long>(z) * p.T + row) * p.Tp;
+      if (p.mode == 1 && row_ok) {
+        // backward: this thread's half row of P (written by the forward pass long ago: HBM) is requested into L2 now, while
+        // the tile's MMAs run — the two sweeps below then wait for L2 hits instead of three DRAM round trips each
+        // (ncu: 39 % of the kernel's stall samples sat on these loads)
+        const int pc0 = c_lo * 32, pc1 = min(c_hi * 32, p.Tp);
+        if (pc1 > pc0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.p_in + roff + pc0), "r"((pc1 - pc0) * 2) : "memory");
+      }
       mbar_wait(tfull_bar, acc_phase);
       tc_fence_after();
       constexpr int G = 2;  // (320 threads: 168 registers each — two 32-column chunks in flight per thread)
@@ -210,11 +251,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
             if (cb + i >= c_hi) continue;
             if (col0 + 32 <= p.T) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+              for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
             } else if (col0 < p.T) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.T) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+                if (col0 + j < p.T) s4[j & 3] += ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
             }
           }
         }
@@ -230,8 +271,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
             if (col0 < p.Tp && cb + i < c_hi) {
               float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
-              if (row_ok) {
+              for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
+              if (p.tma_store) {
+                store_chunk(v, col0, mb * BM + q * 32, z);
+              } else if (row_ok) {
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8)
                   if (col0 + g8 * 8 < p.Tp) *reinterpret_cast<uint4*>(p.out + roff + col0 + g8 * 8) = attn_pack8(v + g8 * 8);
@@ -279,7 +322,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
           if (cb * 32 >= p.Tp) break;
           load_p(cb);  // second sweep: the row is L1/L2-resident now
           load_group(cb);
-          if (row_ok) {
+          if (p.tma_store) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+              const int col0 = (cb + i) * 32;
+              if (col0 < p.Tp && cb + i < c_hi) {  // warp-uniform
+                float v[32];
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {  // rows >= T / columns >= Tp were loaded as zeros (and are clipped anyway)
+                  const float2 a = unpack_bf16x2(pu[i][g8].x), b2 = unpack_bf16x2(pu[i][g8].y), c2 = unpack_bf16x2(pu[i][g8].z),
+                               e2 = unpack_bf16x2(pu[i][g8].w);
+                  const float pv[8] = {a.x, a.y, b2.x, b2.y, c2.x, c2.y, e2.x, e2.y};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[g8 * 8 + j] = pv[j] * (__uint_as_float(rg[i][g8 * 8 + j]) - dot) * p.scale;
+                }
+                store_chunk(v, col0, mb * BM + q * 32, z);
+              }
+            }
+          } else if (row_ok) {
 #pragma unroll
             for (int i = 0; i < G; ++i) {
 #pragma unroll
@@ -303,6 +363,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
       mbar_arrive(tempty_bar);
       acc_phase ^= 1;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // bulk stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -523,7 +584,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_fwd_kernel(const __grid_
           const int col0 = (g * G + i) * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.T) s4[j & 3] += exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+            if (col0 + j < p.T) s4[j & 3] += ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
         }
       }
       const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
@@ -535,7 +596,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) attn_fwd_kernel(const __grid_
           const int col0 = (g * G + i) * 32;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? exp2f(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
           uint8_t* kb_row = p_row + (col0 >> 6) * (BM * BK * 2);
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
@@ -617,6 +678,15 @@ extern "C" int tribe_attn_scores(const void* a, int64_t a_ld, int64_t a_off, con
   kp.p_in = reinterpret_cast<const __nv_bfloat16*>(p_in);
   kp.out = reinterpret_cast<__nv_bfloat16*>(out);
   kp.k_lbo = 16, kp.k_sbo = 1024;
+  static const int allow_tma_store = [] {  // TRIBE_TMA_STORE=0: row-per-thread 16-byte stores (the round-1 epilogue)
+    const char* e = getenv("TRIBE_TMA_STORE");
+    return e ? atoi(e) : 1;
+  }();
+  if (allow_tma_store) {
+    rc = encode_out_bf16_3d(out, Tp, T, n_batch * heads, Tp, T * Tp, &kp.tmo);
+    if (rc) return rc;
+    kp.tma_store = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);

@@ -35,6 +35,7 @@
 
 #include "gemm_common.cuh"
 #include "gemm2_sm100.cuh"
+#include "gemm_mt_sm100.cuh"
 
 namespace tribe {
 
@@ -386,6 +387,23 @@ static int encode_out_bf16(const void* ptr, int64_t cols, int64_t rows, int64_t 
   return TRIBE_OK;
 }
 
+// 3-D bf16 output map of the batched multi-row-tile kernel: (columns, rows of one outer batch, outer batch); rows >= m are
+// clipped by the store.  Same 32 x 32 SWIZZLE_64B box as the 2-D map above.
+static int encode_out_bf16_3d(const void* ptr, int64_t cols, int64_t rows, int64_t zo, int64_t ld, int64_t zo_stride, CUtensorMap* out) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(TRIBE_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(zo)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(zo > 1 ? zo_stride : ld * rows) * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  alignas(64) CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TRIBE_ETMAP, "cuTensorMapEncodeTiled failed for the batched output map");
+  *out = tm;
+  return TRIBE_OK;
+}
+
 static std::atomic<int> g_sm_limit{0};  // tribe_gemm_set_sm_limit: 0 = all SMs
 
 static int device_sms() {
@@ -450,6 +468,31 @@ static int launch_gemm2(const GemmKParams& kp, int grid, cudaStream_t stream) {
   return TRIBE_OK;
 }
 
+template <int MT, bool A_MN, bool B_MN>
+static int launch_gemm_mt(const GemmKParams& kp, int grid, cudaStream_t stream) {
+  using Cfg = GemmMtCfg<MT>;
+  static bool attr_set = false;
+  auto kern = gemm_mt_bf16_kernel<MT, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_mt)");
+    attr_set = true;
+  }
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(kMtThreads), Cfg::SMEM_BYTES, stream, kp);
+  count_launch();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "gemm_mt launch");
+  return TRIBE_OK;
+}
+
+template <int MT>
+static int dispatch_major_mt(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_gemm_mt<MT, false, false>(kp, grid, s);
+  if (a_mn && !b_mn) return launch_gemm_mt<MT, true, false>(kp, grid, s);
+  if (!a_mn && b_mn) return launch_gemm_mt<MT, false, true>(kp, grid, s);
+  return launch_gemm_mt<MT, true, true>(kp, grid, s);
+}
+
 template <int BN, int EPI>
 static int dispatch_major2e(const GemmKParams& kp, int grid, bool a_mn, bool b_mn, cudaStream_t s) {
   if (!a_mn && !b_mn) return launch_gemm2<BN, false, false, EPI>(kp, grid, s);
@@ -510,6 +553,16 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   const bool small = allow_small && g->block_n == 0 && !g->kgroup && (g->k + BK - 1) / BK <= 8 && (g->n % 128 == 0 || g->n <= 128) &&
                      static_cast<int64_t>(g->batch) * ((g->m + BM - 1) / BM) * ((g->n + 127) / 128) >= 2 * num_sms();
   if (small) bn = 128;
+  // batched short-K problems with 2-3 row tiles and N a multiple of 128 (attention P.V, dV, dQ, dK): B-stationary units of
+  // all row tiles x 128 columns (gemm_mt_sm100.cuh): a third less L2 -> SM traffic, half the work units.  TRIBE_GEMM_MT=0: off.
+  static const int allow_mt = [] {
+    const char* e = getenv("TRIBE_GEMM_MT");
+    return e ? atoi(e) : 1;
+  }();
+  const int m_tiles = (g->m + BM - 1) / BM;
+  const bool use_mt = allow_mt && !small && g->block_n == 0 && !g->kgroup && !g->adam_p && g->batch >= 2 && (m_tiles == 2 || m_tiles == 3) &&
+                      (g->k + BK - 1) / BK <= 8 && g->n % 128 == 0;
+  if (use_mt) bn = 128;
   if (bn != 128 && bn != 160 && bn != 192 && bn != 256) return set_error(TRIBE_EINVAL, "gemm: block_n must be 128/160/192/256");
   if (g->epilogue == TRIBE_EPI_ROPE) {
     if (!g->rope || g->rope_t <= 0 || g->head_dim % 32 || g->rope_dim % 32 || g->rope_dim > g->head_dim)
@@ -526,7 +579,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
     const char* e = getenv("TRIBE_GEMM_2CTA");
     return e ? atoi(e) : 1;
   }();
-  bool use2 = allow_2cta && bn == 256 && !g->kgroup && g->m >= 1024 && (num_sms() % 2 == 0);
+  bool use2 = allow_2cta && !use_mt && bn == 256 && !g->kgroup && g->m >= 1024 && (num_sms() % 2 == 0);
   if (use2 && g->adam_p && !(a_mn && b_mn)) use2 = false;  // only the wgrad form (both operands MN-major) has a 2-CTA Adam instance
   int rc = encode_operand(g->a, a_mn ? BK : BM, &kp.tma);
   if (rc) return rc;
@@ -550,7 +603,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   kp.rope_cols = g->rope_cols, kp.rope_sign = g->rope_sign;
   kp.k_lbo = k_lbo ? k_lbo : 16, kp.k_sbo = k_sbo ? k_sbo : 1024;
   kp.mn_lbo = mn_lbo ? mn_lbo : BK * 128, kp.mn_sbo = mn_sbo ? mn_sbo : 1024;
-  const int bm = use2 ? BM2 : BM;
+  const int bm = use2 ? BM2 : (use_mt ? m_tiles * BM : BM);
   kp.m_blocks = (g->m + bm - 1) / bm, kp.n_blocks = (g->n + bn - 1) / bn;
   kp.num_tiles = kp.m_blocks * kp.n_blocks * g->batch, kp.num_kb = (g->k + BK - 1) / BK;
   // Tile order: every wave of ~#SM tiles streams one operand completely and re-reads the other; re-read the smaller
@@ -597,6 +650,16 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
     }
     kp.tma_store = 1;
   }
+  if (allow_tma_store && use_mt && vec && !g->d_f32 && !g->d_transposed && g->ldd % 8 == 0) {
+    // D(zo, zi, row, col) = d + zo * d_zo + zi * d_zi + row * ldd + col: the inner batch index must be a column offset
+    const int zin = kp.z_inner, zout = g->batch / zin;
+    const int64_t cols = zin > 1 ? static_cast<int64_t>(zin - 1) * g->d_zi_stride + g->n : g->n;
+    if (g->batch % zin == 0 && cols <= g->ldd && (zin == 1 || g->d_zi_stride >= g->n) && (zout == 1 || g->d_zo_stride >= static_cast<int64_t>(g->m) * g->ldd)) {
+      rc = encode_out_bf16_3d(g->d, cols, g->m, zout, g->ldd, g->d_zo_stride, &kp.tmd);
+      if (rc) return rc;
+      kp.tma_store = 1;
+    }
+  }
 
   // ---- schedule: whole tiles round-robin; the ragged last wave is split along K when a workspace is provided
   const int workers_max = use2 ? num_sms() / 2 : (small ? 2 * num_sms() : num_sms());  // persistent CTAs, or CTA pairs
@@ -636,6 +699,7 @@ static int gemm_impl(const TribeGemm* g, void* stream, uint32_t k_lbo, uint32_t 
   }
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use_mt) return m_tiles == 3 ? dispatch_major_mt<3>(kp, grid, a_mn, b_mn, s) : dispatch_major_mt<2>(kp, grid, a_mn, b_mn, s);
   if (use2) return dispatch_major2<256>(kp, 2 * grid, a_mn, b_mn, s);
   if (small) return dispatch_major_small(kp, grid, a_mn, b_mn, s);
   switch (bn) {

@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
         float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         m = fmaxf(m, exchange(xch_a, m));
         const float msl = m * sl2;
+        // second sweep: e = 2^(sl2 * s - msl) is computed ONCE per score, summed, and written back over the score in TMEM
+        // (tcgen05.st; each thread re-reads only what it wrote) — the third sweep is then a multiply, not a second exp
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int cb = c_lo; cb < c_hi; cb += G) {
           if (cb * 32 >= p.T) break;
@@ -248,17 +250,26 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < G; ++i) {
             const int col0 = (cb + i) * 32;
-            if (cb + i >= c_hi) continue;
+            if (cb + i >= c_hi || col0 >= p.T) continue;  // (columns >= T hold exact zeros: their key rows were zero-filled)
             if (col0 + 32 <= p.T) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
-            } else if (col0 < p.T) {
+              for (int j = 0; j < 32; ++j) {
+                const float e = ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+                s4[j & 3] += e;
+                rg[i][j] = __float_as_uint(e);
+              }
+            } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.T) s4[j & 3] += ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl));
+              for (int j = 0; j < 32; ++j) {
+                const float e = (col0 + j < p.T) ? ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) : 0.f;
+                s4[j & 3] += e;
+                rg[i][j] = __float_as_uint(e);
+              }
             }
+            tmem_st_32x32(t_addr + (cb + i) * 32, rg[i]);
           }
         }
+        tmem_st_wait();
         const float mine = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         const float other = exchange(xch_b, mine);
         const float inv = 1.0f / (half ? other + mine : mine + other);  // the same operand order in both threads of a row
@@ -271,7 +282,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
             if (col0 < p.Tp && cb + i < c_hi) {
               float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.T) ? ex2_fast(fmaf(__uint_as_float(rg[i][j]), sl2, -msl)) * inv : 0.f;
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rg[i][j]) * inv;
               if (p.tma_store) {
                 store_chunk(v, col0, mb * BM + q * 32, z);
               } else if (row_ok) {

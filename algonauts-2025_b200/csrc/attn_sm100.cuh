@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
     uint8_t* my_stage = epi_stage + (warp - 2) * 4096;
     int stage_buf = 0;
     auto store_chunk = [&](const float* v, int col0, int row0, int z) {  // warp-uniform arguments except v
+      if (row0 >= p.T) return;  // the warp's 32 rows all lie past T: nothing to store (and no buffer is consumed)
       uint4 pk[4];
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) pk[g8] = attn_pack8(v + g8 * 8);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
       stage_write_bf16_sw64(sbuf, lane, pk);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0 && row0 < p.T) {
+      if (lane == 0) {
         tma_store_3d(&p.tmo, sbuf, col0, row0, z);  // rows >= T and columns >= Tp are clipped by the hardware
         tma_store_commit();
       }

@@ -211,22 +211,25 @@ __global__ void __launch_bounds__(kMtThreads, 1) gemm_mt_bf16_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
           if (p.tma_store && col0 + 32 <= p.n) {
-            epilogue_math<false>(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
-            uint4 pk[4];
+            const int row0 = t.m0 + i * BM + q * 32;  // first row of the warp's 32 (warp-uniform)
+            if (row0 < p.m) {                         // (a warp whose rows all lie past m stores nothing and consumes no buffer)
+              epilogue_math<false>(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
+              uint4 pk[4];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              pk[j >> 3] = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
-            uint8_t* sbuf = my_stage + stage_buf * 2048;
-            if (lane == 0) tma_store_wait_read1();  // the store issued from this buffer two chunks ago has read it
-            __syncwarp();
-            stage_write_bf16_sw64(sbuf, lane, pk);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0 && row_ok) {  // (a warp whose 32 rows all lie past m has nothing to store)
-              tma_store_3d(&p.tmd, sbuf, t.zi * static_cast<int>(p.d_zi) + col0, row, t.zo);  // lane 0's row = first row of the warp's 32
-              tma_store_commit();
+              for (int j = 0; j < 32; j += 8)
+                pk[j >> 3] = make_uint4(pack2(v[j], v[j + 1]), pack2(v[j + 2], v[j + 3]), pack2(v[j + 4], v[j + 5]), pack2(v[j + 6], v[j + 7]));
+              uint8_t* sbuf = my_stage + stage_buf * 2048;
+              if (lane == 0) tma_store_wait_read1();  // the store issued from this buffer two chunks ago has read it
+              __syncwarp();
+              stage_write_bf16_sw64(sbuf, lane, pk);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&p.tmd, sbuf, t.zi * static_cast<int>(p.d_zi) + col0, row0, t.zo);
+                tma_store_commit();
+              }
+              stage_buf ^= 1;
             }
-            stage_buf ^= 1;
           } else {
             epilogue_chunk<false>(p, v, row, row_ok, col0, zoff, bias, res_row, pos);
           }

@@ -142,6 +142,11 @@ typedef struct TribeGemm {
   int32_t adam_keep_grad;
 } TribeGemm;
 
+/* Kernel selection (all instances compute the same function): 2-CTA pairs (256 x 256 tiles) for large single problems;
+ * the 1-CTA kernel (128 x BN tiles) for grouped / small problems; batched problems with 2-3 row tiles, <= 8 k-blocks and
+ * n % 128 == 0 (the attention contractions P.V, dV, dQ, dK) run on the B-stationary multi-row-tile kernel
+ * (csrc/gemm_mt_sm100.cuh; results bit-identical to the 1-CTA kernel; a non-zero block_n or TRIBE_GEMM_MT=0 selects the
+ * 1-CTA kernel).  GELU / GELU_BWD evaluate Phi(x) from one exponential (|error| <= 5e-7 absolute). */
 int tribe_gemm_bf16(const TribeGemm* g, void* stream);
 
 /* Descriptor-probe variant used by tests only: overrides the UMMA shared-memory descriptor byte offsets

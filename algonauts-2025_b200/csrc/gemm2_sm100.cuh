@@ -234,6 +234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
     const bool path_f32 = EPI == kEpiF32 && p.vec_ok && !p.bias_gathered;  // (host: fp32 row-major D, STORE / RESIDUAL)
     const bool path_tma = EPI == kEpiGeneric && p.tma_store != 0;
     const bool gelu = p.epilogue == TRIBE_EPI_GELU && p.aux_out != nullptr;  // second TMA-store tile only when the pre-activation is wanted
+    const bool scaled = p.alpha != 1.0f;
     bool store_pending = false;  // lane 0: a bulk store may still be reading this warp's staging tile
     auto finish_chunk = [&](float (&v)[32], int row, bool row_ok, int col0, long long zoff, const float* bias, int res_row, int pos,
                             const uint4* pre_aux) {
@@ -331,8 +332,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
           tmem_ld_32x32(t_addr + c * 32, raw);
           tmem_ld_wait();
           float v[32];
+          if (scaled) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+          } else {  // alpha == 1 (every GEMM of the step but the scaled scores): 32 multiplies per chunk and thread saved
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          }
           finish_chunk(v, row, row_ok, col0, zoff, bias, res_row, pos, have ? ax_cur : nullptr);
 #pragma unroll
           for (int j = 0; j < 4; ++j) ax_cur[j] = ax_nxt[j];

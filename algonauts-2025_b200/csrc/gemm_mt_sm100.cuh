@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kMtThreads, 1) gemm_mt_bf16_kernel(const __gri
     // bf16 row-major outputs leave through TMA stores (3-D map: columns, rows of one outer batch, outer batch — rows past m
     // are clipped by the hardware): a row-per-thread 16-byte store touches 32 different lines per warp instruction, and
     // that store stream — not the MMAs, not the operand loads — was what a tile of these contractions took its time for.
+    const bool scaled = p.alpha != 1.0f;
     uint8_t* my_stage = epi_stage + (warp - 2) * 4096;
     int stage_buf = 0;
     int acc = 0;
@@ -208,8 +209,13 @@ __global__ void __launch_bounds__(kMtThreads, 1) gemm_mt_bf16_kernel(const __gri
           tmem_ld_32x32(t_addr + i * kMtBN + c * 32, raw);
           tmem_ld_wait();
           float v[32];
+          if (scaled) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          }
           if (p.tma_store && col0 + 32 <= p.n) {
             const int row0 = t.m0 + i * BM + q * 32;  // first row of the warp's 32 (warp-uniform)
             if (row0 < p.m) {                         // (a warp whose rows all lie past m stores nothing and consumes no buffer)

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, kAttnNP, false, false);
+      const bool two_parts = p.n_parts > 1;
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -134,14 +135,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_kernel(const __gr
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kAttnStage);
-          const uint32_t sb = sa + kAttnAB;
+          // one descriptor per operand and stage; k-steps and the second B part are constant increments of its 16-byte
+          // address field (the issuing thread must not spend longer on an MMA than the tensor core does: 80 cycles here)
+          const uint64_t da0 = make_smem_desc(sa, p.k_lbo, p.k_sbo);
+          const uint64_t db0 = make_smem_desc(sa + kAttnAB, p.k_lbo, p.k_sbo);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t da = make_smem_desc(sa + kk * 32, p.k_lbo, p.k_sbo);
-            for (int j = 0; j < p.n_parts; ++j) {
-              const uint64_t db = make_smem_desc(sb + j * kAttnBB + kk * 32, p.k_lbo, p.k_sbo);
-              umma_bf16(tmem_base + j * kAttnNP, da, db, idesc, accumulate);
-            }
+            umma_bf16(tmem_base, da0 + ((kk * 32) >> 4), db0 + ((kk * 32) >> 4), idesc, accumulate);
+            if (two_parts) umma_bf16(tmem_base + kAttnNP, da0 + ((kk * 32) >> 4), db0 + ((kAttnBB + kk * 32) >> 4), idesc, accumulate);
             accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);

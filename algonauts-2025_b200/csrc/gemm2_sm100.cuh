@@ -197,12 +197,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1) ge
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          // one descriptor per operand and stage; the four k-steps are constant increments of its 16-byte address field, so
+          // the issuing thread spends a handful of instructions per MMA (it shares its scheduler with two epilogue warps)
+          const uint64_t da0 = make_smem_desc(sa, a_lbo, a_sbo);
+          const uint64_t db0 = make_smem_desc(sa + Cfg::A_BYTES, b_lbo, b_sbo);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo);
-            const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo);
-            umma2_bf16(d_tmem, da, db, idesc, accumulate);
+            umma2_bf16(d_tmem, da0 + ((kk * a_kstep) >> 4), db0 + ((kk * b_kstep) >> 4), idesc, accumulate);
             accumulate = 1;
           }
           umma2_commit_mc(&empty_bar[stage], 0x3);  // both CTAs' smem slots are free once these MMAs have read them

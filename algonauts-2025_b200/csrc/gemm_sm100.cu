@@ -158,12 +158,11 @@ __global__ void __launch_bounds__(kGemmThreads, SMALL ? 2 : 1) gemm_bf16_kernel(
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t sb = sa + Cfg::A_BYTES;
+            const uint64_t da0 = make_smem_desc(sa, a_lbo, a_sbo);  // k-steps = constant increments of the address field
+            const uint64_t db0 = make_smem_desc(sa + Cfg::A_BYTES, b_lbo, b_sbo);
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, a_sbo);
-              const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, b_sbo);
-              umma_bf16(d_tmem, da, db, idesc, accumulate);
+              umma_bf16(d_tmem, da0 + ((kk * a_kstep) >> 4), db0 + ((kk * b_kstep) >> 4), idesc, accumulate);
               accumulate = 1;
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
